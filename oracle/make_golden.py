@@ -1,0 +1,186 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden            # all cases (a few minutes: the reference is
+    python -m oracle.make_golden bw_small   # pure-Python loops), or selected ones
+
+The reference has no tests, fixtures or golden vectors of its own, so
+these files are the parity pin: outputs of the reference's own functions
+(hmm_training, calculate_log_likelihood, get_observations, createCodeVector) on seeded
+synthetic inputs.  Inputs are stored alongside the outputs so the GPU box needs neither
+the reference nor this script.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from hmm_training_b200 import synthetic as S  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _train_ref(ref, obs_list, N, M, iters, eps=1e-6, init=None):
+    """Run the reference trainer; with ``init`` use its own warm-start route
+    (HMM/hmm_training.py:275-297) from a temp Data/ tree."""
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "HMM"))
+        kwargs = dict(load_initial_params=False)
+        if init is not None:
+            pi0, A0, B0 = init
+            d = os.path.join(tmp, "Data", "Eighty-five-percent_20")
+            os.makedirs(d)
+            with open(os.path.join(d, "w.json"), "w") as f:
+                json.dump({"states": N, "symbols": M, "A": np.asarray(A0).tolist(),
+                           "B": np.asarray(B0).tolist(), "Pi": np.asarray(pi0).tolist(), "word": "w"}, f)
+            kwargs = dict(load_initial_params=True, word_name="w")
+        os.chdir(os.path.join(tmp, "HMM"))
+        try:
+            with ref_shim.quiet(), ref_shim.LLCapture(ref.training) as cap:
+                A, B, pi = ref.training.hmm_training(obs_list, N=N, M=M, epsilon=eps, max_iterations=iters,
+                                                     show_progress=False, **kwargs)
+        finally:
+            os.chdir(cwd)
+    return A, B, pi, np.array(cap.values)
+
+
+def _bw_case(ref, name, corpus, N, M, iters, eps=1e-6, init=None):
+    W = len(corpus)
+    A = np.zeros((W, N, N)); B = np.zeros((W, N, M)); pi = np.zeros((W, N))
+    ll = np.full((W, iters), np.nan); its = np.zeros(W, np.int32)
+    for w, word in enumerate(corpus):
+        a, b, p, hist = _train_ref(ref, word, N, M, iters, eps, None if init is None else
+                                   (init[0][w], init[1][w], init[2][w]))
+        A[w], B[w], pi[w] = a, b, p
+        ll[w, :len(hist)] = hist
+        its[w] = len(hist)
+        print(f"  {name}: word {w} done, {len(hist)} iterations", flush=True)
+    obs, offsets, word_of_seq = S.pack_corpus(corpus, M)
+    extra = {}
+    if init is not None:
+        extra = dict(pi0=np.asarray(init[0]), A0=np.asarray(init[1]), B0=np.asarray(init[2]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), obs=obs, offsets=offsets, word_of_seq=word_of_seq,
+                        N=N, M=M, max_iterations=iters, epsilon=eps, A=A, B=B, pi=pi, ll_hist=ll,
+                        iters=its, **extra)
+    return A, B, pi
+
+
+def case_bw_c1(ref):
+    """BASELINE config 1: 10 words x 20 utterances x U{90..110} frames, N=4, M=256."""
+    corpus = S.word_corpus(0, 10, 20, kind="clustered")
+    A, B, pi = _bw_case(ref, "bw_c1_clustered_s0_it10", corpus, 4, 256, 10)
+    # recognition golden on held-out utterances, scored against those 10 models
+    test = S.word_corpus(100, 10, 4, kind="clustered")
+    HMM = ref.classes.HMMTrained
+    models = [HMM(4, 256, A[w], B[w], pi[w], f"w{w}") for w in range(10)]
+    seqs = [s for word in test for s in word]
+    ll = np.array([[ref.testing.calculate_log_likelihood(s, m) for m in models] for s in seqs])
+    obs, offsets, true_word = S.pack_corpus(test, 256)
+    np.savez_compressed(os.path.join(OUT, "score_c1.npz"), obs=obs, offsets=offsets, true_word=true_word,
+                        A=A, B=B, pi=pi, ll=ll)
+
+
+def case_bw_small(ref):
+    _bw_case(ref, "bw_uniform_s1_it3", S.word_corpus(1, 3, 20, kind="uniform"), 4, 256, 3)
+    _bw_case(ref, "bw_clustered_s2_it1", S.word_corpus(2, 3, 20, kind="clustered"), 4, 256, 1)
+    # converges before max_iterations (iteration-count parity)
+    _bw_case(ref, "bw_converge_eps", S.word_corpus(3, 4, 6, M=16, tmin=15, tmax=25), 4, 16, 60, eps=1e-3)
+
+
+def case_bw_warm(ref):
+    """N != 4 through the reference's own warm-start route, and structural zeros."""
+    rng = np.random.default_rng(5)
+    N, M, W = 6, 32, 2
+    corpus = S.word_corpus(4, W, 8, N=N, M=M, tmin=25, tmax=35)
+    pi0 = np.zeros((W, N)); A0 = np.zeros((W, N, N)); B0 = np.zeros((W, N, M))
+    for w in range(W):
+        pi0[w] = rng.dirichlet(np.ones(N))
+        A0[w] = rng.dirichlet(np.ones(N), size=N)
+        B0[w] = rng.dirichlet(np.ones(M), size=N)
+    _bw_case(ref, "bw_warm_n6_m32", corpus, N, M, 5, init=(pi0, A0, B0))
+
+    # structural zeros: pi = e0, strict left-to-right A, exact zeros in B so that some
+    # sequences are impossible (-inf) and some states/symbols have no finite term;
+    # includes T=1 and T=2 sequences.
+    N, M, W = 4, 12, 2
+    corpus = []
+    for w in range(W):
+        seqs = S.clustered_sequences(rng, 6, N=N, M=M, tmin=8, tmax=14, spread=3)
+        seqs.append(np.array([0], dtype=np.int64))
+        seqs.append(np.array([1, 4], dtype=np.int64))
+        seqs.append(np.array([11, 0, 3], dtype=np.int64))  # starts with a symbol state 0 cannot emit
+        corpus.append(seqs)
+    pi0 = np.tile(np.array([1.0, 0, 0, 0]), (W, 1))
+    A0 = np.tile(np.array([[0.5, 0.5, 0, 0], [0, 0.5, 0.5, 0], [0, 0, 0.5, 0.5], [0, 0, 0, 1.0]]), (W, 1, 1))
+    B0 = np.zeros((W, N, M))
+    for w in range(W):
+        b = rng.random((N, M)) + 0.05
+        b[0, 9:] = 0.0   # state 0 cannot emit symbols 9..11
+        b[3, :3] = 0.0   # state 3 cannot emit symbols 0..2
+        b[2, 5] = 0.0
+        B0[w] = b / b.sum(axis=1, keepdims=True)
+    _bw_case(ref, "bw_structural_zeros", corpus, N, M, 4, init=(pi0, A0, B0))
+
+
+def case_vq(ref):
+    Raw, Cen = ref.cvc.RawDataMFCC, ref.cvc.CentroidDataMFCC
+    X = S.mfcc_mixture(0, 2000, K=64)
+    C = S.random_codebook(1, 256)
+    C[17] = C[5]          # exact duplicate centroid: lowest index must win
+    C[200] = 0.0; C[201] = 0.0  # twin all-zero centroids (empty-cluster artefact)
+    X[10] = C[5]; X[11] = C[200]; X[12, 1:] = C[33, 1:]  # exact hits, energy dim ignored
+    frames = [Raw(raw_samples=np.array([]), mfcc=x.copy()) for x in X]
+    cents = [Cen(mfcc=c.copy(), id=i) for i, c in enumerate(C)]
+    recs = [frames[:700], frames[700:701], frames[701:]]
+    obs = ref.training.get_observations(recs, cents)
+    np.savez_compressed(os.path.join(OUT, "vq_2000x256.npz"), X=X, C=C, idx=np.concatenate(obs).astype(np.int32),
+                        rec_lens=np.array([len(r) for r in recs]))
+
+
+def _lbg_case(ref, name, X, K, max_iter, eps=0.001):
+    Raw = ref.cvc.RawDataMFCC
+    frames = [Raw(raw_samples=np.array([]), mfcc=x.copy()) for x in X]
+    with ref_shim.quiet() as buf:
+        cents, gens = ref.cvf.createCodeVector(frames, centroids_quantity=K, max_iterations=max_iter,
+                                               epsilon=eps, save_updates=False)
+    iters = [int(line.split("Converged after")[1].split()[0]) for line in buf.getvalue().splitlines()
+             if "Converged after" in line]
+    gens_flat = np.concatenate([np.array([c.mfcc for c in g]) for g in gens])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), X=X, K=K, max_iterations=max_iter, epsilon=eps,
+                        C=np.array([c.mfcc for c in cents]), ids=np.array([c.id for c in cents]),
+                        gens=gens_flat, gen_sizes=np.array([len(g) for g in gens]),
+                        assign=np.array([f.parent_centroid_id for f in frames], dtype=np.int32),
+                        generation=np.array([f.generation for f in frames], dtype=np.int32),
+                        iters=np.array(iters, dtype=np.int32))
+    print(f"  {name}: iters {iters}", flush=True)
+
+
+def case_lbg(ref):
+    _lbg_case(ref, "lbg_600_k32", S.mfcc_mixture(3, 600, K=16), 32, 100)
+    _lbg_case(ref, "lbg_1200_k256_it3", S.mfcc_mixture(4, 1200, K=64), 256, 3)
+    # few distinct points -> empty clusters -> all-zero twin centroids (:435)
+    rng = np.random.default_rng(7)
+    base = S.mfcc_mixture(5, 3, K=3)
+    _lbg_case(ref, "lbg_empty_clusters", base[rng.integers(0, 3, size=60)], 16, 20)
+    _lbg_case(ref, "lbg_k1", S.mfcc_mixture(6, 40, K=2), 1, 5)
+    _lbg_case(ref, "lbg_k24_nonpow2", S.mfcc_mixture(8, 200, K=8), 24, 10)
+
+
+CASES = {"bw_c1": case_bw_c1, "bw_small": case_bw_small, "bw_warm": case_bw_warm,
+         "vq": case_vq, "lbg": case_lbg}
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_shim.load()
+    for name in (sys.argv[1:] or list(CASES)):
+        print(f"[golden] {name}", flush=True)
+        CASES[name](ref)

@@ -1,0 +1,71 @@
+"""The CPU oracle (oracle/) pinned against golden vectors produced by the UNMODIFIED
+reference (oracle/make_golden.py).  CPU-only; runs everywhere."""
+import numpy as np
+import pytest
+
+from helpers import assert_close, assert_same_support, floored_set, load_golden, split_corpus
+from oracle import hmm_oracle as O
+from oracle import vq_oracle
+
+BW_CASES = ["bw_c1_clustered_s0_it10", "bw_uniform_s1_it3", "bw_clustered_s2_it1", "bw_converge_eps",
+            "bw_warm_n6_m32", "bw_structural_zeros"]
+
+
+@pytest.mark.parametrize("name", BW_CASES)
+def test_oracle_baum_welch_matches_reference(name):
+    g = load_golden(name)
+    N, M = int(g["N"]), int(g["M"])
+    corpus = split_corpus(g)
+    for w, word in enumerate(corpus):
+        init = (g["pi0"][w], g["A0"][w], g["B0"][w]) if "pi0" in g else None
+        A, B, pi, hist, it = O.hmm_training(word, N=N, M=M, epsilon=float(g["epsilon"]),
+                                            max_iterations=int(g["max_iterations"]), init=init,
+                                            return_history=True)
+        assert it == int(g["iters"][w]), f"{name} word {w}: iteration count"
+        assert_close(hist, g["ll_hist"][w, :it], f"{name} w{w} ll")
+        assert_close(A, g["A"][w], f"{name} w{w} A")
+        assert_close(pi, g["pi"][w], f"{name} w{w} pi")
+        assert_close(B, g["B"][w], f"{name} w{w} B")
+        assert_same_support(A, g["A"][w], "A")
+        assert_same_support(pi, g["pi"][w], "pi")
+        assert np.array_equal(floored_set(B, M), floored_set(g["B"][w], M))
+
+
+def test_oracle_scoring_matches_reference():
+    g = load_golden("score_c1")
+    off = g["offsets"]
+    seqs = [g["obs"][off[r]:off[r + 1]].astype(np.int64) for r in range(len(off) - 1)]
+    models = [(g["A"][w], g["B"][w], g["pi"][w]) for w in range(g["A"].shape[0])]
+    ll = O.score_batch(seqs, models)
+    assert_close(ll, g["ll"], "score ll")
+    one = O.calculate_log_likelihood(seqs[3], *models[2])
+    assert_close(one, g["ll"][3, 2], "single ll")
+    assert np.array_equal(O.argmax_first(ll), O.argmax_first(g["ll"]))
+
+
+def test_oracle_vq_matches_reference_bit_exact():
+    g = load_golden("vq_2000x256")
+    idx = vq_oracle.encode(g["X"], g["C"])
+    assert np.array_equal(idx, g["idx"])
+    assert idx[10] == 5 and idx[11] == 200 and idx[12] == 33  # duplicates: lowest index wins
+
+
+@pytest.mark.parametrize("name", ["lbg_600_k32", "lbg_1200_k256_it3", "lbg_empty_clusters", "lbg_k1",
+                                  "lbg_k24_nonpow2"])
+def test_oracle_lbg_matches_reference(name):
+    g = load_golden(name)
+    C, gens, assign, iters, _ = vq_oracle.lbg(g["X"], int(g["K"]), int(g["max_iterations"]), float(g["epsilon"]))
+    assert C.shape == g["C"].shape
+    assert np.array_equal(iters, g["iters"])
+    assert_close(C, g["C"], "centroids", rtol=1e-12, atol=0)
+    assert_close(np.concatenate(gens), g["gens"], "generations", rtol=1e-12, atol=0)
+    assert [len(x) for x in gens] == list(g["gen_sizes"])
+    if len(g["iters"]):
+        assert np.array_equal(assign, g["assign"])
+
+
+def test_oracle_errors():
+    with pytest.raises(IndexError):
+        O.hmm_training([np.array([], dtype=np.int64)], max_iterations=1)
+    with pytest.raises(ValueError):
+        vq_oracle.lbg(np.zeros((0, 13)), 4)

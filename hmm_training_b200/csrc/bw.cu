@@ -1,0 +1,814 @@
+// Host side of the Baum-Welch trainer and the forward scorer: sequence sorting/blocking,
+// device layout, the EM loop, and the C ABI declared in include/hmmb200.h.
+#include <algorithm>
+#include <cstdlib>
+#include <numeric>
+
+#include "bw_kernels.cuh"
+
+namespace hmmb {
+
+// ---------------------------------------------------------------- small kernels local to this TU
+// B0 [W][N][M] (linear) -> Bt [W][M][N]; non-positive / NaN entries become structural zeros,
+// which is what safe_log does to them (HMM/hmm_training.py:46-54, :323-325).
+__global__ void k_load_B(const double *__restrict__ B, int N, int M, double *__restrict__ Bt) {
+    const size_t w = blockIdx.y;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < N * M; e += gridDim.x * blockDim.x) {
+        const int k = e / N, j = e - k * N;
+        const double v = B[(w * N + j) * M + k];
+        Bt[w * (size_t)M * N + e] = v > 0.0 ? v : 0.0;
+    }
+}
+__global__ void k_load_clamped(const double *__restrict__ src, int64_t n, double *__restrict__ dst) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const double v = src[e];
+        dst[e] = v > 0.0 ? v : 0.0;
+    }
+}
+__global__ void k_fill(double *p, int64_t n, double v) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) p[e] = v;
+}
+__global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) p[e] = v;
+}
+
+// ---------------------------------------------------------------- scoring kernels
+template <typename SymT>
+__global__ void __launch_bounds__(BW_THREADS)
+k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4 *__restrict__ obs_blk,
+         const int32_t *__restrict__ len_sorted, const int32_t *__restrict__ order, const double *__restrict__ pi,
+         const double *__restrict__ A, const double *__restrict__ Bt, int M, int W, double *__restrict__ ll_out) {
+    extern __shared__ double sB[];
+    const int w = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(Bt + (size_t)w * M * 4);
+        double2 *dst = reinterpret_cast<double2 *>(sB);
+        for (int e = tid; e < M * 2; e += BW_THREADS) dst[e] = __ldg(src + e);
+    }
+    double a[16], p[4];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[q] = __ldg(A + (size_t)w * 16 + q);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) p[q] = __ldg(pi + (size_t)w * 4 + q);
+    __syncthreads();
+    const int b0 = blockIdx.x * blocks_per_cta;
+    const int b1 = min(nblk, b0 + blocks_per_cta);
+    for (int b = b0 + warp; b < b1; b += BW_WARPS) {
+        const Blk bk = blks[b];
+        const int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
+        const double ll = fwd4_run<SymT, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, a, p, nullptr);
+        if (lane < bk.nseq) ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
+    }
+}
+
+template <int NP, typename SymT>
+__global__ void __launch_bounds__(BW_THREADS)
+k_scoreG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, const int32_t *__restrict__ len_sorted,
+         const int32_t *__restrict__ order, int64_t U, int64_t per_group, int N, int M, int W,
+         const double *__restrict__ pi, const double *__restrict__ A, const double *__restrict__ Bt,
+         double *__restrict__ ll_out) {
+    __shared__ double sStage[BW_WARPS][128];
+    const int w = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int GPW = 32 / NP;
+    const int j = lane % NP, gbase = lane - j;
+    const int64_t group = ((int64_t)blockIdx.x * BW_WARPS + warp) * GPW + lane / NP;
+    double acol[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) acol[i] = (i < N && j < N) ? __ldg(A + ((size_t)w * N + i) * N + j) : 0.0;
+    const double pj = j < N ? __ldg(pi + (size_t)w * N + j) : 0.0;
+    for (int64_t k = 0; k < per_group; ++k) {
+        const int64_t r = group * per_group + k;
+        const int T = r < U ? len_sorted[r] : 0;
+        const int Tw = warp_max_int(T);
+        if (Tw == 0) continue;
+        const SymT *o = obs + (T > 0 ? off_sorted[r] : 0);
+        const double ll = fwdG_run<NP, SymT, false>(T, Tw, N, j, gbase, lane, o, Bt + (size_t)w * M * N, acol, pj,
+                                                    nullptr, sStage[warp]);
+        if (T > 0 && j == 0) ll_out[(size_t)order[r] * W + w] = ll;
+    }
+}
+
+// test_hmm's argmax (HMM/hmm_testing.py:143-153): strict '>' from -inf, first model wins.
+__global__ void k_argmax_first(const double *__restrict__ ll, int64_t U, int W, int32_t *__restrict__ out) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= U) return;
+    double best = neg_inf();
+    int bi = -1;
+    for (int w = 0; w < W; ++w) {
+        const double v = ll[(size_t)u * W + w];
+        if (v > best) { best = v; bi = w; }
+    }
+    out[u] = bi;
+}
+
+// Exact recomputation of the (utterance, model) pairs the precision guard marked with NaN.
+template <typename SymT, bool BLOCKED>
+__global__ void __launch_bounds__(BW_THREADS)
+k_score_exact(const void *__restrict__ obs, const int64_t *__restrict__ base_sorted, const int32_t *__restrict__ len_sorted,
+              const int32_t *__restrict__ order, int64_t U, int N, int M, int W, const double *__restrict__ pi,
+              const double *__restrict__ A, const double *__restrict__ Bt, double *__restrict__ ll_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * BW_WARPS + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * BW_WARPS;
+    for (int64_t i = gw; i < U; i += nw) {
+        double *row = ll_out + (size_t)order[i] * W;
+        const int T = len_sorted[i];
+        for (int w0 = 0; w0 < W; w0 += 32) {
+            const double v = (w0 + lane < W) ? row[w0 + lane] : 0.0;
+            unsigned m = __ballot_sync(0xffffffffu, v != v);
+            while (m) {
+                const int w = w0 + __ffs(m) - 1;
+                m &= m - 1;
+                const double *piw = pi + (size_t)w * N, *Aw = A + (size_t)w * N * N, *Btw = Bt + (size_t)w * M * N;
+                double logP;
+                if (BLOCKED) {
+                    BlkObs<SymT> o{reinterpret_cast<const uint4 *>(obs) + base_sorted[i]};
+                    logP = exact_forward(T, N, lane, o, piw, Aw, Btw, (double *)nullptr);
+                } else {
+                    LinObs<SymT> o{reinterpret_cast<const SymT *>(obs) + base_sorted[i]};
+                    logP = exact_forward(T, N, lane, o, piw, Aw, Btw, (double *)nullptr);
+                }
+                if (lane == 0) row[w] = logP;
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- sequence set (shared by BW and scoring)
+struct SeqSet {
+    int64_t R = 0, frames = 0;
+    int N = 0, M = 0, NP = 0, sym_bytes = 1;
+    bool special4 = false;
+    std::vector<int32_t> order;       // sorted -> original
+    std::vector<int64_t> seq_begin;   // per word [W+1] (sorted order)
+    std::vector<int32_t> cta_begin;   // per word [W+1]
+    int nblk = 0, ncta = 0;
+    int64_t spill_steps = 0;          // special: sum of tmax over blocks
+    int tmax_all = 0;                 // longest sequence
+    // device
+    void *d_obs = nullptr;            // special: uint4 blocks; generic: canonical symbols
+    int64_t *d_off = nullptr, *d_foff = nullptr;  // d_foff: frame prefix (generic) / uint4 row of the lane (N = 4 path)
+    int32_t *d_len = nullptr, *d_word = nullptr, *d_order = nullptr;
+    Blk *d_blks = nullptr;
+    CtaWork *d_work = nullptr;
+    void release() {
+        dev_free(d_obs); dev_free(d_off); dev_free(d_foff); dev_free(d_len); dev_free(d_word); dev_free(d_order);
+        dev_free(d_blks); dev_free(d_work);
+        d_obs = nullptr; d_off = d_foff = nullptr; d_len = d_word = d_order = nullptr; d_blks = nullptr; d_work = nullptr;
+    }
+};
+
+static int pick_np(int N) { return N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : 32)); }
+
+template <typename InT>
+static int launch_prepare(SeqSet &s, const InT *d_in, int64_t nsym, int *d_bad, const std::vector<Blk> &blks) {
+    Ctx &c = ctx();
+    if (s.special4) {
+        if (s.sym_bytes == 1)
+            HMMB_LAUNCH("prepare", (k_repack_blocks<InT, uint8_t>), s.nblk, 128, 0, d_in, s.d_off, s.d_len, s.d_blks, s.nblk,
+                        (uint4 *)s.d_obs, s.M, d_bad);
+        else
+            HMMB_LAUNCH("prepare", (k_repack_blocks<InT, uint16_t>), s.nblk, 128, 0, d_in, s.d_off, s.d_len, s.d_blks,
+                        s.nblk, (uint4 *)s.d_obs, s.M, d_bad);
+    } else {
+        int grid = (int)std::min<int64_t>((nsym + 255) / 256, (int64_t)c.sm_count * 8);
+        if (grid < 1) grid = 1;
+        if (s.sym_bytes == 1)
+            HMMB_LAUNCH("prepare", (k_convert_obs<InT, uint8_t>), grid, 256, 0, d_in, nsym, (uint8_t *)s.d_obs, s.M, d_bad);
+        else
+            HMMB_LAUNCH("prepare", (k_convert_obs<InT, uint16_t>), grid, 256, 0, d_in, nsym, (uint16_t *)s.d_obs, s.M, d_bad);
+    }
+    (void)blks;
+    return HMMB_OK;
+}
+
+// Sort sequences by (word, length desc), build blocks / CTA work items, move the codewords
+// to the device in the layout the kernels read.  word_of_seq == nullptr: a single "word"
+// (scoring: every utterance is scored against every model).
+static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets,
+                        const int32_t *word_of_seq, int64_t R, int W, int N, int M, bool allow_special) {
+    Ctx &c = ctx();
+    if (R < 0 || W <= 0 || !offsets || (R > 0 && !obs)) { set_error("bad sequence arguments"); return HMMB_ERR_ARG; }
+    if (N < 1 || N > HMMB_MAX_STATES) { set_error("N=%d outside supported range 1..%d", N, HMMB_MAX_STATES); return HMMB_ERR_UNSUPPORTED; }
+    if (M < 1 || M > 65536) { set_error("M=%d outside supported range 1..65536", M); return HMMB_ERR_UNSUPPORTED; }
+    if (idx_bytes != 1 && idx_bytes != 2 && idx_bytes != 4 && idx_bytes != 8) { set_error("idx_bytes must be 1, 2, 4 or 8"); return HMMB_ERR_ARG; }
+    s.R = R; s.N = N; s.M = M; s.NP = pick_np(N);
+    s.sym_bytes = M <= 256 ? 1 : 2;
+    s.special4 = allow_special && N == 4 && M <= 512 && !getenv("HMMB_FORCE_GENERIC");
+
+    std::vector<int32_t> len(R);
+    for (int64_t r = 0; r < R; ++r) {
+        const int64_t T = offsets[r + 1] - offsets[r];
+        if (T <= 0) {
+            // reference: IndexError at hmm_training.py:376 / hmm_testing.py:75 for an empty recording
+            set_error(T == 0 ? "sequence %lld is empty (T == 0)" : "offsets not monotone at sequence %lld", (long long)r);
+            return T == 0 ? HMMB_ERR_EMPTY : HMMB_ERR_ARG;
+        }
+        if (T > (1 << 30)) { set_error("sequence %lld too long", (long long)r); return HMMB_ERR_UNSUPPORTED; }
+        if (word_of_seq && (word_of_seq[r] < 0 || word_of_seq[r] >= W)) {
+            set_error("word_of_seq[%lld]=%d outside [0,%d)", (long long)r, word_of_seq[r], W);
+            return HMMB_ERR_ARG;
+        }
+        len[r] = (int32_t)T;
+    }
+    s.frames = R > 0 ? offsets[R] - offsets[0] : 0;
+    s.order.resize(R);
+    std::iota(s.order.begin(), s.order.end(), 0);
+    bool sorted = true;
+    for (int64_t r = 1; r < R && sorted; ++r) {
+        const int wa = word_of_seq ? word_of_seq[r - 1] : 0, wb = word_of_seq ? word_of_seq[r] : 0;
+        if (wa > wb || (wa == wb && len[r - 1] < len[r])) sorted = false;
+    }
+    if (!sorted)
+        std::stable_sort(s.order.begin(), s.order.end(), [&](int32_t x, int32_t y) {
+            const int wx = word_of_seq ? word_of_seq[x] : 0, wy = word_of_seq ? word_of_seq[y] : 0;
+            if (wx != wy) return wx < wy;
+            return len[x] > len[y];
+        });
+    const int nwords = word_of_seq ? W : 1;
+    std::vector<int64_t> off_s(R), foff_s(R);
+    std::vector<int32_t> len_s(R), word_s(R);
+    s.seq_begin.assign(nwords + 1, 0);
+    int64_t facc = 0;
+    for (int64_t i = 0; i < R; ++i) {
+        const int32_t r = s.order[i];
+        off_s[i] = offsets[r] - offsets[0];
+        len_s[i] = len[r];
+        word_s[i] = word_of_seq ? word_of_seq[r] : 0;
+        foff_s[i] = facc;
+        facc += len[r];
+        s.tmax_all = std::max(s.tmax_all, (int)len[r]);
+        s.seq_begin[word_s[i] + 1]++;
+    }
+    for (int w = 0; w < nwords; ++w) s.seq_begin[w + 1] += s.seq_begin[w];
+
+    std::vector<Blk> blks;
+    std::vector<CtaWork> work;
+    int64_t obs_rows = 0;
+    if (s.special4) {
+        const int SPC = s.sym_bytes == 1 ? 16 : 8;
+        std::vector<int> word_blk_begin(nwords + 1, 0);
+        for (int w = 0; w < nwords; ++w) {
+            word_blk_begin[w] = (int)blks.size();
+            for (int64_t i = s.seq_begin[w]; i < s.seq_begin[w + 1]; i += 32) {
+                Blk b;
+                b.word = w;
+                b.first = (int32_t)i;
+                b.nseq = (int32_t)std::min<int64_t>(32, s.seq_begin[w + 1] - i);
+                b.tmax = len_s[i];  // sorted by length descending within the word
+                b.obs_base = obs_rows;
+                b.spill_base = s.spill_steps;
+                for (int l = 0; l < b.nseq; ++l) foff_s[i + l] = obs_rows + l;  // used by the exact kernels
+                obs_rows += (int64_t)((b.tmax + SPC - 1) / SPC) * 32;
+                s.spill_steps += b.tmax;
+                blks.push_back(b);
+            }
+        }
+        word_blk_begin[nwords] = (int)blks.size();
+        s.nblk = (int)blks.size();
+        // CTA work items: ~8 CTAs per SM in total, at least one warp-round (4 blocks) each
+        const int target = c.sm_count * 8;
+        int bpc = std::max(1, (s.nblk + target - 1) / target);
+        if (bpc > 1) bpc = (bpc + BW_WARPS - 1) / BW_WARPS * BW_WARPS;
+        s.cta_begin.assign(nwords + 1, 0);
+        for (int w = 0; w < nwords; ++w) {
+            s.cta_begin[w] = (int)work.size();
+            for (int b = word_blk_begin[w]; b < word_blk_begin[w + 1]; b += bpc) {
+                CtaWork cw;
+                cw.word = w;
+                cw.blk_begin = b;
+                cw.blk_end = std::min(word_blk_begin[w + 1], b + bpc);
+                cw.seq_begin = blks[b].first;
+                work.push_back(cw);
+            }
+        }
+        s.cta_begin[nwords] = (int)work.size();
+        s.ncta = (int)work.size();
+    }
+
+    // ---- device buffers
+    const size_t nR = (size_t)std::max<int64_t>(R, 1);
+    HMMB_TRY(dev_alloc_t(&s.d_off, nR));
+    HMMB_TRY(dev_alloc_t(&s.d_foff, nR));
+    HMMB_TRY(dev_alloc_t(&s.d_len, nR));
+    HMMB_TRY(dev_alloc_t(&s.d_word, nR));
+    HMMB_TRY(dev_alloc_t(&s.d_order, nR));
+    if (R > 0) {
+        HMMB_CUDA(cudaMemcpyAsync(s.d_off, off_s.data(), R * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+        HMMB_CUDA(cudaMemcpyAsync(s.d_foff, foff_s.data(), R * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+        HMMB_CUDA(cudaMemcpyAsync(s.d_len, len_s.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+        HMMB_CUDA(cudaMemcpyAsync(s.d_word, word_s.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+        HMMB_CUDA(cudaMemcpyAsync(s.d_order, s.order.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+    }
+    if (s.special4) {
+        HMMB_TRY(dev_alloc_t(&s.d_blks, std::max<size_t>(blks.size(), 1)));
+        HMMB_TRY(dev_alloc_t(&s.d_work, std::max<size_t>(work.size(), 1)));
+        if (!blks.empty()) {
+            HMMB_CUDA(cudaMemcpyAsync(s.d_blks, blks.data(), blks.size() * sizeof(Blk), cudaMemcpyHostToDevice, c.stream));
+            HMMB_CUDA(cudaMemcpyAsync(s.d_work, work.data(), work.size() * sizeof(CtaWork), cudaMemcpyHostToDevice, c.stream));
+        }
+        HMMB_TRY(dev_alloc(&s.d_obs, (size_t)std::max<int64_t>(obs_rows, 1) * sizeof(uint4)));
+    } else {
+        HMMB_TRY(dev_alloc(&s.d_obs, (size_t)std::max<int64_t>(s.frames, 1) * s.sym_bytes));
+    }
+    // raw codewords -> device (if needed) -> canonical layout
+    const void *d_in = obs;
+    void *d_tmp = nullptr;
+    const size_t in_bytes = (size_t)s.frames * idx_bytes;
+    if (R > 0) {
+        const char *src = (const char *)obs + (size_t)offsets[0] * idx_bytes;
+        if (!obs_on_device) {
+            HMMB_TRY(dev_alloc(&d_tmp, in_bytes));
+            HMMB_CUDA(cudaMemcpyAsync(d_tmp, src, in_bytes, cudaMemcpyHostToDevice, c.stream));
+            d_in = d_tmp;
+        } else {
+            d_in = src;
+        }
+    }
+    int *d_bad = nullptr;
+    HMMB_TRY(dev_alloc_t(&d_bad, 1));
+    HMMB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), c.stream));
+    int rc = HMMB_OK;
+    if (R > 0) {
+        switch (idx_bytes) {
+            case 1: rc = launch_prepare(s, (const uint8_t *)d_in, s.frames, d_bad, blks); break;
+            case 2: rc = launch_prepare(s, (const uint16_t *)d_in, s.frames, d_bad, blks); break;
+            case 4: rc = launch_prepare(s, (const uint32_t *)d_in, s.frames, d_bad, blks); break;
+            default: rc = launch_prepare(s, (const unsigned long long *)d_in, s.frames, d_bad, blks); break;
+        }
+    }
+    int bad = 0;
+    if (rc == HMMB_OK) {
+        cudaError_t e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "prepare sync", __FILE__, __LINE__);
+    }
+    dev_free(d_tmp);
+    dev_free(d_bad);
+    if (rc != HMMB_OK) return rc;
+    if (bad) {
+        set_error("codeword out of range: some observation is >= M=%d (reference: IndexError)", M);
+        return HMMB_ERR_RANGE;
+    }
+    return HMMB_OK;
+}
+
+}  // namespace hmmb
+
+using namespace hmmb;
+
+// ---------------------------------------------------------------- the trainer handle
+struct hmmb_bw {
+    SeqSet s;
+    int W = 0, N = 0, M = 0;
+    double *d_pi = nullptr, *d_A = nullptr, *d_Bt = nullptr;
+    double *d_spill = nullptr, *d_llseq = nullptr, *d_accum = nullptr, *d_partials = nullptr;
+    double *d_prev = nullptr, *d_hist = nullptr;
+    int32_t *d_active = nullptr, *d_iters = nullptr, *d_any = nullptr, *d_cta_begin = nullptr;
+    int64_t *d_seq_begin = nullptr;
+    // precision guard: sticky per-sequence hand-over flags, counters, exact-kernel scratch
+    uint8_t *d_flag = nullptr;
+    int32_t *d_newflags = nullptr;
+    int64_t *d_nexact = nullptr;
+    double *d_exact_scratch = nullptr;
+    int exact_grid = 1;
+    int64_t exact_stride = 0;
+    int64_t n_backward_handover = 0;
+    int64_t nacc = 0, astride = 0, accum_n = 0, pstride = 0;
+    int hist_cap = 0;
+    int rank = 0, world = 1;
+    hmmb_allreduce_fn allreduce = nullptr;
+    void *user = nullptr;
+    bool params_set = false, any_active = true;
+};
+
+static void bw_release(hmmb_bw *h) {
+    h->s.release();
+    dev_free(h->d_pi); dev_free(h->d_A); dev_free(h->d_Bt); dev_free(h->d_spill); dev_free(h->d_llseq);
+    dev_free(h->d_accum); dev_free(h->d_partials); dev_free(h->d_prev); dev_free(h->d_hist); dev_free(h->d_active);
+    dev_free(h->d_iters); dev_free(h->d_any); dev_free(h->d_cta_begin); dev_free(h->d_seq_begin);
+    dev_free(h->d_flag); dev_free(h->d_newflags); dev_free(h->d_nexact); dev_free(h->d_exact_scratch);
+}
+
+static int bw_alloc_accum(hmmb_bw *h) {
+    dev_free(h->d_accum);
+    h->d_accum = nullptr;
+    h->accum_n = (int64_t)h->W * h->astride + (int64_t)h->world * h->W * 2;
+    return dev_alloc_t(&h->d_accum, (size_t)h->accum_n);
+}
+
+// (C linkage comes from the declarations in include/hmmb200.h)
+
+int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets,
+                   const int32_t *word_of_seq, int64_t R, int W, int N, int M) {
+    HMMB_TRY(require_init());
+    if (!out || !word_of_seq) { set_error("hmmb_bw_create: null argument"); return HMMB_ERR_ARG; }
+    *out = nullptr;
+    Ctx &c = ctx();
+    hmmb_bw *h = new hmmb_bw();
+    h->W = W; h->N = N; h->M = M;
+    int rc = seqset_build(h->s, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, true);
+    auto fail = [&](int code) { bw_release(h); delete h; return code; };
+    if (rc != HMMB_OK) return fail(rc);
+    SeqSet &s = h->s;
+    h->nacc = (int64_t)N + (int64_t)N * N + (int64_t)M * N;
+    h->astride = (h->nacc + 1 + 1) & ~int64_t(1);
+    h->pstride = h->nacc;
+    h->hist_cap = 0;
+#define TRYF(expr) do { int _r = (expr); if (_r != HMMB_OK) return fail(_r); } while (0)
+#define CUDAF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(cuda_fail(_e, #expr, __FILE__, __LINE__)); } while (0)
+    TRYF(dev_alloc_t(&h->d_pi, (size_t)W * N));
+    TRYF(dev_alloc_t(&h->d_A, (size_t)W * N * N));
+    TRYF(dev_alloc_t(&h->d_Bt, (size_t)W * M * N));
+    TRYF(dev_alloc_t(&h->d_llseq, (size_t)std::max<int64_t>(R, 1)));
+    TRYF(bw_alloc_accum(h));
+    TRYF(dev_alloc_t(&h->d_prev, (size_t)W));
+    TRYF(dev_alloc_t(&h->d_active, (size_t)W));
+    TRYF(dev_alloc_t(&h->d_iters, (size_t)W));
+    TRYF(dev_alloc_t(&h->d_any, 1));
+    TRYF(dev_alloc_t(&h->d_flag, (size_t)std::max<int64_t>(R, 1)));
+    TRYF(dev_alloc_t(&h->d_newflags, 1));
+    TRYF(dev_alloc_t(&h->d_nexact, 1));
+    {
+        // exact log-space kernel: one warp per handed-over sequence, log alpha scratch per warp
+        h->exact_stride = (int64_t)std::max(s.tmax_all, 1) * N;
+        int64_t warps = std::min<int64_t>((int64_t)c.sm_count * 8, std::max<int64_t>(1, (256LL << 20) / (h->exact_stride * 8)));
+        warps = std::min<int64_t>(warps, std::max<int64_t>(1, (R + 31) / 32));
+        h->exact_grid = (int)std::max<int64_t>(1, (warps + BW_WARPS - 1) / BW_WARPS);
+        TRYF(dev_alloc_t(&h->d_exact_scratch, (size_t)h->exact_grid * BW_WARPS * h->exact_stride));
+    }
+    TRYF(dev_alloc_t(&h->d_seq_begin, (size_t)W + 1));
+    CUDAF(cudaMemcpyAsync(h->d_seq_begin, s.seq_begin.data(), (W + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+    size_t spill_bytes;
+    if (s.special4) {
+        spill_bytes = (size_t)std::max<int64_t>(s.spill_steps, 1) * 64 * sizeof(double2);
+        TRYF(dev_alloc_t(&h->d_partials, (size_t)std::max(s.ncta, 1) * h->pstride));
+        TRYF(dev_alloc_t(&h->d_cta_begin, (size_t)W + 1));
+        CUDAF(cudaMemcpyAsync(h->d_cta_begin, s.cta_begin.data(), (W + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+    } else {
+        spill_bytes = (size_t)std::max<int64_t>(s.frames, 1) * N * sizeof(double);
+    }
+    {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        (void)total_b;
+    }
+    rc = dev_alloc((void **)&h->d_spill, spill_bytes);
+    if (rc != HMMB_OK) {
+        set_error("alpha spill of %.2f GB does not fit in device memory; shard the sequences over more GPUs",
+                  spill_bytes / 1e9);
+        return fail(HMMB_ERR_OOM);
+    }
+    CUDAF(cudaStreamSynchronize(c.stream));  // host staging vectors in seqset_build are gone after this point
+#undef TRYF
+#undef CUDAF
+    *out = h;
+    return HMMB_OK;
+}
+
+int hmmb_bw_destroy(hmmb_bw_t *h) {
+    if (!h) return HMMB_OK;
+    if (ctx().inited) cudaStreamSynchronize(ctx().stream);
+    bw_release(h);
+    delete h;
+    return HMMB_OK;
+}
+
+int64_t hmmb_bw_total_frames(hmmb_bw_t *h) { return h ? h->s.frames : 0; }
+
+int hmmb_bw_set_params(hmmb_bw_t *h, const double *pi0, const double *A0, const double *B0) {
+    HMMB_TRY(require_init());
+    if (!h || !pi0 || !A0 || !B0) { set_error("hmmb_bw_set_params: null argument"); return HMMB_ERR_ARG; }
+    Ctx &c = ctx();
+    const int W = h->W, N = h->N, M = h->M;
+    double *tmp = nullptr;
+    const size_t nB = (size_t)W * N * M, nA = (size_t)W * N * N, nP = (size_t)W * N;
+    HMMB_TRY(dev_alloc_t(&tmp, nB + nA + nP));
+    HMMB_CUDA(cudaMemcpyAsync(tmp, B0, nB * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    HMMB_CUDA(cudaMemcpyAsync(tmp + nB, A0, nA * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    HMMB_CUDA(cudaMemcpyAsync(tmp + nB + nA, pi0, nP * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    dim3 gb((unsigned)std::min((N * M + 255) / 256, 64), (unsigned)W);
+    HMMB_LAUNCH("bw_load", k_load_B, gb, 256, 0, tmp, N, M, h->d_Bt);
+    HMMB_LAUNCH("bw_load", k_load_clamped, (unsigned)std::min<size_t>((nA + 255) / 256, 1024), 256, 0, tmp + nB, (int64_t)nA, h->d_A);
+    HMMB_LAUNCH("bw_load", k_load_clamped, (unsigned)std::min<size_t>((nP + 255) / 256, 1024), 256, 0, tmp + nB + nA, (int64_t)nP, h->d_pi);
+    HMMB_LAUNCH("bw_load", k_fill, (unsigned)((W + 255) / 256), 256, 0, h->d_prev, (int64_t)W, -INFINITY);
+    HMMB_LAUNCH("bw_load", k_fill_i32, (unsigned)((W + 255) / 256), 256, 0, h->d_active, (int64_t)W, 1);
+    HMMB_LAUNCH("bw_load", k_fill_i32, (unsigned)((W + 255) / 256), 256, 0, h->d_iters, (int64_t)W, 0);
+    if (h->d_hist) HMMB_LAUNCH("bw_load", k_fill, 64, 256, 0, h->d_hist, (int64_t)W * h->hist_cap, (double)NAN);
+    HMMB_CUDA(cudaMemsetAsync(h->d_flag, 0, (size_t)std::max<int64_t>(h->s.R, 1), c.stream));
+    HMMB_CUDA(cudaMemsetAsync(h->d_newflags, 0, sizeof(int32_t), c.stream));
+    HMMB_CUDA(cudaMemsetAsync(h->d_nexact, 0, sizeof(int64_t), c.stream));
+    h->n_backward_handover = 0;
+    HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    dev_free(tmp);
+    h->params_set = true;
+    h->any_active = true;
+    return HMMB_OK;
+}
+
+int hmmb_bw_set_dist(hmmb_bw_t *h, int rank, int world, hmmb_allreduce_fn allreduce, void *user) {
+    HMMB_TRY(require_init());
+    if (!h || world < 1 || rank < 0 || rank >= world || (world > 1 && !allreduce)) {
+        set_error("hmmb_bw_set_dist: bad arguments (rank=%d world=%d)", rank, world);
+        return HMMB_ERR_ARG;
+    }
+    h->rank = rank; h->world = world; h->allreduce = allreduce; h->user = user;
+    return bw_alloc_accum(h);
+}
+
+static int bw_ensure_hist(hmmb_bw *h, int cap) {
+    if (cap <= h->hist_cap) return HMMB_OK;
+    Ctx &c = ctx();
+    double *nh = nullptr;
+    HMMB_TRY(dev_alloc_t(&nh, (size_t)h->W * cap));
+    HMMB_LAUNCH("bw_load", k_fill, 64, 256, 0, nh, (int64_t)h->W * cap, (double)NAN);
+    if (h->d_hist && h->hist_cap > 0)
+        HMMB_CUDA(cudaMemcpy2DAsync(nh, cap * sizeof(double), h->d_hist, h->hist_cap * sizeof(double),
+                                    h->hist_cap * sizeof(double), h->W, cudaMemcpyDeviceToDevice, c.stream));
+    HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    dev_free(h->d_hist);
+    h->d_hist = nh;
+    h->hist_cap = cap;
+    return HMMB_OK;
+}
+
+template <typename SymT, bool BLOCKED>
+static int launch_exact(hmmb_bw *h) {
+    SeqSet &s = h->s;
+    HMMB_LAUNCH("bw_exact", (k_bw_exact<SymT, BLOCKED>), h->exact_grid, BW_THREADS, 0, s.d_obs, BLOCKED ? s.d_foff : s.d_off,
+                s.d_len, s.d_word, s.R, h->N, h->M, h->d_pi, h->d_A, h->d_Bt, h->d_llseq, h->d_active, h->d_flag,
+                h->d_exact_scratch, h->exact_stride, h->d_accum, h->astride, h->d_nexact);
+    return HMMB_OK;
+}
+
+template <int NP, typename SymT>
+static int launch_generic_estep(hmmb_bw *h) {
+    Ctx &c = ctx();
+    SeqSet &s = h->s;
+    constexpr int GPW = 32 / NP;
+    const int64_t groups_needed = std::max<int64_t>(s.R, 1);
+    int64_t grid = (groups_needed + BW_WARPS * GPW - 1) / (BW_WARPS * GPW);
+    grid = std::min<int64_t>(grid, (int64_t)c.sm_count * 16);
+    const int64_t total_groups = grid * BW_WARPS * GPW;
+    const int64_t per_group = (s.R + total_groups - 1) / total_groups;
+    HMMB_LAUNCH("bw_forward", (k_bw_fwdG<NP, SymT>), (unsigned)grid, BW_THREADS, 0, (const SymT *)s.d_obs, s.d_off, s.d_len,
+                s.d_word, s.d_foff, s.R, per_group, h->N, h->M, h->d_pi, h->d_A, h->d_Bt, h->d_spill, h->d_llseq,
+                h->d_active, h->d_flag);
+    HMMB_TRY((launch_exact<SymT, false>(h)));
+    HMMB_LAUNCH("bw_backward", (k_bw_bwdG<NP, SymT>), (unsigned)grid, BW_THREADS, 0, (const SymT *)s.d_obs, s.d_off, s.d_len,
+                s.d_word, s.d_foff, s.R, per_group, h->N, h->M, h->d_A, h->d_Bt, h->d_spill, h->d_llseq, h->d_active,
+                h->d_accum, h->astride, h->d_flag, h->d_newflags);
+    return HMMB_OK;
+}
+
+template <typename SymT>
+static int launch_special_estep(hmmb_bw *h) {
+    SeqSet &s = h->s;
+    if (s.ncta == 0) return HMMB_OK;
+    const size_t smem_f = (size_t)h->M * 4 * sizeof(double);
+    const size_t smem_b = smem_f * (1 + BW_WARPS);
+    HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwd4<SymT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    HMMB_LAUNCH("bw_forward", k_bw_fwd4<SymT>, s.ncta, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
+                s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag);
+    HMMB_TRY((launch_exact<SymT, true>(h)));
+    HMMB_LAUNCH("bw_backward", k_bw_bwd4<SymT>, s.ncta, BW_THREADS, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
+                s.d_len, h->d_A, h->d_Bt, h->M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_partials,
+                h->pstride, h->d_flag, h->d_newflags);
+    return HMMB_OK;
+}
+
+static int bw_estep(hmmb_bw *h) {
+    SeqSet &s = h->s;
+    if (s.special4) return s.sym_bytes == 1 ? launch_special_estep<uint8_t>(h) : launch_special_estep<uint16_t>(h);
+#define GEN(NPV)                                                                               \
+    case NPV:                                                                                  \
+        return s.sym_bytes == 1 ? launch_generic_estep<NPV, uint8_t>(h) : launch_generic_estep<NPV, uint16_t>(h);
+    switch (s.NP) {
+        GEN(4) GEN(8) GEN(16) GEN(32)
+    }
+#undef GEN
+    return HMMB_ERR_UNSUPPORTED;
+}
+
+int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync_each) {
+    HMMB_TRY(require_init());
+    if (!h || !h->params_set) { set_error("hmmb_bw_iterate: parameters not set"); return HMMB_ERR_ARG; }
+    Ctx &c = ctx();
+    HMMB_TRY(bw_ensure_hist(h, std::max(max_iter, 1)));
+    for (int it = 0; it < n_iter; ++it) {
+        if (!h->any_active) break;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            HMMB_CUDA(cudaMemsetAsync(h->d_accum, 0, (size_t)h->accum_n * sizeof(double), c.stream));
+            HMMB_TRY(bw_estep(h));
+            if (!sync_each) break;
+            // backward-pass hand-overs are discovered after their sequence already contributed:
+            // redo this E-step once with them routed to the exact kernel (flags are sticky)
+            int32_t nf = 0;
+            HMMB_CUDA(cudaMemcpyAsync(&nf, h->d_newflags, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+            HMMB_CUDA(cudaStreamSynchronize(c.stream));
+            if (nf == 0) break;
+            h->n_backward_handover += nf;
+            HMMB_CUDA(cudaMemsetAsync(h->d_newflags, 0, sizeof(int32_t), c.stream));
+        }
+        HMMB_LAUNCH("bw_reduce", k_bw_reduce, h->W, RED_THREADS, 0, h->s.special4 ? h->d_partials : nullptr, h->pstride,
+                    h->d_cta_begin, h->d_llseq, h->d_seq_begin, h->d_accum, h->astride, h->nacc,
+                    h->d_accum + (size_t)h->W * h->astride, h->rank, h->W, h->d_active);
+        if (h->allreduce && h->world > 1) {
+            int rc = h->allreduce(h->d_accum, h->accum_n, h->user);
+            if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+        }
+        HMMB_CUDA(cudaMemsetAsync(h->d_any, 0, sizeof(int32_t), c.stream));
+        HMMB_LAUNCH("bw_mstep", k_bw_mstep, h->W, RED_THREADS, 0, h->d_accum, h->astride,
+                    h->d_accum + (size_t)h->W * h->astride, h->world, h->W, h->N, h->M, h->d_pi, h->d_A, h->d_Bt,
+                    h->d_active, h->d_iters, h->d_prev, h->d_hist, h->hist_cap, eps, max_iter, h->d_any);
+        if (sync_each) {
+            int32_t any = 0;
+            HMMB_CUDA(cudaMemcpyAsync(&any, h->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+            HMMB_CUDA(cudaStreamSynchronize(c.stream));
+            h->any_active = any != 0;
+        }
+    }
+    if (!sync_each && n_iter > 0) {
+        int32_t any = 0;
+        HMMB_CUDA(cudaMemcpyAsync(&any, h->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        HMMB_CUDA(cudaStreamSynchronize(c.stream));
+        h->any_active = any != 0;
+    }
+    return HMMB_OK;
+}
+
+int hmmb_bw_get_params(hmmb_bw_t *h, int finalize, double *pi, double *A, double *B) {
+    HMMB_TRY(require_init());
+    if (!h || !h->params_set) { set_error("hmmb_bw_get_params: parameters not set"); return HMMB_ERR_ARG; }
+    Ctx &c = ctx();
+    const int W = h->W, N = h->N, M = h->M;
+    const size_t nB = (size_t)W * N * M, nA = (size_t)W * N * N, nP = (size_t)W * N;
+    double *tmp = nullptr;
+    HMMB_TRY(dev_alloc_t(&tmp, nB + nA + nP));
+    HMMB_LAUNCH("bw_finalize", k_bw_finalize, W, RED_THREADS, 0, h->d_pi, h->d_A, h->d_Bt, N, M, finalize, tmp + nB + nA,
+                tmp + nB, tmp);
+    if (B) HMMB_CUDA(cudaMemcpyAsync(B, tmp, nB * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (A) HMMB_CUDA(cudaMemcpyAsync(A, tmp + nB, nA * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (pi) HMMB_CUDA(cudaMemcpyAsync(pi, tmp + nB + nA, nP * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    dev_free(tmp);
+    return HMMB_OK;
+}
+
+int hmmb_bw_get_history(hmmb_bw_t *h, double *ll_hist, int hist_cap, int32_t *iters) {
+    HMMB_TRY(require_init());
+    if (!h) { set_error("hmmb_bw_get_history: null handle"); return HMMB_ERR_ARG; }
+    Ctx &c = ctx();
+    if (ll_hist && hist_cap > 0) {
+        for (int64_t e = 0; e < (int64_t)h->W * hist_cap; ++e) ll_hist[e] = NAN;
+        const int ncopy = std::min(hist_cap, h->hist_cap);
+        if (ncopy > 0 && h->d_hist)
+            HMMB_CUDA(cudaMemcpy2DAsync(ll_hist, hist_cap * sizeof(double), h->d_hist, h->hist_cap * sizeof(double),
+                                        ncopy * sizeof(double), h->W, cudaMemcpyDeviceToHost, c.stream));
+    }
+    if (iters) HMMB_CUDA(cudaMemcpyAsync(iters, h->d_iters, h->W * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    return HMMB_OK;
+}
+
+int hmmb_bw_diagnostics(hmmb_bw_t *h, int64_t *exact_sequence_passes, int64_t *backward_handovers) {
+    HMMB_TRY(require_init());
+    if (!h) { set_error("hmmb_bw_diagnostics: null handle"); return HMMB_ERR_ARG; }
+    Ctx &c = ctx();
+    int64_t ne = 0;
+    int32_t nf = 0;
+    HMMB_CUDA(cudaMemcpyAsync(&ne, h->d_nexact, sizeof(int64_t), cudaMemcpyDeviceToHost, c.stream));
+    HMMB_CUDA(cudaMemcpyAsync(&nf, h->d_newflags, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    if (exact_sequence_passes) *exact_sequence_passes = ne;
+    if (backward_handovers) *backward_handovers = h->n_backward_handover + nf;
+    return HMMB_OK;
+}
+
+int hmmb_bw_get_seq_ll(hmmb_bw_t *h, double *ll_seq) {
+    HMMB_TRY(require_init());
+    if (!h || !ll_seq) { set_error("hmmb_bw_get_seq_ll: null argument"); return HMMB_ERR_ARG; }
+    Ctx &c = ctx();
+    std::vector<double> tmp((size_t)h->s.R);
+    if (h->s.R > 0) {
+        HMMB_CUDA(cudaMemcpyAsync(tmp.data(), h->d_llseq, h->s.R * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    for (int64_t i = 0; i < h->s.R; ++i) ll_seq[h->s.order[i]] = tmp[i];
+    return HMMB_OK;
+}
+
+int hmmb_bw_fit(const void *obs, int idx_bytes, const int64_t *offsets, const int32_t *word_of_seq, int64_t R, int W,
+                int N, int M, const double *pi0, const double *A0, const double *B0, double eps, int max_iter,
+                double *pi, double *A, double *B, double *ll_hist, int32_t *iters) {
+    hmmb_bw_t *h = nullptr;
+    HMMB_TRY(hmmb_bw_create(&h, obs, idx_bytes, 0, offsets, word_of_seq, R, W, N, M));
+    int rc = hmmb_bw_set_params(h, pi0, A0, B0);
+    if (rc == HMMB_OK) rc = hmmb_bw_iterate(h, max_iter, eps, max_iter, 1);
+    if (rc == HMMB_OK) rc = hmmb_bw_get_params(h, 1, pi, A, B);
+    if (rc == HMMB_OK && (ll_hist || iters)) rc = hmmb_bw_get_history(h, ll_hist, std::max(max_iter, 1), iters);
+    hmmb_bw_destroy(h);
+    return rc;
+}
+
+// ---------------------------------------------------------------- recognition
+template <int NP, typename SymT>
+static int launch_score_generic(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll) {
+    Ctx &c = ctx();
+    constexpr int GPW = 32 / NP;
+    int64_t grid = (std::max<int64_t>(s.R, 1) + BW_WARPS * GPW - 1) / (BW_WARPS * GPW);
+    grid = std::min<int64_t>(grid, (int64_t)c.sm_count * 16);
+    const int64_t total_groups = grid * BW_WARPS * GPW;
+    const int64_t per_group = (s.R + total_groups - 1) / total_groups;
+    dim3 g((unsigned)grid, (unsigned)W);
+    HMMB_LAUNCH("score", (k_scoreG<NP, SymT>), g, BW_THREADS, 0, (const SymT *)s.d_obs, s.d_off, s.d_len, s.d_order, s.R,
+                per_group, s.N, s.M, W, d_pi, d_A, d_Bt, d_ll);
+    return HMMB_OK;
+}
+
+template <typename SymT>
+static int launch_score_special(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll) {
+    Ctx &c = ctx();
+    if (s.nblk == 0) return HMMB_OK;
+    // each CTA re-uses one model's B for several 32-utterance blocks
+    int bpc = std::max(BW_WARPS, (s.nblk * W + c.sm_count * 16 - 1) / (c.sm_count * 16));
+    bpc = (bpc + BW_WARPS - 1) / BW_WARPS * BW_WARPS;
+    bpc = std::min(bpc, 64);
+    dim3 g((unsigned)((s.nblk + bpc - 1) / bpc), (unsigned)W);
+    const size_t smem = (size_t)s.M * 4 * sizeof(double);
+    HMMB_LAUNCH("score", k_score4<SymT>, g, BW_THREADS, smem, s.d_blks, s.nblk, bpc, (const uint4 *)s.d_obs, s.d_len,
+                s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll);
+    return HMMB_OK;
+}
+
+int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets, int64_t U, int W, int N, int M,
+               const double *pi, const double *A, const double *B, double *ll_out, int32_t *argmax_out) {
+    HMMB_TRY(require_init());
+    if (!pi || !A || !B || W <= 0 || W > 65535) { set_error("hmmb_score: bad arguments (W=%d)", W); return HMMB_ERR_ARG; }
+    Ctx &c = ctx();
+    SeqSet s;
+    struct Guard {
+        SeqSet &s; std::vector<void *> ptrs;
+        ~Guard() { s.release(); for (void *p : ptrs) dev_free(p); }
+    } guard{s, {}};
+    HMMB_TRY(seqset_build(s, obs, idx_bytes, obs_on_device, offsets, nullptr, U, 1, N, M, true));
+    if (U == 0) return HMMB_OK;
+    const size_t nB = (size_t)W * N * M, nA = (size_t)W * N * N, nP = (size_t)W * N;
+    double *tmp = nullptr, *d_pi = nullptr, *d_A = nullptr, *d_Bt = nullptr, *d_ll = nullptr;
+    int32_t *d_arg = nullptr;
+    HMMB_TRY(dev_alloc_t(&tmp, nB + nA + nP)); guard.ptrs.push_back(tmp);
+    HMMB_TRY(dev_alloc_t(&d_pi, nP)); guard.ptrs.push_back(d_pi);
+    HMMB_TRY(dev_alloc_t(&d_A, nA)); guard.ptrs.push_back(d_A);
+    HMMB_TRY(dev_alloc_t(&d_Bt, nB)); guard.ptrs.push_back(d_Bt);
+    HMMB_TRY(dev_alloc_t(&d_ll, (size_t)U * W)); guard.ptrs.push_back(d_ll);
+    HMMB_TRY(dev_alloc_t(&d_arg, (size_t)U)); guard.ptrs.push_back(d_arg);
+    HMMB_CUDA(cudaMemcpyAsync(tmp, B, nB * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    HMMB_CUDA(cudaMemcpyAsync(tmp + nB, A, nA * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    HMMB_CUDA(cudaMemcpyAsync(tmp + nB + nA, pi, nP * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    dim3 gb((unsigned)std::min((N * M + 255) / 256, 64), (unsigned)W);
+    HMMB_LAUNCH("score_load", k_load_B, gb, 256, 0, tmp, N, M, d_Bt);
+    HMMB_LAUNCH("score_load", k_load_clamped, (unsigned)std::min<size_t>((nA + 255) / 256, 1024), 256, 0, tmp + nB, (int64_t)nA, d_A);
+    HMMB_LAUNCH("score_load", k_load_clamped, (unsigned)std::min<size_t>((nP + 255) / 256, 1024), 256, 0, tmp + nB + nA, (int64_t)nP, d_pi);
+    int rc;
+    if (s.special4) {
+        rc = s.sym_bytes == 1 ? launch_score_special<uint8_t>(s, W, d_pi, d_A, d_Bt, d_ll)
+                              : launch_score_special<uint16_t>(s, W, d_pi, d_A, d_Bt, d_ll);
+    } else {
+#define GEN(NPV)                                                                                         \
+    case NPV:                                                                                            \
+        rc = s.sym_bytes == 1 ? launch_score_generic<NPV, uint8_t>(s, W, d_pi, d_A, d_Bt, d_ll)         \
+                              : launch_score_generic<NPV, uint16_t>(s, W, d_pi, d_A, d_Bt, d_ll);       \
+        break;
+        switch (s.NP) {
+            GEN(4) GEN(8) GEN(16) GEN(32)
+            default: rc = HMMB_ERR_UNSUPPORTED;
+        }
+#undef GEN
+    }
+    HMMB_TRY(rc);
+    {
+        // precision guard: pairs marked NaN are recomputed in log space
+        int64_t warps = std::min<int64_t>((int64_t)c.sm_count * 16, U);
+        const int eg = (int)std::max<int64_t>(1, (warps + BW_WARPS - 1) / BW_WARPS);
+        if (s.special4) {
+            if (s.sym_bytes == 1)
+                HMMB_LAUNCH("score_exact", (k_score_exact<uint8_t, true>), eg, BW_THREADS, 0, s.d_obs, s.d_foff, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);
+            else
+                HMMB_LAUNCH("score_exact", (k_score_exact<uint16_t, true>), eg, BW_THREADS, 0, s.d_obs, s.d_foff, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);
+        } else {
+            if (s.sym_bytes == 1)
+                HMMB_LAUNCH("score_exact", (k_score_exact<uint8_t, false>), eg, BW_THREADS, 0, s.d_obs, s.d_off, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);
+            else
+                HMMB_LAUNCH("score_exact", (k_score_exact<uint16_t, false>), eg, BW_THREADS, 0, s.d_obs, s.d_off, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);
+        }
+    }
+    HMMB_LAUNCH("score_argmax", k_argmax_first, (unsigned)((U + 255) / 256), 256, 0, d_ll, U, W, d_arg);
+    if (ll_out) HMMB_CUDA(cudaMemcpyAsync(ll_out, d_ll, (size_t)U * W * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (argmax_out) HMMB_CUDA(cudaMemcpyAsync(argmax_out, d_arg, (size_t)U * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    return HMMB_OK;
+}
+

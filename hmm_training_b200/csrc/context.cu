@@ -1,0 +1,267 @@
+// Context, error reporting, caching allocator and phase timers of libhmmb200.
+#include "common.cuh"
+
+namespace hmmb {
+
+static thread_local char g_err[1024] = "";
+static Ctx g_ctx;
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return e == cudaErrorMemoryAllocation ? HMMB_ERR_OOM : HMMB_ERR_CUDA;
+}
+
+Ctx &ctx() { return g_ctx; }
+
+int require_init() {
+    if (g_ctx.inited) return HMMB_OK;
+    return hmmb_init(-1);
+}
+
+int dev_alloc(void **p, size_t bytes) {
+    Ctx &c = g_ctx;
+    if (bytes == 0) bytes = 256;
+    bytes = (bytes + 255) & ~size_t(255);
+    auto it = c.free_blocks.lower_bound(bytes);
+    if (it != c.free_blocks.end() && it->first <= bytes + bytes / 4 + (1 << 20)) {
+        *p = it->second;
+        c.live_blocks[*p] = it->first;
+        c.free_blocks.erase(it);
+        return HMMB_OK;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        dev_release_cache();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        *p = nullptr;
+        return HMMB_ERR_OOM;
+    }
+    c.live_blocks[*p] = bytes;
+    return HMMB_OK;
+}
+
+void dev_free(void *p) {
+    if (!p) return;
+    Ctx &c = g_ctx;
+    auto it = c.live_blocks.find(p);
+    if (it == c.live_blocks.end()) return;
+    c.free_blocks.insert({it->second, p});
+    c.live_blocks.erase(it);
+}
+
+void dev_release_cache() {
+    Ctx &c = g_ctx;
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    for (auto &kv : c.free_blocks) cudaFree(kv.second);
+    c.free_blocks.clear();
+}
+
+int phase_id(const char *name) {
+    Ctx &c = g_ctx;
+    for (size_t i = 0; i < c.phase_names.size(); ++i)
+        if (c.phase_names[i] == name) return (int)i;
+    c.phase_names.push_back(name);
+    c.phase_ms.push_back(0.0);
+    c.phase_n.push_back(0);
+    return (int)c.phase_names.size() - 1;
+}
+
+static cudaEvent_t get_event() {
+    Ctx &c = g_ctx;
+    if (!c.event_pool.empty()) {
+        cudaEvent_t e = c.event_pool.back();
+        c.event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void phase_begin(int id) {
+    Ctx &c = g_ctx;
+    PhaseRec r;
+    r.phase = id;
+    r.a = get_event();
+    r.b = get_event();
+    cudaEventRecord(r.a, c.stream);
+    c.pending.push_back(r);
+}
+
+void phase_end(int id) {
+    Ctx &c = g_ctx;
+    (void)id;
+    cudaEventRecord(c.pending.back().b, c.stream);
+    if (c.pending.size() > 4096) phase_collect();
+}
+
+int phase_collect() {
+    Ctx &c = g_ctx;
+    if (c.pending.empty()) return HMMB_OK;
+    HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    for (auto &r : c.pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            c.phase_ms[r.phase] += ms;
+            c.phase_n[r.phase] += 1;
+        }
+        c.event_pool.push_back(r.a);
+        c.event_pool.push_back(r.b);
+    }
+    c.pending.clear();
+    return HMMB_OK;
+}
+
+}  // namespace hmmb
+
+using namespace hmmb;
+
+extern "C" {
+
+int hmmb_init(int device) {
+    Ctx &c = ctx();
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        set_error("no CUDA device available (%s); libhmmb200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return HMMB_ERR_CUDA;
+    }
+    if (device < 0) {
+        if (c.inited) return HMMB_OK;
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= count) {
+        set_error("device %d out of range (%d devices)", device, count);
+        return HMMB_ERR_ARG;
+    }
+    if (c.inited && c.device == device) return HMMB_OK;
+    if (c.inited) hmmb_shutdown();
+    HMMB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HMMB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    c.cc_major = prop.major;
+    c.cc_minor = prop.minor;
+    c.smem_optin = prop.sharedMemPerBlockOptin;
+    c.global_mem = (int64_t)prop.totalGlobalMem;
+    HMMB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
+    c.inited = true;
+    return HMMB_OK;
+}
+
+int hmmb_shutdown(void) {
+    Ctx &c = ctx();
+    if (!c.inited) return HMMB_OK;
+    cudaSetDevice(c.device);
+    phase_collect();
+    dev_release_cache();
+    for (auto &kv : c.live_blocks) cudaFree(kv.first);
+    c.live_blocks.clear();
+    for (auto ev : c.event_pool) cudaEventDestroy(ev);
+    c.event_pool.clear();
+    if (c.own_stream) cudaStreamDestroy(c.own_stream);
+    c.own_stream = c.stream = nullptr;
+    c.inited = false;
+    return HMMB_OK;
+}
+
+const char *hmmb_last_error(void) { return g_err; }
+
+const char *hmmb_version(void) { return "hmmb200 0.1 (sm_100a)"; }
+
+int hmmb_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *global_mem_bytes) {
+    HMMB_TRY(require_init());
+    Ctx &c = ctx();
+    if (sm_count) *sm_count = c.sm_count;
+    if (cc_major) *cc_major = c.cc_major;
+    if (cc_minor) *cc_minor = c.cc_minor;
+    if (global_mem_bytes) *global_mem_bytes = c.global_mem;
+    return HMMB_OK;
+}
+
+int hmmb_set_stream(void *cuda_stream) {
+    HMMB_TRY(require_init());
+    Ctx &c = ctx();
+    phase_collect();
+    c.stream = cuda_stream ? (cudaStream_t)cuda_stream : c.own_stream;
+    return HMMB_OK;
+}
+
+void *hmmb_get_stream(void) {
+    if (require_init() != HMMB_OK) return nullptr;
+    return (void *)ctx().stream;
+}
+
+int hmmb_synchronize(void) {
+    HMMB_TRY(require_init());
+    HMMB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return HMMB_OK;
+}
+
+void *hmmb_host_alloc(int64_t bytes) {
+    if (require_init() != HMMB_OK) return nullptr;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("pinned host allocation of %lld bytes failed", (long long)bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+int hmmb_host_free(void *p) {
+    if (!p) return HMMB_OK;
+    HMMB_CUDA(cudaFreeHost(p));
+    return HMMB_OK;
+}
+
+int64_t hmmb_launch_count(void) { return ctx().launches; }
+
+double hmmb_phase_ms(const char *phase, int64_t *launches) {
+    Ctx &c = ctx();
+    if (!c.inited) return -1.0;
+    phase_collect();
+    for (size_t i = 0; i < c.phase_names.size(); ++i)
+        if (c.phase_names[i] == phase) {
+            if (launches) *launches = c.phase_n[i];
+            return c.phase_n[i] ? c.phase_ms[i] : -1.0;
+        }
+    if (launches) *launches = 0;
+    return -1.0;
+}
+
+int hmmb_phase_reset(void) {
+    Ctx &c = ctx();
+    if (!c.inited) return HMMB_OK;
+    phase_collect();
+    for (size_t i = 0; i < c.phase_ms.size(); ++i) {
+        c.phase_ms[i] = 0.0;
+        c.phase_n[i] = 0;
+    }
+    return HMMB_OK;
+}
+
+int hmmb_set_profiling(int enabled) {
+    HMMB_TRY(require_init());
+    phase_collect();
+    ctx().profiling = enabled != 0;
+    return HMMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+// VQ encode and LBG (binary-split k-means) codebook kernels for sm_100a.
+//
+// Replaces (reference paths relative to the reference root):
+//   get_observations ........ HMM/hmm_training.py:82-120
+//   createCodeVector ........ CodeVector/codevector_functions.py:442-531
+//   new_epsilon_centroids ... CodeVector/codevector_functions.py:383-411
+//   new_adjust_centroids .... CodeVector/codevector_functions.py:414-439
+//
+// Arithmetic contract (bit-exact indices): the reference computes
+// np.linalg.norm(x[1:] - c[1:]) = sqrt(dot(d, d)); with the image's numpy/OpenBLAS the
+// 12-term dot is the sequential FMA chain acc = fma(d_i, d_i, acc), i = 1..12.  The kernel
+// evaluates exactly that chain in fp64 (__dsub_rn + __fma_rn, no re-association), compares
+// with strict '<' on the square root (only evaluated when the squared distance improves),
+// so the lowest index wins ties exactly as at hmm_training.py:112.
+//
+// Roofline: 12 DADD + 12 DFMA per (frame, centroid) pair -> FP64-pipe bound
+// (AI ~ 85 flop/B); HBM traffic is 104 B in + 4 B out per frame.
+#include "common.cuh"
+
+namespace hmmb {
+
+constexpr int VQ_THREADS = 256;
+constexpr int VQ_TILE = 512;  // centroids per shared-memory tile: 512 * 12 * 8 B = 48 KB
+constexpr int VQ_D = 12;      // dims 1..12 take part in the distance
+constexpr int ACC_W = 14;     // per-centroid accumulator row: 13 sums + count
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// MODE 0: encode only.  MODE 1: LBG pass = encode + per-centroid 13-dim sums, counts and
+// the sum of winning distances, reduced in shared memory and flushed once per CTA.
+template <int MODE>
+__global__ void __launch_bounds__(VQ_THREADS)
+k_vq_assign(const double *__restrict__ X, int64_t F, const double *__restrict__ C, int K,
+            int32_t *__restrict__ idx_out, double *__restrict__ dist_out, double *__restrict__ accum,
+            int smem_accum) {
+    extern __shared__ double smem[];
+    double *sC = smem;                              // [tile][12]
+    double *sAcc = smem + (size_t)VQ_TILE * VQ_D;   // [K][14] (MODE 1, if smem_accum)
+    __shared__ double sRed[VQ_THREADS / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (MODE == 1 && smem_accum) {
+        for (int e = tid; e < K * ACC_W; e += VQ_THREADS) sAcc[e] = 0.0;
+    }
+    double dist_local = 0.0;
+    const int ntiles = (K + VQ_TILE - 1) / VQ_TILE;
+    const int64_t nbatch = (F + VQ_THREADS - 1) / VQ_THREADS;
+
+    for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+        const int64_t f = batch * VQ_THREADS + tid;
+        const bool valid = f < F;
+        double x[13];
+#pragma unroll
+        for (int d = 0; d < 13; ++d) x[d] = valid ? __ldg(X + f * 13 + d) : 0.0;
+
+        double best_d2 = pos_inf(), best_s = pos_inf();
+        int best = 0;
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const int k0 = tile * VQ_TILE;
+            const int kt = min(VQ_TILE, K - k0);
+            if (ntiles > 1 || batch == blockIdx.x) {
+                __syncthreads();
+                for (int e = tid; e < kt * VQ_D; e += VQ_THREADS) {
+                    int k = e / VQ_D, d = e - k * VQ_D;
+                    sC[e] = __ldg(C + (size_t)(k0 + k) * 13 + 1 + d);
+                }
+                __syncthreads();
+            }
+            int k = 0;
+            for (; k + 4 <= kt; k += 4) {
+                const double2 *c0 = reinterpret_cast<const double2 *>(sC + (size_t)k * VQ_D);
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                for (int q = 0; q < VQ_D / 2; ++q) {
+                    double2 p0 = c0[q], p1 = c0[q + 6], p2 = c0[q + 12], p3 = c0[q + 18];
+                    double v;
+                    v = __dsub_rn(x[1 + 2 * q], p0.x); a0 = __fma_rn(v, v, a0);
+                    v = __dsub_rn(x[2 + 2 * q], p0.y); a0 = __fma_rn(v, v, a0);
+                    v = __dsub_rn(x[1 + 2 * q], p1.x); a1 = __fma_rn(v, v, a1);
+                    v = __dsub_rn(x[2 + 2 * q], p1.y); a1 = __fma_rn(v, v, a1);
+                    v = __dsub_rn(x[1 + 2 * q], p2.x); a2 = __fma_rn(v, v, a2);
+                    v = __dsub_rn(x[2 + 2 * q], p2.y); a2 = __fma_rn(v, v, a2);
+                    v = __dsub_rn(x[1 + 2 * q], p3.x); a3 = __fma_rn(v, v, a3);
+                    v = __dsub_rn(x[2 + 2 * q], p3.y); a3 = __fma_rn(v, v, a3);
+                }
+                // in index order; sqrt only when the squared distance improves
+                if (a0 < best_d2) { double s = sqrt(a0); if (s < best_s) { best_s = s; best_d2 = a0; best = k0 + k; } }
+                if (a1 < best_d2) { double s = sqrt(a1); if (s < best_s) { best_s = s; best_d2 = a1; best = k0 + k + 1; } }
+                if (a2 < best_d2) { double s = sqrt(a2); if (s < best_s) { best_s = s; best_d2 = a2; best = k0 + k + 2; } }
+                if (a3 < best_d2) { double s = sqrt(a3); if (s < best_s) { best_s = s; best_d2 = a3; best = k0 + k + 3; } }
+            }
+            for (; k < kt; ++k) {
+                const double *c = sC + (size_t)k * VQ_D;
+                double a = 0.0;
+#pragma unroll
+                for (int d = 0; d < VQ_D; ++d) {
+                    double v = __dsub_rn(x[1 + d], c[d]);
+                    a = __fma_rn(v, v, a);
+                }
+                if (a < best_d2) { double s = sqrt(a); if (s < best_s) { best_s = s; best_d2 = a; best = k0 + k; } }
+            }
+        }
+        if (valid) {
+            if (idx_out) idx_out[f] = best;
+            if (dist_out) dist_out[f] = best_s;
+        }
+        if (MODE == 1) {
+            if (valid) dist_local += best_s;
+            double *acc = smem_accum ? sAcc : accum;
+            if (K <= 16) {
+                // few centroids: every lane hits the same handful of rows, so reduce per
+                // key across the warp with shuffles and issue one atomic per (key, dim).
+                unsigned remaining = __ballot_sync(0xffffffffu, valid);
+                while (remaining) {
+                    int leader = __ffs(remaining) - 1;
+                    int key = __shfl_sync(0xffffffffu, best, leader);
+                    bool mine = valid && best == key;
+                    unsigned m = __ballot_sync(0xffffffffu, mine);
+                    remaining &= ~m;
+#pragma unroll
+                    for (int d = 0; d < 13; ++d) {
+                        double v = warp_sum(mine ? x[d] : 0.0);
+                        if (lane == 0) atomicAdd(acc + key * ACC_W + d, v);
+                    }
+                    if (lane == 0) atomicAdd(acc + key * ACC_W + 13, (double)__popc(m));
+                }
+            } else if (valid) {
+#pragma unroll
+                for (int d = 0; d < 13; ++d) atomicAdd(acc + best * ACC_W + d, x[d]);
+                atomicAdd(acc + best * ACC_W + 13, 1.0);
+            }
+        }
+    }
+    if (MODE == 1) {
+        double v = warp_sum(dist_local);
+        if (lane == 0) sRed[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < VQ_THREADS / 32; ++w) s += sRed[w];
+            atomicAdd(accum + (size_t)K * ACC_W, s);
+        }
+        if (smem_accum) {
+            for (int e = tid; e < K * ACC_W; e += VQ_THREADS) {
+                double a = sAcc[e];
+                if (a != 0.0) atomicAdd(accum + e, a);
+            }
+        }
+    }
+}
+
+// new_adjust_centroids: mean of the assigned frames (all 13 dims), zeros(13) if empty.
+__global__ void k_lbg_update(const double *__restrict__ accum, int K, double *__restrict__ C) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= K * 13) return;
+    int k = e / 13, d = e - k * 13;
+    double n = accum[k * ACC_W + 13];
+    C[e] = n > 0.0 ? accum[k * ACC_W + d] / n : 0.0;
+}
+
+// new_epsilon_centroids: centroid i -> 2i = c * 1.001, 2i+1 = c * 0.999 (all 13 dims).
+__global__ void k_lbg_split(const double *__restrict__ C, int K, double *__restrict__ C2) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= K * 13) return;
+    int k = e / 13, d = e - k * 13;
+    double v = C[e];
+    C2[(size_t)(2 * k) * 13 + d] = v * 1.001;
+    C2[(size_t)(2 * k + 1) * 13 + d] = v * 0.999;
+}
+
+static size_t vq_smem_bytes(int K, int mode, int *smem_accum) {
+    size_t tile = (size_t)VQ_TILE * VQ_D * sizeof(double);
+    size_t acc = (size_t)K * ACC_W * sizeof(double);
+    *smem_accum = 0;
+    if (mode == 1 && tile + acc <= 200 * 1024) {
+        *smem_accum = 1;
+        return tile + acc;
+    }
+    return tile;
+}
+
+static int vq_launch(int mode, const double *dX, int64_t F, const double *dC, int K, int32_t *d_idx,
+                     double *d_dist, double *d_accum) {
+    Ctx &c = ctx();
+    int smem_accum = 0;
+    size_t smem = vq_smem_bytes(K, mode, &smem_accum);
+    int64_t nbatch = (F + VQ_THREADS - 1) / VQ_THREADS;
+    if (nbatch == 0) return HMMB_OK;
+    // persistent-style grid: a multiple of the SM count, each CTA strides over frame batches
+    int per_sm = smem > 100 * 1024 ? 1 : (smem > 60 * 1024 ? 3 : 4);
+    int64_t grid = (int64_t)c.sm_count * per_sm * (mode == 1 ? 1 : 4);
+    if (grid > nbatch) grid = nbatch;
+    if (mode == 0) {
+        HMMB_CUDA(cudaFuncSetAttribute(k_vq_assign<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HMMB_LAUNCH("vq_encode", k_vq_assign<0>, (unsigned)grid, VQ_THREADS, smem, dX, F, dC, K, d_idx, d_dist,
+                    d_accum, smem_accum);
+    } else {
+        HMMB_CUDA(cudaFuncSetAttribute(k_vq_assign<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HMMB_LAUNCH("lbg_assign", k_vq_assign<1>, (unsigned)grid, VQ_THREADS, smem, dX, F, dC, K, d_idx, d_dist,
+                    d_accum, smem_accum);
+    }
+    return HMMB_OK;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { dev_free(p); }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace hmmb
+
+using namespace hmmb;
+
+extern "C" {
+
+int hmmb_vq_encode_dev(const double *dX, int64_t F, const double *dC, int K, int32_t *d_idx, double *d_dist) {
+    HMMB_TRY(require_init());
+    if (F < 0 || K <= 0 || !dC || (F > 0 && (!dX || !d_idx))) {
+        set_error("hmmb_vq_encode_dev: bad arguments (F=%lld, K=%d)", (long long)F, K);
+        return HMMB_ERR_ARG;
+    }
+    return vq_launch(0, dX, F, dC, K, d_idx, d_dist, nullptr);
+}
+
+int hmmb_vq_encode(const double *X, int64_t F, const double *C, int K, int32_t *idx_out) {
+    HMMB_TRY(require_init());
+    if (F < 0 || K <= 0 || !C || (F > 0 && (!X || !idx_out))) {
+        set_error("hmmb_vq_encode: bad arguments (F=%lld, K=%d)", (long long)F, K);
+        return HMMB_ERR_ARG;
+    }
+    if (F == 0) return HMMB_OK;
+    Ctx &c = ctx();
+    DevBuf dX, dC, dI;
+    HMMB_TRY(dev_alloc(&dX.p, (size_t)F * 13 * sizeof(double)));
+    HMMB_TRY(dev_alloc(&dC.p, (size_t)K * 13 * sizeof(double)));
+    HMMB_TRY(dev_alloc(&dI.p, (size_t)F * sizeof(int32_t)));
+    HMMB_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)F * 13 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    HMMB_CUDA(cudaMemcpyAsync(dC.p, C, (size_t)K * 13 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    HMMB_TRY(vq_launch(0, dX.as<double>(), F, dC.as<double>(), K, dI.as<int32_t>(), nullptr, nullptr));
+    HMMB_CUDA(cudaMemcpyAsync(idx_out, dI.p, (size_t)F * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    return HMMB_OK;
+}
+
+int hmmb_lbg_fit(const double *X, int64_t F, int x_on_device, int K, int max_iter, double eps, double *C_out,
+                 double *gens_out, int32_t *assign_out, int32_t *iters_per_gen, double *gdist_out,
+                 hmmb_allreduce_fn allreduce, void *user) {
+    HMMB_TRY(require_init());
+    if (F <= 0 && !allreduce) {
+        set_error("No raw data provided");  // codevector_functions.py:445-446
+        return HMMB_ERR_EMPTY;
+    }
+    if (K <= 0 || !C_out || !gens_out || (F > 0 && !X) || F < 0) {
+        set_error("hmmb_lbg_fit: bad arguments (F=%lld, K=%d)", (long long)F, K);
+        return HMMB_ERR_ARG;
+    }
+    Ctx &c = ctx();
+    int n_gen = 0;
+    while ((2 << n_gen) <= K) ++n_gen;  // floor(log2 K)
+    const int Kmax = 1 << (n_gen > 0 ? n_gen : 1);
+    DevBuf dXb, dCa, dCb, dI, dAcc;
+    const double *dX = X;
+    if (!x_on_device && F > 0) {
+        HMMB_TRY(dev_alloc(&dXb.p, (size_t)F * 13 * sizeof(double)));
+        HMMB_CUDA(cudaMemcpyAsync(dXb.p, X, (size_t)F * 13 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        dX = dXb.as<double>();
+    }
+    HMMB_TRY(dev_alloc(&dCa.p, (size_t)Kmax * 13 * sizeof(double)));
+    HMMB_TRY(dev_alloc(&dCb.p, (size_t)Kmax * 13 * sizeof(double)));
+    HMMB_TRY(dev_alloc(&dI.p, (size_t)(F > 0 ? F : 1) * sizeof(int32_t)));
+    const size_t acc_n = (size_t)Kmax * ACC_W + 2;
+    HMMB_TRY(dev_alloc(&dAcc.p, acc_n * sizeof(double)));
+    double *cur = dCa.as<double>(), *nxt = dCb.as<double>();
+    double *acc = dAcc.as<double>();
+    int32_t *d_idx = dI.as<int32_t>();
+    std::vector<double> hC((size_t)Kmax * 13);
+
+    // C0 = mean of all frames (:458-459): one accumulate pass against a single zero centroid
+    HMMB_CUDA(cudaMemsetAsync(cur, 0, 13 * sizeof(double), c.stream));
+    HMMB_CUDA(cudaMemsetAsync(acc, 0, acc_n * sizeof(double), c.stream));
+    HMMB_TRY(vq_launch(1, dX, F, cur, 1, d_idx, nullptr, acc));
+    if (allreduce) {
+        int rc = allreduce(acc, ACC_W + 1, user);
+        if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+    }
+    HMMB_LAUNCH("lbg_update", k_lbg_update, 1, 32, 0, acc, 1, cur);
+    size_t gpos = 0;
+    HMMB_CUDA(cudaMemcpyAsync(gens_out, cur, 13 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    gpos += 13;
+    HMMB_LAUNCH("lbg_split", k_lbg_split, 1, 32, 0, cur, 1, nxt);  // :469
+    { double *t = cur; cur = nxt; nxt = t; }
+    int Kg = 2;
+    HMMB_CUDA(cudaMemsetAsync(d_idx, 0, (size_t)(F > 0 ? F : 1) * sizeof(int32_t), c.stream));
+
+    for (int g = 1; g <= n_gen; ++g) {
+        double prev = 0.0, diff = eps + 100.0, gd = 0.0;  // :475-476
+        int it = 0;
+        while (diff > eps && it < max_iter) {  // :485
+            ++it;
+            HMMB_CUDA(cudaMemsetAsync(acc, 0, ((size_t)Kg * ACC_W + 1) * sizeof(double), c.stream));
+            HMMB_TRY(vq_launch(1, dX, F, cur, Kg, d_idx, nullptr, acc));
+            if (allreduce) {
+                int rc = allreduce(acc, (int64_t)Kg * ACC_W + 1, user);
+                if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+            }
+            HMMB_LAUNCH("lbg_update", k_lbg_update, (Kg * 13 + 127) / 128, 128, 0, acc, Kg, nxt);
+            HMMB_CUDA(cudaMemcpyAsync(&gd, acc + (size_t)Kg * ACC_W, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+            HMMB_CUDA(cudaStreamSynchronize(c.stream));
+            { double *t = cur; cur = nxt; nxt = t; }
+            diff = fabs(prev - gd);  // :509-510
+            prev = gd;
+        }
+        if (iters_per_gen) iters_per_gen[g - 1] = it;
+        if (gdist_out) gdist_out[g - 1] = gd;
+        HMMB_CUDA(cudaMemcpyAsync(gens_out + gpos, cur, (size_t)Kg * 13 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        gpos += (size_t)Kg * 13;
+        if (g < n_gen) {  // :520-521
+            HMMB_LAUNCH("lbg_split", k_lbg_split, (Kg * 13 + 127) / 128, 128, 0, cur, Kg, nxt);
+            { double *t = cur; cur = nxt; nxt = t; }
+            Kg *= 2;
+        }
+    }
+    HMMB_CUDA(cudaMemcpyAsync(C_out, cur, (size_t)Kg * 13 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (assign_out && F > 0)
+        HMMB_CUDA(cudaMemcpyAsync(assign_out, d_idx, (size_t)F * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    return Kg;
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+/* hmmb200 — C ABI of the B200-native HMM hot path (libhmmb200.so).
+ *
+ * The reference (DemianMArin/HMM_Training) is pure Python and has no FFI of its own; its
+ * hot path sits behind plain Python functions.  Each entry point below names the reference
+ * function (file:line, relative to the reference root) whose arithmetic it replaces; the
+ * Python shims in hmm_training_b200/ keep the reference's signatures and call these through
+ * ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; host buffers are caller-owned unless a parameter is
+ *     documented as a device pointer; matrices are C-contiguous fp64.
+ *   - every function returns HMMB_OK (0) or a negative HMMB_ERR_* code;
+ *     hmmb_last_error() returns a thread-local message for the last failure.
+ *   - one context per process per GPU (hmmb_init); the library is NOT thread-safe.
+ *   - all kernels are launched on one stream (hmmb_set_stream / hmmb_get_stream).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     HMMB_ERR_CUDA.
+ */
+#ifndef HMMB200_H
+#define HMMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMMB_OK 0
+#define HMMB_ERR_CUDA (-1)        /* CUDA runtime failure / no device                        */
+#define HMMB_ERR_ARG (-2)         /* invalid argument                                        */
+#define HMMB_ERR_OOM (-3)         /* device or host allocation failed                        */
+#define HMMB_ERR_EMPTY (-4)       /* empty input: T == 0 sequence (reference: IndexError,    */
+                                  /* hmm_training.py:376) or no frames (ValueError,          */
+                                  /* codevector_functions.py:445)                            */
+#define HMMB_ERR_RANGE (-5)       /* codeword >= M (reference: IndexError on log_b_matrix)   */
+#define HMMB_ERR_UNSUPPORTED (-6) /* outside documented limits (N > 32, M > 65536, ...)      */
+
+#define HMMB_DIM 13               /* MFCC vector length (codevector_classes.py:211)          */
+#define HMMB_MAX_STATES 32
+
+/* ------------------------------------------------------------------ context */
+int hmmb_init(int device);                 /* select device, create stream + workspace      */
+int hmmb_shutdown(void);                   /* free workspace, destroy stream                */
+const char *hmmb_last_error(void);
+const char *hmmb_version(void);
+int hmmb_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *global_mem_bytes);
+int hmmb_set_stream(void *cuda_stream);    /* NULL restores the library's own stream        */
+void *hmmb_get_stream(void);
+int hmmb_synchronize(void);
+/* pinned host memory for callers that want async H2D/D2H */
+void *hmmb_host_alloc(int64_t bytes);
+int hmmb_host_free(void *p);
+/* kernels launched by this library since hmmb_init (the "gpu_launches" claim in bench.py) */
+int64_t hmmb_launch_count(void);
+/* elapsed ms of the last call's named phase, measured with CUDA events on the stream:
+ * "vq_encode", "lbg_assign", "bw_forward", "bw_backward", "bw_reduce", "bw_mstep", "score";
+ * negative if the phase has not run.  Accumulated over launches; *launches gets the count. */
+double hmmb_phase_ms(const char *phase, int64_t *launches);
+int hmmb_phase_reset(void);
+int hmmb_set_profiling(int enabled);       /* event timing around every kernel (default off) */
+
+/* Sum-allreduce hook for the multi-GPU path: called between the E-step and the M-step
+ * (and once per Lloyd pass) with a DEVICE buffer of n doubles that must be summed in place
+ * across ranks, ordered after all work already queued on hmmb_get_stream().  The Python
+ * shim implements it with torch.distributed.all_reduce over NCCL.  NULL = single GPU. */
+typedef int (*hmmb_allreduce_fn)(void *dev_buf, int64_t n_doubles, void *user);
+
+/* ------------------------------------------------------------------ VQ encode
+ * Replaces get_observations, HMM/hmm_training.py:82-120: per frame argmin_k of
+ * sqrt(sum_{d=1..12} (x_d - c_kd)^2), strict '<' (lowest index wins ties); dimension 0
+ * (energy) is ignored (:100,:107).  X [F,13], C [K,13] fp64 -> idx_out [F] int32.        */
+int hmmb_vq_encode(const double *X, int64_t F, const double *C, int K, int32_t *idx_out);
+/* same on device-resident buffers; d_dist (nullable) receives the winning distance       */
+int hmmb_vq_encode_dev(const double *dX, int64_t F, const double *dC, int K, int32_t *d_idx,
+                       double *d_dist);
+
+/* ------------------------------------------------------------------ LBG codebook
+ * Replaces createCodeVector, CodeVector/codevector_functions.py:442-531 (with
+ * new_epsilon_centroids :383-411 and new_adjust_centroids :414-439).  K =
+ * centroids_quantity; n_gen = floor(log2 K); the call returns Kout = 2^max(n_gen,1), the
+ * number of rows written to C_out, or a negative error.
+ *   C_out [Kout,13]; gens_out [(1 + 2 + ... + 2^n_gen), 13] = [C0] + converged centroids of
+ *   each generation (:466,:517); assign_out [F] = frame.parent_centroid_id (:502);
+ *   iters_per_gen [n_gen]; gdist_out [n_gen] (nullable) last sum of min distances (:503).
+ * x_on_device != 0: X is a device pointer (frames already resident in HBM).
+ * Multi-GPU: every rank passes its shard of frames and the same hook; sums/counts/distance
+ * are all-reduced once per Lloyd pass.                                      */
+int hmmb_lbg_fit(const double *X, int64_t F, int x_on_device, int K, int max_iter, double eps,
+                 double *C_out, double *gens_out, int32_t *assign_out, int32_t *iters_per_gen,
+                 double *gdist_out, hmmb_allreduce_fn allreduce, void *user);
+
+/* ------------------------------------------------------------------ Baum-Welch
+ * Replaces hmm_training, HMM/hmm_training.py:265-541, batched over W word models:
+ * E-step (calculate_log_alpha :122-160, calculate_log_beta :163-199, gamma/xi :380-410),
+ * M-step (:412-500, 1e-20 floor :497), convergence statistic (:503-508), exit
+ * normalisation (:524-539).  The reference trains words one at a time; here every word
+ * keeps its own iteration counter and stops exactly where the reference would.
+ *
+ * Sequences are ragged: obs holds all codewords back to back (idx_bytes = 1, 2, 4 or 8 per
+ * codeword, unsigned), sequence r is obs[offsets[r] .. offsets[r+1]) and belongs to word
+ * word_of_seq[r] in [0, W).  Limits: 1 <= N <= 32, 1 <= M <= 65536, T >= 1.            */
+typedef struct hmmb_bw hmmb_bw_t;
+
+int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_device,
+                   const int64_t *offsets, const int32_t *word_of_seq, int64_t R, int W, int N,
+                   int M);
+int hmmb_bw_destroy(hmmb_bw_t *h);
+/* pi0 [W,N], A0 [W,N,N], B0 [W,N,M] linear-space initial parameters; resets iteration state */
+int hmmb_bw_set_params(hmmb_bw_t *h, const double *pi0, const double *A0, const double *B0);
+int hmmb_bw_set_dist(hmmb_bw_t *h, int rank, int world, hmmb_allreduce_fn allreduce, void *user);
+/* run up to n_iter EM iterations (stops early when every word has converged: diff < eps or
+ * max_iter reached, :346).  sync_each != 0 checks the device-side "any word active" flag
+ * after each iteration; 0 queues all n_iter iterations without a host sync.             */
+int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync_each);
+/* finalize != 0 applies the exit normalisation (:529-539).  Outputs: pi [W,N], A [W,N,N],
+ * B [W,N,M]; ll_hist [W,max_iter_cap] per-iteration convergence statistic (NaN-padded),
+ * iters [W]; any output pointer may be NULL.                                              */
+int hmmb_bw_get_params(hmmb_bw_t *h, int finalize, double *pi, double *A, double *B);
+int hmmb_bw_get_history(hmmb_bw_t *h, double *ll_hist, int hist_cap, int32_t *iters);
+/* per-sequence log P(O|lambda) of the last E-step, in input order [R] (:376-377)         */
+int hmmb_bw_get_seq_ll(hmmb_bw_t *h, double *ll_seq);
+int64_t hmmb_bw_total_frames(hmmb_bw_t *h);
+/* precision-guard counters since hmmb_bw_set_params: sequence passes recomputed by the exact
+ * log-space kernel, and sequences handed over by the backward pass (each costs one E-step
+ * redo when hmmb_bw_iterate runs with sync_each != 0; with sync_each == 0 they are only
+ * counted and take effect from the next iteration).                                        */
+int hmmb_bw_diagnostics(hmmb_bw_t *h, int64_t *exact_sequence_passes, int64_t *backward_handovers);
+
+/* one-shot convenience: create + set_params + iterate + get + destroy (host buffers)      */
+int hmmb_bw_fit(const void *obs, int idx_bytes, const int64_t *offsets, const int32_t *word_of_seq,
+                int64_t R, int W, int N, int M, const double *pi0, const double *A0,
+                const double *B0, double eps, int max_iter, double *pi, double *A, double *B,
+                double *ll_hist, int32_t *iters);
+
+/* ------------------------------------------------------------------ recognition
+ * Replaces calculate_log_likelihood, HMM/hmm_testing.py:49-104, and the argmax loop of
+ * test_hmm, :139-161: ll_out [U,W] = log P(O_u | model_w) from LINEAR pi/A/B (zeros are
+ * structural -inf, :67-69); argmax_out [U] = first model with the strictly largest score,
+ * -1 ("unknown", :161) if every score is -inf.  ll_out / argmax_out may be NULL.
+ * obs_on_device != 0: obs is a device pointer; offsets stay on the host.                  */
+int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets, int64_t U,
+               int W, int N, int M, const double *pi, const double *A, const double *B,
+               double *ll_out, int32_t *argmax_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMMB200_H */

@@ -1,0 +1,49 @@
+"""CPU-side checks of the C-ABI boundary: the library builds/loads and exports every symbol
+include/hmmb200.h declares; without a GPU compute calls fail loudly (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from hmm_training_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "hmmb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hmmb_[a-z0-9_]+)\s*\(", src)) - {"hmmb_allreduce_fn"})
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _header_functions()
+    assert len(declared) >= 25
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in hmmb200.h but not exported"
+        assert name in bound, f"{name} declared in hmmb200.h but not bound in _lib.SYMBOLS"
+    assert lib.hmmb_version().decode().startswith("hmmb200")
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from hmm_training_b200 import engine
+    with pytest.raises(_lib.HmmbError) as ei:
+        engine.vq_encode(np.zeros((4, 13)), np.zeros((2, 13)))
+    assert ei.value.code == _lib.ERR_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "hmm_training_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
+                assert "/root/reference" not in text, f"{f} reads the reference tree"

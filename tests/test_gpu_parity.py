@@ -1,0 +1,297 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden vectors and with
+the CPU oracle on seeded inputs.  Needs a GPU: run with ``-m gpu`` on the B200 box.
+
+Tolerances: indices bit-exact; A/B/pi and per-iteration LL within
+|x - ref| <= 1e-9*|ref| + 1e-30; zero pattern of A/pi and the set of floored B entries equal.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_close, assert_same_support, floored_set, load_golden, split_corpus
+from hmm_training_b200 import engine, synthetic
+from oracle import hmm_oracle as O
+from oracle import vq_oracle
+
+pytestmark = pytest.mark.gpu
+
+BW_CASES = ["bw_c1_clustered_s0_it10", "bw_uniform_s1_it3", "bw_clustered_s2_it1", "bw_converge_eps",
+            "bw_warm_n6_m32", "bw_structural_zeros"]
+
+
+@pytest.fixture(params=["special", "generic"])
+def kernel_family(request, monkeypatch):
+    """N=4 goes through the one-sequence-per-thread kernels by default; HMMB_FORCE_GENERIC
+    routes the same inputs through the lanes-per-sequence kernels."""
+    if request.param == "generic":
+        monkeypatch.setenv("HMMB_FORCE_GENERIC", "1")
+    else:
+        monkeypatch.delenv("HMMB_FORCE_GENERIC", raising=False)
+    return request.param
+
+
+def _init_for(g, W, N, M):
+    if "pi0" in g:
+        return g["pi0"], g["A0"], g["B0"]
+    pi, A, B = engine.default_init(N, M)
+    return np.tile(pi, (W, 1)), np.tile(A, (W, 1, 1)), np.tile(B, (W, 1, 1))
+
+
+def _check_bw(name, g, pi, A, B, hist, iters, N, M):
+    W = A.shape[0]
+    assert np.array_equal(iters, g["iters"]), f"{name}: iteration counts {iters} vs {g['iters']}"
+    for w in range(W):
+        it = int(iters[w])
+        assert_close(hist[w, :it], g["ll_hist"][w, :it], f"{name} w{w} ll")
+        assert_close(A[w], g["A"][w], f"{name} w{w} A")
+        assert_close(pi[w], g["pi"][w], f"{name} w{w} pi")
+        assert_close(B[w], g["B"][w], f"{name} w{w} B")
+        assert_same_support(A[w], g["A"][w], f"{name} w{w} A")
+        assert_same_support(pi[w], g["pi"][w], f"{name} w{w} pi")
+        assert np.array_equal(floored_set(B[w], M), floored_set(g["B"][w], M)), f"{name} w{w}: floored B set"
+
+
+@pytest.mark.parametrize("name", BW_CASES)
+def test_baum_welch_matches_reference_golden(name, kernel_family):
+    g = load_golden(name)
+    N, M = int(g["N"]), int(g["M"])
+    W = g["A"].shape[0]
+    pi0, A0, B0 = _init_for(g, W, N, M)
+    pi, A, B, hist, iters = engine.bw_fit(g["obs"], g["offsets"], g["word_of_seq"], W, N, M, pi0, A0, B0,
+                                          epsilon=float(g["epsilon"]), max_iterations=int(g["max_iterations"]))
+    _check_bw(name, g, pi, A, B, hist, iters, N, M)
+
+
+def test_baum_welch_shuffled_sequence_order(kernel_family):
+    """The library sorts sequences by (word, length); interleaved / shuffled input must give
+    the same models (sum order changes only at the 1e-16 level)."""
+    g = load_golden("bw_uniform_s1_it3")
+    N, M = int(g["N"]), int(g["M"])
+    corpus = split_corpus(g)
+    rng = np.random.default_rng(0)
+    seqs = [(w, s) for w, word in enumerate(corpus) for s in word]
+    perm = rng.permutation(len(seqs))
+    obs = np.concatenate([seqs[i][1] for i in perm]).astype(np.int64)  # int64 input path
+    lens = np.array([len(seqs[i][1]) for i in perm])
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    wos = np.array([seqs[i][0] for i in perm], dtype=np.int32)
+    W = len(corpus)
+    pi0, A0, B0 = _init_for(g, W, N, M)
+    pi, A, B, hist, iters = engine.bw_fit(obs, offsets, wos, W, N, M, pi0, A0, B0, max_iterations=3)
+    _check_bw("shuffled", g, pi, A, B, hist, iters, N, M)
+
+
+@pytest.mark.parametrize("N,M,T", [(4, 256, 200), (4, 300, 37), (3, 20, 15), (8, 64, 40), (16, 1024, 50), (32, 128, 12)])
+def test_baum_welch_matches_oracle_seeded(N, M, T):
+    """Seeded synthetic data, random dense + default init, against the numpy oracle."""
+    rng = np.random.default_rng(N * 1000 + M)
+    W, S = 3, 40
+    corpus = [synthetic.clustered_sequences(rng, S, N=N, M=M, tmin=max(1, T - 5), tmax=T + 5, shift=7 * w,
+                                            spread=max(2, M // (2 * N))) for w in range(W)]
+    obs, offsets, wos = synthetic.pack_corpus(corpus, M)
+    pi0 = np.zeros((W, N)); A0 = np.zeros((W, N, N)); B0 = np.zeros((W, N, M))
+    for w in range(W):
+        if w == 0:
+            pi0[w], A0[w], B0[w] = engine.default_init(N, M)
+        else:
+            pi0[w] = rng.dirichlet(np.ones(N)); A0[w] = rng.dirichlet(np.ones(N), size=N)
+            B0[w] = rng.dirichlet(np.ones(M), size=N)
+    iters_max = 4
+    pi, A, B, hist, iters = engine.bw_fit(obs, offsets, wos, W, N, M, pi0, A0, B0, max_iterations=iters_max)
+    for w in range(W):
+        Ao, Bo, pio, h, it = O.hmm_training(corpus[w], N=N, M=M, max_iterations=iters_max,
+                                            init=(pi0[w], A0[w], B0[w]), return_history=True)
+        assert it == iters[w]
+        assert_close(hist[w, :it], h, f"N{N} M{M} w{w} ll")
+        assert_close(A[w], Ao, f"N{N} M{M} w{w} A")
+        assert_close(B[w], Bo, f"N{N} M{M} w{w} B")
+        assert_close(pi[w], pio, f"N{N} M{M} w{w} pi")
+        assert_same_support(A[w], Ao)
+        assert np.array_equal(floored_set(B[w], M), floored_set(Bo, M))
+
+
+def test_baum_welch_is_deterministic():
+    g = load_golden("bw_clustered_s2_it1")
+    N, M, W = 4, 256, 3
+    pi0, A0, B0 = _init_for(g, W, N, M)
+    a = engine.bw_fit(g["obs"], g["offsets"], g["word_of_seq"], W, N, M, pi0, A0, B0, max_iterations=3)
+    b = engine.bw_fit(g["obs"], g["offsets"], g["word_of_seq"], W, N, M, pi0, A0, B0, max_iterations=3)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y, equal_nan=True)  # N=4 path has no atomics: bitwise reproducible
+
+
+def test_baum_welch_errors():
+    pi0, A0, B0 = (x[None] for x in engine.default_init(4, 256))
+    with pytest.raises(IndexError):  # T == 0 (reference: IndexError at hmm_training.py:376)
+        engine.bw_fit(np.array([1, 2, 3], np.uint8), np.array([0, 3, 3]), np.array([0, 0], np.int32), 1, 4, 256,
+                      pi0, A0, B0, max_iterations=1)
+    with pytest.raises(IndexError):  # codeword >= M
+        pi1, A1, B1 = (x[None] for x in engine.default_init(4, 16))
+        engine.bw_fit(np.array([1, 200, 3], np.uint8), np.array([0, 3]), np.array([0], np.int32), 1, 4, 16,
+                      pi1, A1, B1, max_iterations=1)
+
+
+def test_scoring_matches_reference_golden(kernel_family):
+    g = load_golden("score_c1")
+    ll, arg = engine.score(g["obs"], g["offsets"], 4, 256, g["pi"], g["A"], g["B"])
+    assert_close(ll, g["ll"], "score ll")
+    assert np.array_equal(arg, O.argmax_first(g["ll"]))
+
+
+@pytest.mark.parametrize("N,M", [(4, 256), (6, 32), (16, 1024)])
+def test_scoring_matches_oracle_with_structural_zeros(N, M):
+    rng = np.random.default_rng(N + M)
+    W, U = 5, 70
+    pi = rng.dirichlet(np.ones(N), size=W); A = rng.dirichlet(np.ones(N), size=(W, N))
+    B = rng.dirichlet(np.ones(M), size=(W, N))
+    pi[1] = 0; pi[1, 0] = 1.0
+    A[1] = np.triu(A[1]); A[1] /= A[1].sum(axis=1, keepdims=True)
+    B[2, :, : M // 2] = 0.0  # model 2 cannot emit the lower half of the codebook -> many -inf
+    B[3, 0, :] = 0.0
+    seqs = [rng.integers(0, M, size=int(rng.integers(1, 60))) for _ in range(U)]
+    seqs[5] = rng.integers(M // 2, M, size=30)  # possible under model 2
+    obs, offsets = np.concatenate(seqs), np.concatenate([[0], np.cumsum([len(s) for s in seqs])])
+    ll, arg = engine.score(obs.astype(np.int64), offsets, N, M, pi, A, B)
+    ref = O.score_batch(seqs, [(A[w], B[w], pi[w]) for w in range(W)])
+    assert_close(ll, ref, "score")
+    assert np.array_equal(np.isneginf(ll), np.isneginf(ref))
+    assert np.isneginf(ll[:, 2]).sum() > U // 2 and np.isfinite(ll[5, 2])
+    assert np.array_equal(arg, O.argmax_first(ref))
+    allbad = engine.score(np.zeros(4, np.uint8), np.array([0, 4]), N, M, pi[2:3], A[2:3], B[2:3])
+    assert allbad[1][0] == -1 and np.isneginf(allbad[0]).all()  # "unknown" (hmm_testing.py:161)
+
+
+def _tiny_models(rng, W, N, M):
+    """Left-to-right models whose emission rows hold denormal / 1e-300-range / zero entries:
+    what saved reference models look like after safe_exp underflow (hmm_training.py:524-526)."""
+    pi = np.zeros((W, N)); pi[:, 0] = 1.0
+    A = np.zeros((W, N, N))
+    for i in range(N):
+        A[:, i, i] = 0.7
+        A[:, i, min(i + 1, N - 1)] += 0.3
+    B = rng.dirichlet(np.ones(M), size=(W, N))
+    tiny = np.array([1e-300, 3e-310, 1e-320, 4.9e-324, 0.0, 1e-250])
+    for w in range(W):
+        for k in range(M):
+            if k % 3 != w % 3:
+                continue
+            keep = rng.integers(0, N)  # one state keeps a normal probability for this symbol
+            for j in range(N):
+                if j != keep:
+                    B[w, j, k] = tiny[rng.integers(0, len(tiny))]
+    return pi, A, B
+
+
+@pytest.mark.parametrize("N,M", [(4, 16), (6, 16)])
+def test_scoring_with_denormal_emissions(N, M):
+    """Steps whose total probability is ~1e-320 (denormal B on the only live path) must keep
+    the reference's log-space precision (exponent-split slow path)."""
+    rng = np.random.default_rng(11 + N)
+    W, U = 6, 200
+    pi, A, B = _tiny_models(rng, W, N, M)
+    seqs = [rng.integers(0, M, size=int(rng.integers(1, 40))) for _ in range(U)]
+    obs, offsets = np.concatenate(seqs), np.concatenate([[0], np.cumsum([len(s) for s in seqs])])
+    ll, arg = engine.score(obs.astype(np.uint8), offsets, N, M, pi, A, B)
+    ref = O.score_batch(seqs, [(A[w], B[w], pi[w]) for w in range(W)])
+    assert np.isfinite(ref).sum() > 100 and (ref[np.isfinite(ref)] < -700).sum() > 50  # the case is exercised
+    assert np.array_equal(np.isneginf(ll), np.isneginf(ref))
+    assert_close(ll, ref, "denormal scoring")
+    assert np.array_equal(arg, O.argmax_first(ref))
+
+
+@pytest.mark.parametrize("N,M", [(4, 16), (6, 16)])
+def test_training_from_denormal_emissions(N, M):
+    rng = np.random.default_rng(5 + N)
+    W = 3
+    pi0, A0, B0 = _tiny_models(rng, W, N, M)
+    corpus = [[rng.integers(0, M, size=int(rng.integers(2, 30))) for _ in range(30)] for _ in range(W)]
+    obs, offsets, wos = synthetic.pack_corpus(corpus, M)
+    pi, A, B, hist, iters = engine.bw_fit(obs, offsets, wos, W, N, M, pi0, A0, B0, max_iterations=3)
+    for w in range(W):
+        Ao, Bo, pio, h, it = O.hmm_training(corpus[w], N=N, M=M, max_iterations=3, init=(pi0[w], A0[w], B0[w]),
+                                            return_history=True)
+        assert it == iters[w]
+        assert_close(hist[w, :it], h, f"w{w} ll")
+        assert_close(A[w], Ao, f"w{w} A"); assert_close(B[w], Bo, f"w{w} B"); assert_close(pi[w], pio, f"w{w} pi")
+        assert_same_support(A[w], Ao); assert_same_support(pi[w], pio)
+
+
+def test_vq_encode_matches_reference_golden():
+    g = load_golden("vq_2000x256")
+    idx = engine.vq_encode(g["X"], g["C"])
+    assert np.array_equal(idx, g["idx"])
+
+
+@pytest.mark.parametrize("F,K", [(1, 1), (33, 7), (5000, 256), (3000, 700), (257, 1024)])
+def test_vq_encode_matches_oracle(F, K):
+    X = synthetic.mfcc_mixture(F + K, F, K=min(K, 64))
+    C = synthetic.random_codebook(K, K)
+    if K > 3:
+        C[K - 1] = C[1]
+    idx = engine.vq_encode(X, C)
+    assert np.array_equal(idx, vq_oracle.encode(X, C))
+
+
+def test_vq_encode_empty():
+    assert engine.vq_encode(np.zeros((0, 13)), synthetic.random_codebook(0, 4)).shape == (0,)
+
+
+def test_lbg_degenerate_duplicates_near_tie():
+    """60 frames drawn from 3 distinct points: every split puts a point exactly between the
+    twin children c*1.001 / c*0.999, so the winner is decided by the last bit of the centroid
+    mean.  The reference sums frames sequentially (np.mean), the GPU in a tree, so WHICH twin
+    keeps the points may differ (documented near-tie); the multiset of non-empty
+    centroids, the number of all-zero centroids (codevector_functions.py:435) and the
+    partition of the frames must still agree."""
+    g = load_golden("lbg_empty_clusters")
+    C, gens, assign, iters, _ = engine.lbg_fit(g["X"], int(g["K"]), int(g["max_iterations"]), float(g["epsilon"]))
+    assert C.shape == g["C"].shape and np.array_equal(iters, g["iters"])
+    nz, nz_ref = C[np.any(C != 0, axis=1)], g["C"][np.any(g["C"] != 0, axis=1)]
+    assert nz.shape == nz_ref.shape
+    assert_close(nz[np.lexsort(nz.T)], nz_ref[np.lexsort(nz_ref.T)], "non-empty centroids", rtol=1e-9, atol=1e-12)
+    relabel = {}
+    for a, b in zip(assign, g["assign"]):
+        assert relabel.setdefault(int(a), int(b)) == int(b)
+
+
+@pytest.mark.parametrize("name", ["lbg_600_k32", "lbg_1200_k256_it3", "lbg_k1", "lbg_k24_nonpow2"])
+def test_lbg_matches_reference_golden(name):
+    g = load_golden(name)
+    C, gens, assign, iters, _ = engine.lbg_fit(g["X"], int(g["K"]), int(g["max_iterations"]), float(g["epsilon"]))
+    assert C.shape == g["C"].shape
+    assert np.array_equal(iters, g["iters"])
+    assert_close(C, g["C"], "centroids", rtol=1e-9, atol=1e-12)
+    assert_close(np.concatenate(gens), g["gens"], "generations", rtol=1e-9, atol=1e-12)
+    if len(g["iters"]):
+        assert np.array_equal(assign, g["assign"])
+
+
+def test_lbg_no_data():
+    with pytest.raises(ValueError):
+        engine.lbg_fit(np.zeros((0, 13)), 4)
+
+
+def test_large_roundtrip_properties():
+    """BASELINE-size properties that need no oracle: rows sum to 1, VQ idempotence
+    (a centroid encodes to itself or an identical earlier twin), scoring the training
+    data with the trained model reproduces the E-step's per-sequence log-likelihood."""
+    N, M, W, S, T = 4, 256, 10, 2000, 200
+    obs, offsets, wos = synthetic.fixed_length_codewords(0, W, S, T, N, M)
+    pi0, A0, B0 = engine.default_init(N, M)
+    with engine.BaumWelch(obs, offsets, wos, W, N, M) as bw:
+        bw.set_params(np.tile(pi0, (W, 1)), np.tile(A0, (W, 1, 1)), np.tile(B0, (W, 1, 1)))
+        bw.iterate(3, 1e-6, 100)
+        pi_raw, A_raw, B_raw = bw.params(finalize=False)
+        bw.iterate(1, 1e-6, 100)  # E-step with the parameters above; seq_ll belongs to them
+        ll_seq = bw.seq_ll()
+        pi, A, B = bw.params(finalize=True)
+        hist, iters = bw.history(100)
+    assert np.all(iters == 4)
+    assert np.allclose(pi.sum(axis=1), 1) and np.allclose(A.sum(axis=2), 1) and np.allclose(B.sum(axis=2), 1)
+    assert np.all(np.diff(hist[:, :4], axis=1) > -1e-6)  # EM does not decrease the statistic here
+    sub = slice(0, 500)
+    ll, _ = engine.score(obs[: 500 * T], offsets[:501], N, M, pi_raw, A_raw, B_raw)
+    assert_close(ll[np.arange(500), wos[sub]], ll_seq[sub], "E-step LL vs scorer", rtol=1e-12, atol=0)
+    C = synthetic.random_codebook(3, 256)
+    assert np.array_equal(engine.vq_encode(C, C), np.arange(256))

@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Default workload = BASELINE.json config 3: 10-word discrete HMM (N=4, M=256) Baum-Welch over
+100 000 synthetic sequences per word at T=200 (200 M frames per EM iteration), per GPU (weak
+scaling: every rank holds its own shard of that size; the pi/A/B accumulators are combined
+with one NCCL all-reduce per iteration).  One "step" = one full EM iteration (E-step forward +
+backward/accumulate, reduce, all-reduce, M-step) over the whole batch.
+
+Printed JSON (rank 0, one line): metric/value = Baum-Welch frames/s/iteration with the
+codewords resident in HBM; `e2e` = the same through the public packed-array API
+(engine.bw_fit -> hmmb_bw_*) from pinned HOST buffers, H2D/D2H inside the timed region;
+`roofline` for the dominant kernel from CUDA events recorded around every launch on the
+launching stream; `cpu_baseline` = the CPU oracle (numpy port of the reference) on a bounded
+sample using all host cores; secondary blocks `vq_encode`, `lbg`, `score` for the other
+BASELINE configs.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+WORKLOADS = {
+    # name: (W, S per word per GPU, T, N, M)
+    "bw_c3": dict(W=10, S=100_000, T=200, N=4, M=256, desc="config 3: 10 words x 100k seq x T=200, N=4, M=256"),
+    "bw_c4": dict(W=1000, S=500, T=200, N=16, M=1024, desc="config 4: 1000 words x 500 seq x T=200, N=16, M=1024"),
+    "bw_c1": dict(W=10, S=20, T=100, N=4, M=256, desc="config 1: 10 words x 20 seq x T~100 (latency-bound parity config)"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def _cpu_train_word(args):
+    from oracle import hmm_oracle as O
+    seqs, N, M, iters, init = args
+    t = time.perf_counter()
+    O.hmm_training(seqs, N=N, M=M, epsilon=-1.0, max_iterations=iters, init=init)
+    return time.perf_counter() - t
+
+
+def cpu_baum_welch(cfg, seq_per_word: int, iters: int, procs: int):
+    """The CPU oracle (numpy restatement of the reference's log-space Baum-Welch) on a bounded
+    sample of the same workload, one process per word over `procs` host cores."""
+    import multiprocessing as mp
+    from hmm_training_b200 import engine, synthetic
+    W, T, N, M = min(cfg["W"], max(procs, 1) * 2), cfg["T"], cfg["N"], cfg["M"]
+    obs, offsets, wos = synthetic.fixed_length_codewords(12345, W, seq_per_word, T, N, M)
+    init = engine.default_init(N, M)
+    jobs = []
+    for w in range(W):
+        rows = obs.reshape(W * seq_per_word, T)[w * seq_per_word:(w + 1) * seq_per_word]
+        jobs.append(([r.astype(np.int64) for r in rows], N, M, iters, init))
+    t0 = time.perf_counter()
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_train_word, jobs)
+    else:
+        for j in jobs:
+            _cpu_train_word(j)
+    dt = time.perf_counter() - t0
+    frames = W * seq_per_word * T
+    return frames * iters / dt, dt, f"{W} words x {seq_per_word} seq x T={T} (N={N}, M={M}), {iters} EM iterations"
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's algorithm on the host cores.  The reference itself is
+    pure Python and only exists in the build container, so this arm times oracle/ (the
+    validated numpy port, kind="port") with every host core, on the same workload shape."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    spw = int(os.environ.get("HMMB_CPU_SEQ_PER_WORD", "60" if cfg["N"] <= 4 else "4"))
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_baum_welch(cfg, max(spw // 4, 1), 1, cores)
+    vals = []
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, dt, sample = cpu_baum_welch(cfg, spw, 1, cores)
+        vals.append(v)
+    value = float(np.mean(vals))
+    wall = time.perf_counter() - t_all
+    line = {
+        "impl": "reference", "metric": "baum_welch_frames_per_s_per_iter", "value": value, "unit": "frames/s/iter",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s/iter", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bw_c3", choices=list(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's sequences (debug)")
+    ap.add_argument("--no-extras", action="store_true", help="skip VQ / LBG / scoring / CPU-baseline blocks")
+    args = ap.parse_args()
+    cfg = dict(WORKLOADS[args.workload])
+    cfg["S"] = max(1, int(round(cfg["S"] * args.scale)))
+    if args.impl == "reference":
+        run_reference(args, cfg)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from hmm_training_b200 import _lib, engine, synthetic
+    from hmm_training_b200 import dist as hdist
+    lib = _lib.load()
+    _lib.init(local_rank)
+    hdist.bind_torch_stream()
+    hbm_peak, peak_src = measured_peaks()
+
+    W, S, T, N, M = cfg["W"], cfg["S"], cfg["T"], cfg["N"], cfg["M"]
+    obs, offsets, wos = synthetic.fixed_length_codewords(1000 + rank, W, S, T, N, M)
+    frames_rank = int(offsets[-1])
+    pi0, A0, B0 = engine.default_init(N, M)
+    pi0, A0, B0 = np.tile(pi0, (W, 1)), np.tile(A0, (W, 1, 1)), np.tile(B0, (W, 1, 1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = lib.hmmb_launch_count()
+    bw = engine.BaumWelch(obs, offsets, wos, W, N, M)
+    bw.set_params(pi0, A0, B0)
+    if world > 1:
+        bw.set_dist(rank, world, hdist.make_allreduce())
+    cap = args.warmup + args.steps + 8
+    bw.iterate(args.warmup, -1.0, cap, sync_each=False)
+    _lib.check(lib.hmmb_set_profiling(1))
+    _lib.check(lib.hmmb_phase_reset())
+    barrier()
+    l_before = lib.hmmb_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        bw.iterate(args.steps, -1.0, cap, sync_each=False)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    gpu_launches = int(lib.hmmb_launch_count() - l_before)
+    phases = {}
+    for name in ("bw_forward", "bw_exact", "bw_backward", "bw_reduce", "bw_mstep"):
+        pms, n = _lib.phase_ms(name)
+        if n:
+            phases[name] = {"ms_per_launch": pms / n, "launches": n}
+    _lib.check(lib.hmmb_set_profiling(0))
+    exact_passes, bwd_handover = bw.diagnostics()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    frames_total = frames_rank * world
+    value = frames_total / (ms_per_step * 1e-3)
+    bw.close()
+
+    # ---- roofline of the dominant kernel (algorithmic bytes: DESIGN.md §Kernels)
+    sym_b = 1 if M <= 256 else 2
+    alg = {"bw_forward": frames_rank * (sym_b + 8 * N), "bw_backward": frames_rank * (sym_b + 8 * N)}
+    dom = max((k for k in alg if k in phases), key=lambda k: phases[k]["ms_per_launch"], default=None)
+    roofline = None
+    if dom:
+        ach = alg[dom] / (phases[dom]["ms_per_launch"] * 1e-3) / 1e9
+        estep_ms = sum(phases[k]["ms_per_launch"] for k in ("bw_forward", "bw_backward") if k in phases)
+        roofline = {"bound": "hbm", "kernel": "k_bw_bwd" if dom == "bw_backward" else "k_bw_fwd", "achieved": ach,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg[dom],
+                    "estep": {"algorithmic_bytes_per_frame": 2 * sym_b + 16 * N,
+                              "achieved": frames_rank * (2 * sym_b + 16 * N) / (estep_ms * 1e-3) / 1e9,
+                              "frac": frames_rank * (2 * sym_b + 16 * N) / (estep_ms * 1e-3) / 1e9 / hbm_peak},
+                    "phases": phases}
+
+    # ---- e2e: public packed-array API from pinned host buffers, one EM iteration per call
+    e2e = None
+    try:
+        obs_p = torch.empty(obs.shape, dtype=torch.uint8 if obs.dtype == np.uint8 else torch.int16, pin_memory=True)
+        obs_h = obs_p.numpy().view(obs.dtype)
+        obs_h[:] = obs
+        off_h = torch.from_numpy(offsets).pin_memory().numpy()
+        wos_h = torch.from_numpy(wos).pin_memory().numpy()
+        ar = hdist.make_allreduce() if world > 1 else None
+        k_e2e = max(2, min(args.steps, 5))
+        engine.bw_fit(obs_h, off_h, wos_h, W, N, M, pi0, A0, B0, -1.0, 1, allreduce=ar, rank=rank, world=world)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            out = engine.bw_fit(obs_h, off_h, wos_h, W, N, M, pi0, A0, B0, -1.0, 1, allreduce=ar, rank=rank, world=world)
+        barrier()
+        dt = (time.perf_counter() - t0) / k_e2e
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = obs_h.nbytes + off_h.nbytes + wos_h.nbytes + pi0.nbytes + A0.nbytes + B0.nbytes
+        d2h = sum(x.nbytes for x in out)
+        e2e = {"value": frames_total / dt, "unit": "frames/s/iter", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": k_e2e,
+               "api": "engine.bw_fit (hmmb_bw_create/set_params/iterate/get_params) with pinned host buffers, 1 EM iteration per call"}
+    except Exception as exc:  # pragma: no cover
+        e2e = {"error": repr(exc)}
+
+    extras = {}
+    if not args.no_extras and rank == 0:
+        extras = run_extras(torch, lib, _lib, engine, synthetic, hbm_peak, world == 1)
+
+    cpu_baseline = None
+    if world == 1 and not args.no_extras:
+        cores = os.cpu_count() or 1
+        spw = int(os.environ.get("HMMB_CPU_SEQ_PER_WORD", "60" if N <= 4 else "4"))
+        v, dt, sample = cpu_baum_welch(cfg, spw, 1, cores)
+        cpu_baseline = {"value": v, "unit": "frames/s/iter", "cores": cores, "kind": "port", "sample": sample,
+                        "seconds": dt}
+
+    if rank == 0:
+        line = {
+            "metric": "baum_welch_frames_per_s_per_iter", "value": value, "unit": "frames/s/iter", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["desc"], "frames_per_gpu_per_iter": frames_rank, "W": W, "seq_per_word_per_gpu": S,
+                       "T": T, "N": N, "M": M, "parallelism": f"sequences sharded over {world} GPU(s), 1 allreduce/iter",
+                       "l2": "inputs larger than L2 (codewords + alpha spill >> 126 MB)"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
+            "clocks": clk.summary(), "precision_guard": {"exact_sequence_passes": exact_passes,
+                                                         "backward_handovers": bwd_handover},
+        }
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(torch, lib, _lib, engine, synthetic, hbm_peak, with_cpu):
+    """Secondary blocks for BASELINE configs 2 (VQ / LBG, 1M frames) and 5 (recognition)."""
+    out = {}
+    F, K = 1_000_000, 256
+    X = synthetic.mfcc_mixture(0, F, K)
+    C = synthetic.random_codebook(1, K)
+    dX = torch.from_numpy(X).cuda()
+    dC = torch.from_numpy(C).cuda()
+    dI = torch.empty(F, dtype=torch.int32, device="cuda")
+    call = lambda: _lib.check(lib.hmmb_vq_encode_dev(dX.data_ptr(), F, dC.data_ptr(), K, dI.data_ptr(), None))
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    ev0.record()
+    for _ in range(reps):
+        call()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    Xp = torch.from_numpy(X).pin_memory().numpy()
+    engine.vq_encode(Xp, C)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        engine.vq_encode(Xp, C)
+    dt = (time.perf_counter() - t0) / 3
+    flops = F * K * 36.0
+    out["vq_encode"] = {"metric": "vq_encode_frames_per_s", "value": F / (ms * 1e-3), "unit": "frames/s",
+                        "frames": F, "K": K, "ms": ms,
+                        "roofline": {"bound": "fp64", "achieved_tflops": flops / (ms * 1e-3) / 1e12,
+                                     "hbm_achieved_gbs": F * 108 / (ms * 1e-3) / 1e9,
+                                     "hbm_frac": F * 108 / (ms * 1e-3) / 1e9 / hbm_peak,
+                                     "note": "12 DADD + 12 DFMA per frame-centroid pair; FP64-pipe bound (AI ~ 85 flop/B)"},
+                        "e2e": {"value": F / dt, "unit": "frames/s", "h2d_bytes_per_step": int(X.nbytes + C.nbytes),
+                                "d2h_bytes_per_step": 4 * F}}
+    t0 = time.perf_counter()
+    Cb, gens, assign, iters, gd = engine.lbg_fit(None, K, 100, 1e-3, x_dev_ptr=dX.data_ptr(), F=F)
+    dt = time.perf_counter() - t0
+    passes = int(iters.sum())
+    out["lbg"] = {"metric": "lbg_codebook_build_s", "value": dt, "unit": "s", "frames": F, "K": K,
+                  "lloyd_passes": passes, "iters_per_generation": [int(i) for i in iters],
+                  "frame_passes_per_s": F * passes / dt}
+    if with_cpu:
+        from oracle import vq_oracle
+        n = 20000
+        vq_oracle.encode(X[:1000], C)
+        t0 = time.perf_counter()
+        vq_oracle.encode(X[:n], C)
+        dtc = time.perf_counter() - t0
+        out["vq_encode"]["cpu_baseline"] = {"value": n / dtc, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                            "sample": f"{n} frames x K={K} (C oracle, OpenMP)"}
+    del dX, dI
+    # recognition: U utterances x 10 models
+    U, Wm = 1_000_000, 10
+    rng = np.random.default_rng(5)
+    obs, offsets, _ = synthetic.fixed_length_codewords(77, Wm, U // Wm, 100, 4, 256)
+    pi, A, B = engine.default_init(4, 256)
+    Bm = rng.dirichlet(np.ones(256) * 0.3, size=(Wm, 4))
+    pim, Am = np.tile(pi, (Wm, 1)), np.tile(A, (Wm, 1, 1))
+    engine.score(obs[:100 * 1000], offsets[:1001], 4, 256, pim, Am, Bm)
+    t0 = time.perf_counter()
+    ll, arg = engine.score(obs, offsets, 4, 256, pim, Am, Bm)
+    dt = time.perf_counter() - t0
+    out["score"] = {"metric": "recognition_utterances_per_s", "value": U / dt, "unit": "utterances/s (host API, e2e)",
+                    "utterances": U, "models": Wm, "T": 100, "seconds": dt}
+    return out
+
+
+if __name__ == "__main__":
+    main()

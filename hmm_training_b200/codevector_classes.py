@@ -1,0 +1,138 @@
+"""Frame / centroid containers and their JSON + pickle layout, as consumed and produced by the
+hot path (reference: CodeVector/codevector_classes.py — RawDataMFCC :204-279,
+CentroidDataMFCC :321-342, DataStorage :434-597).
+
+Only the data layout is reproduced.  The reference recomputes ``mfcc`` with librosa whenever
+``raw_samples`` is non-empty (:217-220, and therefore also in ``from_dict``, :266-279); MFCC
+extraction is upstream of the hot path so here ``mfcc_vector`` is always taken
+as stored.  Files written by either side load in the other.
+"""
+from __future__ import annotations
+
+import json
+import pickle
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+
+
+@dataclass
+class RawDataMFCC:
+    raw_samples: np.ndarray = field(default_factory=lambda: np.array([]))
+    sample_rate: int = 16000
+    n_channels: int = 1
+    frame_duration_ms: float = 20.0
+    mfcc: np.ndarray = field(default_factory=lambda: np.zeros(13))
+    parent_centroid_id: int = 0
+    generation: int = 0
+    frame_number: int = 0
+    recording: str = ""
+
+    def __post_init__(self):
+        self.raw_samples = np.asarray(self.raw_samples).flatten()
+        self.mfcc = np.asarray(self.mfcc, dtype=float).flatten()
+
+    def to_dict(self):
+        return {"raw_samples": self.raw_samples.tolist(), "sample_rate": self.sample_rate,
+                "n_channels": self.n_channels, "frame_duration_ms": self.frame_duration_ms,
+                "mfcc_vector": self.mfcc.tolist(), "parent_centroid_id": int(self.parent_centroid_id),
+                "generation": int(self.generation), "frame_number": self.frame_number, "recording": self.recording}
+
+    @classmethod
+    def from_dict(cls, data):
+        return cls(raw_samples=np.array(data["raw_samples"]), sample_rate=data["sample_rate"],
+                   n_channels=data["n_channels"], frame_duration_ms=data["frame_duration_ms"],
+                   mfcc=np.array(data["mfcc_vector"]), parent_centroid_id=data["parent_centroid_id"],
+                   generation=data["generation"], frame_number=data["frame_number"], recording=data["recording"])
+
+
+@dataclass
+class CentroidDataMFCC:
+    mfcc: np.ndarray = field(default_factory=lambda: np.zeros(13))
+    id: int = 0
+
+    def to_dict(self):
+        return {"mfcc": np.asarray(self.mfcc).tolist(), "id": int(self.id)}
+
+    @classmethod
+    def from_dict(cls, data):
+        return cls(mfcc=np.array(data["mfcc"]), id=data["id"])
+
+
+class DataStorage:
+    """JSON (indent=2) and pickle I/O with the reference's method names (:438-597)."""
+
+    @staticmethod
+    def save_raw_data(raw_data_list, filepath: str, print_messages=False):
+        with open(filepath, "w") as f:
+            json.dump([frame.to_dict() for frame in raw_data_list], f, indent=2)
+        if print_messages:
+            print(f"    Saved {len(raw_data_list)} frames to {filepath}")
+
+    @staticmethod
+    def load_raw_data_mfcc(filepath: str, data_type: str = "auto", print_messages=True):
+        with open(filepath, "r") as f:
+            data = json.load(f)
+        if not data:
+            return []
+        out = [RawDataMFCC.from_dict(d) for d in data]
+        if print_messages:
+            print(f"  Loaded {len(out)} frames from {filepath}")
+        return out
+
+    @staticmethod
+    def save_centroids(centroids: List[CentroidDataMFCC], filepath: str):
+        with open(filepath, "w") as f:
+            json.dump([c.to_dict() for c in centroids], f, indent=2)
+        print(f"Saved {len(centroids)} centroids to {filepath}")
+
+    @staticmethod
+    def load_centroids(filepath: str, print_messages=True) -> List[CentroidDataMFCC]:
+        with open(filepath, "r") as f:
+            data = json.load(f)
+        centroids = [CentroidDataMFCC.from_dict(d) for d in data]
+        if print_messages:
+            print(f"Loaded {len(centroids)} centroids from {filepath}")
+        return centroids
+
+    @staticmethod
+    def save_generations(generations: List[List[CentroidDataMFCC]], filepath: str):
+        with open(filepath, "w") as f:
+            json.dump([[c.to_dict() for c in gen] for gen in generations], f, indent=2)
+        print(f"Saved {len(generations)} generations to {filepath}")
+
+    @staticmethod
+    def load_generations(filepath: str) -> List[List[CentroidDataMFCC]]:
+        with open(filepath, "r") as f:
+            data = json.load(f)
+        generations = [[CentroidDataMFCC.from_dict(d) for d in gen] for gen in data]
+        print(f"Loaded {len(generations)} generations from {filepath}")
+        return generations
+
+    @staticmethod
+    def save_data_binary(data, filepath: str, print_messages=False):
+        with open(filepath, "wb") as f:
+            pickle.dump(data, f)
+        if print_messages:
+            print(f"    Saved data to {filepath} (binary format)")
+
+    @staticmethod
+    def load_data_binary(filepath: str):
+        with open(filepath, "rb") as f:
+            data = pickle.load(f)
+        print(f"Loaded data from {filepath} (binary format)")
+        return data
+
+
+def frames_matrix(frames) -> np.ndarray:
+    """[F, 13] fp64 matrix of the frames' .mfcc (duck-typed: the reference's own RawDataMFCC
+    objects work as well)."""
+    F = len(frames)
+    X = np.empty((F, 13), dtype=np.float64)
+    for i, fr in enumerate(frames):
+        v = np.asarray(fr.mfcc, dtype=np.float64).reshape(-1)
+        if v.shape[0] != 13:
+            raise ValueError("Vectors must be of size 13.")
+        X[i] = v
+    return X

@@ -11,12 +11,14 @@ namespace hmmb {
 // ---------------------------------------------------------------- small kernels local to this TU
 // B0 [W][N][M] (linear) -> Bt [W][M][N]; non-positive / NaN entries become structural zeros,
 // which is what safe_log does to them (HMM/hmm_training.py:46-54, :323-325).
-__global__ void k_load_B(const double *__restrict__ B, int N, int M, double *__restrict__ Bt) {
+__global__ void k_load_B(const double *__restrict__ B, int N, int M, double *__restrict__ Bt,
+                         int32_t *__restrict__ b_has_zero) {
     const size_t w = blockIdx.y;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < N * M; e += gridDim.x * blockDim.x) {
         const int k = e / N, j = e - k * N;
         const double v = B[(w * N + j) * M + k];
         Bt[w * (size_t)M * N + e] = v > 0.0 ? v : 0.0;
+        if (!(v > 0.0) && b_has_zero) b_has_zero[w] = 1;  // benign race: every writer stores 1
     }
 }
 __global__ void k_load_clamped(const double *__restrict__ src, int64_t n, double *__restrict__ dst) {
@@ -33,7 +35,15 @@ __global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
 }
 
 // ---------------------------------------------------------------- scoring kernels
-template <typename SymT>
+// is every model's A upper-bidiagonal?  (device flag written by k_check_bidiag)
+__global__ void k_check_bidiag(const double *__restrict__ A, int W, int N, int32_t *__restrict__ not_bidiag) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < W * N * N; e += gridDim.x * blockDim.x) {
+        const int ij = e % (N * N), i = ij / N, j = ij % N;
+        if (j != i && j != i + 1 && A[e] > 0.0) *not_bidiag = 1;
+    }
+}
+
+template <bool BIDIAG>
 __global__ void __launch_bounds__(BW_THREADS)
 k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4 *__restrict__ obs_blk,
          const int32_t *__restrict__ len_sorted, const int32_t *__restrict__ order, const double *__restrict__ pi,
@@ -46,9 +56,8 @@ k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4
         double2 *dst = reinterpret_cast<double2 *>(sB);
         for (int e = tid; e < M * 2; e += BW_THREADS) dst[e] = __ldg(src + e);
     }
-    double a[16], p[4];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) a[q] = __ldg(A + (size_t)w * 16 + q);
+    double a[BIDIAG ? 7 : 16], p[4];
+    load_A4<BIDIAG>(A + (size_t)w * 16, a);
 #pragma unroll
     for (int q = 0; q < 4; ++q) p[q] = __ldg(pi + (size_t)w * 4 + q);
     __syncthreads();
@@ -57,7 +66,7 @@ k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4
     for (int b = b0 + warp; b < b1; b += BW_WARPS) {
         const Blk bk = blks[b];
         const int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
-        const double ll = fwd4_run<SymT, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, a, p, nullptr);
+        const double ll = fwd4_run<BIDIAG, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, a, p, nullptr);
         if (lane < bk.nseq) ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
     }
 }
@@ -167,12 +176,8 @@ template <typename InT>
 static int launch_prepare(SeqSet &s, const InT *d_in, int64_t nsym, int *d_bad, const std::vector<Blk> &blks) {
     Ctx &c = ctx();
     if (s.special4) {
-        if (s.sym_bytes == 1)
-            HMMB_LAUNCH("prepare", (k_repack_blocks<InT, uint8_t>), s.nblk, 128, 0, d_in, s.d_off, s.d_len, s.d_blks, s.nblk,
-                        (uint4 *)s.d_obs, s.M, d_bad);
-        else
-            HMMB_LAUNCH("prepare", (k_repack_blocks<InT, uint16_t>), s.nblk, 128, 0, d_in, s.d_off, s.d_len, s.d_blks,
-                        s.nblk, (uint4 *)s.d_obs, s.M, d_bad);
+        HMMB_LAUNCH("prepare", k_repack_blocks4<InT>, s.nblk, 256, 0, d_in, s.d_off, s.d_len, s.d_blks, s.nblk,
+                    (uint4 *)s.d_obs, s.M, d_bad);
     } else {
         int grid = (int)std::min<int64_t>((nsym + 255) / 256, (int64_t)c.sm_count * 8);
         if (grid < 1) grid = 1;
@@ -197,7 +202,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     if (idx_bytes != 1 && idx_bytes != 2 && idx_bytes != 4 && idx_bytes != 8) { set_error("idx_bytes must be 1, 2, 4 or 8"); return HMMB_ERR_ARG; }
     s.R = R; s.N = N; s.M = M; s.NP = pick_np(N);
     s.sym_bytes = M <= 256 ? 1 : 2;
-    s.special4 = allow_special && N == 4 && M <= 512 && !getenv("HMMB_FORCE_GENERIC");
+    s.special4 = allow_special && N == 4 && M <= BW4_MAX_M && !getenv("HMMB_FORCE_GENERIC");
 
     std::vector<int32_t> len(R);
     for (int64_t r = 0; r < R; ++r) {
@@ -249,7 +254,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     std::vector<CtaWork> work;
     int64_t obs_rows = 0;
     if (s.special4) {
-        const int SPC = s.sym_bytes == 1 ? 16 : 8;
+        const int SPC = SPC4;  // packed u16 entries (codeword | conflict rank) per uint4
         std::vector<int> word_blk_begin(nwords + 1, 0);
         for (int w = 0; w < nwords; ++w) {
             word_blk_begin[w] = (int)blks.size();
@@ -368,6 +373,8 @@ struct hmmb_bw {
     double *d_spill = nullptr, *d_llseq = nullptr, *d_accum = nullptr, *d_partials = nullptr;
     double *d_prev = nullptr, *d_hist = nullptr;
     int32_t *d_active = nullptr, *d_iters = nullptr, *d_any = nullptr, *d_cta_begin = nullptr;
+    int32_t *d_bzero = nullptr;   // per word: B has an exact zero (disables the lean backward path)
+    bool bidiag = false;          // every word's A is upper-bidiagonal (checked in set_params)
     int64_t *d_seq_begin = nullptr;
     // precision guard: sticky per-sequence hand-over flags, counters, exact-kernel scratch
     uint8_t *d_flag = nullptr;
@@ -390,7 +397,7 @@ static void bw_release(hmmb_bw *h) {
     dev_free(h->d_pi); dev_free(h->d_A); dev_free(h->d_Bt); dev_free(h->d_spill); dev_free(h->d_llseq);
     dev_free(h->d_accum); dev_free(h->d_partials); dev_free(h->d_prev); dev_free(h->d_hist); dev_free(h->d_active);
     dev_free(h->d_iters); dev_free(h->d_any); dev_free(h->d_cta_begin); dev_free(h->d_seq_begin);
-    dev_free(h->d_flag); dev_free(h->d_newflags); dev_free(h->d_nexact); dev_free(h->d_exact_scratch);
+    dev_free(h->d_bzero); dev_free(h->d_flag); dev_free(h->d_newflags); dev_free(h->d_nexact); dev_free(h->d_exact_scratch);
 }
 
 static int bw_alloc_accum(hmmb_bw *h) {
@@ -429,6 +436,7 @@ int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_d
     TRYF(dev_alloc_t(&h->d_active, (size_t)W));
     TRYF(dev_alloc_t(&h->d_iters, (size_t)W));
     TRYF(dev_alloc_t(&h->d_any, 1));
+    TRYF(dev_alloc_t(&h->d_bzero, (size_t)W));
     TRYF(dev_alloc_t(&h->d_flag, (size_t)std::max<int64_t>(R, 1)));
     TRYF(dev_alloc_t(&h->d_newflags, 1));
     TRYF(dev_alloc_t(&h->d_nexact, 1));
@@ -491,7 +499,18 @@ int hmmb_bw_set_params(hmmb_bw_t *h, const double *pi0, const double *A0, const 
     HMMB_CUDA(cudaMemcpyAsync(tmp + nB, A0, nA * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     HMMB_CUDA(cudaMemcpyAsync(tmp + nB + nA, pi0, nP * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     dim3 gb((unsigned)std::min((N * M + 255) / 256, 64), (unsigned)W);
-    HMMB_LAUNCH("bw_load", k_load_B, gb, 256, 0, tmp, N, M, h->d_Bt);
+    HMMB_CUDA(cudaMemsetAsync(h->d_bzero, 0, (size_t)W * sizeof(int32_t), c.stream));
+    HMMB_LAUNCH("bw_load", k_load_B, gb, 256, 0, tmp, N, M, h->d_Bt, h->d_bzero);
+    {
+        // upper-bidiagonal A (the reference's left-to-right default) selects the 7-term kernels;
+        // zeros of A stay zeros under re-estimation, so the choice holds for the whole fit
+        h->bidiag = (N == 4);
+        for (size_t e = 0; e < nA && h->bidiag; ++e) {
+            const int ij = (int)(e % (size_t)(N * N)), i = ij / N, j = ij % N;
+            if (j != i && j != i + 1 && A0[e] > 0.0) h->bidiag = false;
+        }
+        if (getenv("HMMB_FORCE_DENSE_A")) h->bidiag = false;
+    }
     HMMB_LAUNCH("bw_load", k_load_clamped, (unsigned)std::min<size_t>((nA + 255) / 256, 1024), 256, 0, tmp + nB, (int64_t)nA, h->d_A);
     HMMB_LAUNCH("bw_load", k_load_clamped, (unsigned)std::min<size_t>((nP + 255) / 256, 1024), 256, 0, tmp + nB + nA, (int64_t)nP, h->d_pi);
     HMMB_LAUNCH("bw_load", k_fill, (unsigned)((W + 255) / 256), 256, 0, h->d_prev, (int64_t)W, -INFINITY);
@@ -564,25 +583,25 @@ static int launch_generic_estep(hmmb_bw *h) {
     return HMMB_OK;
 }
 
-template <typename SymT>
+template <bool BIDIAG>
 static int launch_special_estep(hmmb_bw *h) {
     SeqSet &s = h->s;
     if (s.ncta == 0) return HMMB_OK;
     const size_t smem_f = (size_t)h->M * 4 * sizeof(double);
-    const size_t smem_b = smem_f * (1 + BW_WARPS);
-    HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwd4<SymT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    HMMB_LAUNCH("bw_forward", k_bw_fwd4<SymT>, s.ncta, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
+    const size_t smem_b = smem_f * (1 + BW_WARPS) + (size_t)BW_THREADS * 4 * sizeof(double);
+    HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwd4<BIDIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
                 s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag);
-    HMMB_TRY((launch_exact<SymT, true>(h)));
-    HMMB_LAUNCH("bw_backward", k_bw_bwd4<SymT>, s.ncta, BW_THREADS, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
-                s.d_len, h->d_A, h->d_Bt, h->M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_partials,
-                h->pstride, h->d_flag, h->d_newflags);
+    HMMB_TRY((launch_exact<uint16_t, true>(h)));
+    HMMB_LAUNCH("bw_backward", k_bw_bwd4<BIDIAG>, s.ncta, BW_THREADS, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
+                s.d_len, h->d_A, h->d_Bt, h->M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero,
+                h->d_partials, h->pstride, h->d_flag, h->d_newflags);
     return HMMB_OK;
 }
 
 static int bw_estep(hmmb_bw *h) {
     SeqSet &s = h->s;
-    if (s.special4) return s.sym_bytes == 1 ? launch_special_estep<uint8_t>(h) : launch_special_estep<uint16_t>(h);
+    if (s.special4) return h->bidiag ? launch_special_estep<true>(h) : launch_special_estep<false>(h);
 #define GEN(NPV)                                                                               \
     case NPV:                                                                                  \
         return s.sym_bytes == 1 ? launch_generic_estep<NPV, uint8_t>(h) : launch_generic_estep<NPV, uint16_t>(h);
@@ -597,7 +616,7 @@ int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync
     HMMB_TRY(require_init());
     if (!h || !h->params_set) { set_error("hmmb_bw_iterate: parameters not set"); return HMMB_ERR_ARG; }
     Ctx &c = ctx();
-    HMMB_TRY(bw_ensure_hist(h, std::max(max_iter, 1)));
+    HMMB_TRY(bw_ensure_hist(h, std::min(std::max(max_iter, 1), 1 << 16)));  // history keeps at most 65536 iterations
     for (int it = 0; it < n_iter; ++it) {
         if (!h->any_active) break;
         for (int attempt = 0; attempt < 2; ++attempt) {
@@ -623,7 +642,7 @@ int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync
         HMMB_CUDA(cudaMemsetAsync(h->d_any, 0, sizeof(int32_t), c.stream));
         HMMB_LAUNCH("bw_mstep", k_bw_mstep, h->W, RED_THREADS, 0, h->d_accum, h->astride,
                     h->d_accum + (size_t)h->W * h->astride, h->world, h->W, h->N, h->M, h->d_pi, h->d_A, h->d_Bt,
-                    h->d_active, h->d_iters, h->d_prev, h->d_hist, h->hist_cap, eps, max_iter, h->d_any);
+                    h->d_active, h->d_iters, h->d_prev, h->d_hist, h->hist_cap, eps, max_iter, h->d_any, h->d_bzero);
         if (sync_each) {
             int32_t any = 0;
             HMMB_CUDA(cudaMemcpyAsync(&any, h->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
@@ -729,7 +748,7 @@ static int launch_score_generic(SeqSet &s, int W, const double *d_pi, const doub
     return HMMB_OK;
 }
 
-template <typename SymT>
+template <bool BIDIAG>
 static int launch_score_special(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll) {
     Ctx &c = ctx();
     if (s.nblk == 0) return HMMB_OK;
@@ -739,7 +758,7 @@ static int launch_score_special(SeqSet &s, int W, const double *d_pi, const doub
     bpc = std::min(bpc, 64);
     dim3 g((unsigned)((s.nblk + bpc - 1) / bpc), (unsigned)W);
     const size_t smem = (size_t)s.M * 4 * sizeof(double);
-    HMMB_LAUNCH("score", k_score4<SymT>, g, BW_THREADS, smem, s.d_blks, s.nblk, bpc, (const uint4 *)s.d_obs, s.d_len,
+    HMMB_LAUNCH("score", k_score4<BIDIAG>, g, BW_THREADS, smem, s.d_blks, s.nblk, bpc, (const uint4 *)s.d_obs, s.d_len,
                 s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll);
     return HMMB_OK;
 }
@@ -769,13 +788,18 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
     HMMB_CUDA(cudaMemcpyAsync(tmp + nB, A, nA * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     HMMB_CUDA(cudaMemcpyAsync(tmp + nB + nA, pi, nP * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     dim3 gb((unsigned)std::min((N * M + 255) / 256, 64), (unsigned)W);
-    HMMB_LAUNCH("score_load", k_load_B, gb, 256, 0, tmp, N, M, d_Bt);
+    HMMB_LAUNCH("score_load", k_load_B, gb, 256, 0, tmp, N, M, d_Bt, (int32_t *)nullptr);
     HMMB_LAUNCH("score_load", k_load_clamped, (unsigned)std::min<size_t>((nA + 255) / 256, 1024), 256, 0, tmp + nB, (int64_t)nA, d_A);
     HMMB_LAUNCH("score_load", k_load_clamped, (unsigned)std::min<size_t>((nP + 255) / 256, 1024), 256, 0, tmp + nB + nA, (int64_t)nP, d_pi);
     int rc;
     if (s.special4) {
-        rc = s.sym_bytes == 1 ? launch_score_special<uint8_t>(s, W, d_pi, d_A, d_Bt, d_ll)
-                              : launch_score_special<uint16_t>(s, W, d_pi, d_A, d_Bt, d_ll);
+        bool bidiag = true;
+        for (size_t e = 0; e < nA && bidiag; ++e) {
+            const int ij = (int)(e % 16), i = ij / 4, j = ij % 4;
+            if (j != i && j != i + 1 && A[e] > 0.0) bidiag = false;
+        }
+        rc = bidiag ? launch_score_special<true>(s, W, d_pi, d_A, d_Bt, d_ll)
+                    : launch_score_special<false>(s, W, d_pi, d_A, d_Bt, d_ll);
     } else {
 #define GEN(NPV)                                                                                         \
     case NPV:                                                                                            \
@@ -794,10 +818,7 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
         int64_t warps = std::min<int64_t>((int64_t)c.sm_count * 16, U);
         const int eg = (int)std::max<int64_t>(1, (warps + BW_WARPS - 1) / BW_WARPS);
         if (s.special4) {
-            if (s.sym_bytes == 1)
-                HMMB_LAUNCH("score_exact", (k_score_exact<uint8_t, true>), eg, BW_THREADS, 0, s.d_obs, s.d_foff, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);
-            else
-                HMMB_LAUNCH("score_exact", (k_score_exact<uint16_t, true>), eg, BW_THREADS, 0, s.d_obs, s.d_foff, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);
+            HMMB_LAUNCH("score_exact", (k_score_exact<uint16_t, true>), eg, BW_THREADS, 0, s.d_obs, s.d_foff, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);
         } else {
             if (s.sym_bytes == 1)
                 HMMB_LAUNCH("score_exact", (k_score_exact<uint8_t, false>), eg, BW_THREADS, 0, s.d_obs, s.d_off, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);

@@ -147,113 +147,6 @@ template <> struct Sym<uint16_t> {
     }
 };
 
-// ---------------------------------------------------------------- N = 4 forward pass
-// One sequence per lane.  a[i*4+j] = A[i][j], p[j] = pi[j], sB[sym*4+j] = B[j][sym] (shared).
-// op / sp already include the lane offset.  Replaces calculate_log_alpha
-// (HMM/hmm_training.py:122-160) and the alpha init (:357-360); returns log P(O|lambda)
-// (:376-377), -inf for a structurally impossible sequence, or NaN when the precision guard
-// asks for the exact log-space recomputation.
-template <typename SymT, bool SPILL>
-__device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restrict__ op,
-                                           const double *__restrict__ sB, const double (&a)[16],
-                                           const double (&p)[4], double2 *__restrict__ sp) {
-    constexpr int SPC = Sym<SymT>::SPC;
-    double al0 = 0.0, al1 = 0.0, al2 = 0.0, al3 = 0.0;
-    double er0 = 0.0, er1 = 0.0, er2 = 0.0, er3 = 0.0;  // error bounds, units of 2^-1000
-    bool tainted = false;
-    long long esum = 0;
-    bool stop = false;  // dead (impossible) or flagged for the exact path
-    double ll = neg_inf();
-    const int nch = (tmax + SPC - 1) / SPC;
-    for (int c = 0; c < nch; ++c) {
-        uint4 w = __ldg(op + (size_t)c * 32);
-#pragma unroll 4
-        for (int s = 0; s < SPC; ++s) {
-            const int t = c * SPC + s;
-            const unsigned sym = Sym<SymT>::pop_front(w);
-            if (t < T && !stop) {
-                const double2 b01 = *reinterpret_cast<const double2 *>(sB + sym * 4);
-                const double2 b23 = *reinterpret_cast<const double2 *>(sB + sym * 4 + 2);
-                double n0, n1, n2, n3;
-                if (t == 0) {
-                    n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
-                } else {
-                    n0 = al0 * a[0] + al1 * a[4] + al2 * a[8] + al3 * a[12];
-                    n1 = al0 * a[1] + al1 * a[5] + al2 * a[9] + al3 * a[13];
-                    n2 = al0 * a[2] + al1 * a[6] + al2 * a[10] + al3 * a[14];
-                    n3 = al0 * a[3] + al1 * a[7] + al2 * a[11] + al3 * a[15];
-                }
-                double at0 = n0 * b01.x, at1 = n1 * b01.y, at2 = n2 * b23.x, at3 = n3 * b23.y;
-                double ssum = (at0 + at1) + (at2 + at3);
-                double ea0 = 0.0, ea1 = 0.0, ea2 = 0.0, ea3 = 0.0;
-                if (!(ssum >= TINY_STEP) | is_sub(at0) | is_sub(at1) | is_sub(at2) | is_sub(at3) | tainted) {
-                    // ---- slow paths.  Keep "n_j > 0 <=> state j structurally reachable":
-#define HMMB_FIX_N(J, NJ)                                                                              \
-    if (NJ == 0.0 && t > 0 &&                                                                          \
-        ((al0 > 0.0 && a[J] > 0.0) || (al1 > 0.0 && a[4 + J] > 0.0) || (al2 > 0.0 && a[8 + J] > 0.0) || \
-         (al3 > 0.0 && a[12 + J] > 0.0)))                                                              \
-        NJ = tiny_pos();
-                    HMMB_FIX_N(0, n0) HMMB_FIX_N(1, n1) HMMB_FIX_N(2, n2) HMMB_FIX_N(3, n3)
-#undef HMMB_FIX_N
-                    if (!(ssum >= TINY_STEP)) {
-                        // the whole step is tiny (or impossible): exponent-split products
-                        double o[4];
-                        int E;
-                        const int code = exact_products4(n0, n1, n2, n3, b01.x, b01.y, b23.x, b23.y, o, &E);
-                        if (code == 0) {
-                            stop = true;  // no state can emit o_t: log P = -inf
-                        } else if ((code == 2 && t > 0) || tainted) {
-                            stop = true;  // the surviving states had lost their bits: exact path
-                            ll = nan_mark();
-                        } else {
-                            esum += E;
-                            at0 = o[0]; at1 = o[1]; at2 = o[2]; at3 = o[3];
-                            ssum = (at0 + at1) + (at2 + at3);
-                        }
-                    } else {
-                        // seeds: a reachable state whose value is denormal / underflowed stays
-                        // (barely) positive and contributes its worst-case error to the bound
-                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                        if (n0 > 0.0 && b01.x > 0.0 && is_sub(at0)) { if (at0 == 0.0) at0 = tiny_pos(); s0 = ERR_UNIT; }
-                        if (n1 > 0.0 && b01.y > 0.0 && is_sub(at1)) { if (at1 == 0.0) at1 = tiny_pos(); s1 = ERR_UNIT; }
-                        if (n2 > 0.0 && b23.x > 0.0 && is_sub(at2)) { if (at2 == 0.0) at2 = tiny_pos(); s2 = ERR_UNIT; }
-                        if (n3 > 0.0 && b23.y > 0.0 && is_sub(at3)) { if (at3 == 0.0) at3 = tiny_pos(); s3 = ERR_UNIT; }
-                        if (tainted | (s0 + s1 + s2 + s3 > 0.0)) {
-                            if (t > 0) {
-                                ea0 = (er0 * a[0] + er1 * a[4] + er2 * a[8] + er3 * a[12]) * b01.x;
-                                ea1 = (er0 * a[1] + er1 * a[5] + er2 * a[9] + er3 * a[13]) * b01.y;
-                                ea2 = (er0 * a[2] + er1 * a[6] + er2 * a[10] + er3 * a[14]) * b23.x;
-                                ea3 = (er0 * a[3] + er1 * a[7] + er2 * a[11] + er3 * a[15]) * b23.y;
-                            }
-                            ea0 += s0; ea1 += s1; ea2 += s2; ea3 += s3;
-                            tainted = true;
-                        }
-                    }
-                }
-                if (!stop) {
-                    const double sc = pow2_rescale(ssum, esum);
-                    al0 = at0 * sc; al1 = at1 * sc; al2 = at2 * sc; al3 = at3 * sc;
-                    if (tainted) {
-                        er0 = ea0 * sc; er1 = ea1 * sc; er2 = ea2 * sc; er3 = ea3 * sc;
-                        if (!((er0 + er1) + (er2 + er3) <= ERR_LIMIT)) {
-                            stop = true;
-                            ll = nan_mark();
-                        }
-                    }
-                    if (t == T - 1 && !stop) ll = log((al0 + al1) + (al2 + al3)) + (double)esum * LN2;
-                } else {
-                    al0 = al1 = al2 = al3 = 0.0;
-                }
-                if (SPILL) {
-                    __stcs(sp + (size_t)t * 64, make_double2(al0, al1));
-                    __stcs(sp + (size_t)t * 64 + 32, make_double2(al2, al3));
-                }
-            }
-        }
-    }
-    return ll;
-}
-
 // ---------------------------------------------------------------- generic-N helpers
 template <int NP>
 __device__ __forceinline__ double group_sum(double v) {
@@ -404,9 +297,9 @@ template <typename SymT>
 struct BlkObs {
     const uint4 *p;  // chunk row of this sequence's lane: obs_blk + blk.obs_base + lane
     __device__ __forceinline__ unsigned operator[](int t) const {
-        constexpr int SPC = Sym<SymT>::SPC;
-        const SymT *c = reinterpret_cast<const SymT *>(p + (size_t)(t / SPC) * 32);
-        return c[t % SPC];
+        // N = 4 path layout: 8 packed u16 per uint4, codeword in the low 11 bits (bw4_kernels.cuh)
+        const unsigned short *c = reinterpret_cast<const unsigned short *>(p + (size_t)(t / 8) * 32);
+        return (unsigned)c[t % 8] & 0x7ffu;
     }
 };
 

@@ -1,0 +1,90 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch) for
+the single exchange step of each path — a sum-allreduce of the small per-iteration
+accumulators (pi / xi / emission-count sums, or centroid sums and counts).  Sequences, frames
+and utterances are sharded; nothing else crosses ranks.
+
+The C library calls back into ``make_allreduce()``'s closure with a DEVICE pointer; the
+closure wraps it zero-copy as a torch tensor and all-reduces it on torch's current stream,
+which ``bind_torch_stream()`` has made the library's stream as well, so ordering needs no
+host synchronisation.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+
+class _DeviceBuffer:
+    """Zero-copy view of n fp64 values at a raw device pointer for torch.as_tensor."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+_bound_stream = None
+
+
+def bind_torch_stream():
+    """Make libhmmb200 launch on torch's current CUDA stream, so torch events, NCCL
+    collectives and our kernels are ordered without host synchronisation.  The legacy default
+    stream (handle 0) cannot be handed over, so a dedicated torch stream is made current
+    first in that case.  Returns the torch stream."""
+    global _bound_stream
+    import torch
+    s = torch.cuda.current_stream()
+    if s.cuda_stream == 0:
+        s = torch.cuda.Stream()
+        torch.cuda.set_stream(s)
+    _bound_stream = s  # keep it alive
+    _lib.check(_lib.load().hmmb_set_stream(ctypes.c_void_p(s.cuda_stream)))
+    return s
+
+
+def make_allreduce(group=None, device: str = "cuda"):
+    """Returns fn(ptr, n_doubles) that sums the buffer in place over the process group.
+    device='cpu' treats ptr as host memory (gloo; used by the CPU tests of the plumbing)."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(ptr: int, n: int) -> None:
+        if device == "cpu":
+            buf = (ctypes.c_double * n).from_address(ptr)
+            t = torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
+        else:
+            t = torch.as_tensor(_DeviceBuffer(ptr, n), device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+    return fn
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n items for `rank`; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sequences_round_robin(word_of_seq: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Indices of this rank's sequences: the sequences of every word are dealt round-robin over
+    the ranks, so each rank sees (almost) the same number of sequences of every word."""
+    word_of_seq = np.asarray(word_of_seq)
+    order = np.argsort(word_of_seq, kind="stable")
+    ws = word_of_seq[order]
+    starts = np.flatnonzero(np.r_[True, ws[1:] != ws[:-1]])
+    pos_in_word = np.arange(len(ws)) - np.repeat(starts, np.diff(np.r_[starts, len(ws)]))
+    return np.sort(order[pos_in_word % world == rank])
+
+
+def combine_llstats(stats: Sequence[Tuple[float, float]]) -> float:
+    """log_sum_exp over all ranks' sequences from per-rank (max, sum exp(ll - max)) pairs —
+    the host mirror of what k_bw_mstep does on the device (HMM/hmm_training.py:503)."""
+    mx = max((m for m, _ in stats), default=float("-inf"))
+    if mx == float("-inf"):
+        return float("-inf")
+    s = sum(sv * np.exp(m - mx) for m, sv in stats if m != float("-inf"))
+    return float(mx + np.log(s))

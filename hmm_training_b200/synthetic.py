@@ -60,19 +60,31 @@ def pack_corpus(corpus: List[List[np.ndarray]], M: int) -> Tuple[np.ndarray, np.
 
 def fixed_length_codewords(seed: int, W: int, S: int, T: int, N: int = 4, M: int = 256,
                            dtype=None) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Vectorised generator for the large benchmark configs (config 3/4): W words x S
-    sequences of fixed length T, clustered left-to-right structure, already packed.
-    Sequence r of word w is rows [w*S + r]."""
+    """Vectorised generator for the large benchmark configs (config 3/4/5): W words x S
+    sequences of fixed length T, left-to-right structure (N segments with random cut points,
+    segment s emits (M//N)*s + U{0..M/(2N)+7} + 7*w mod M), already packed.  Sequence r of
+    word w is row w*S + r."""
     rng = np.random.default_rng(seed)
     dt = dtype or (np.uint8 if M <= 256 else np.uint16)
+    wide = np.uint16 if M <= 256 else np.uint32
     R = W * S
-    seg = np.sort(rng.integers(0, N, size=(R, T), dtype=np.int32), axis=1)
-    sym = (M // N) * seg + rng.integers(0, max(M // (2 * N), 1) + 8, size=(R, T), dtype=np.int32)
-    shift = (np.repeat(np.arange(W, dtype=np.int32), S) * 7)[:, None]
-    obs = ((sym + shift) % M).astype(dt).reshape(-1)
+    obs = np.empty((R, T), dtype=dt)
+    spread = max(M // (2 * N), 1) + 8
+    tgrid = np.arange(T, dtype=np.int32)[None, :]
+    chunk = max(1, (1 << 24) // max(T, 1))
+    for lo in range(0, R, chunk):
+        hi = min(R, lo + chunk)
+        cuts = np.sort(rng.integers(0, T + 1, size=(hi - lo, N - 1), dtype=np.int32), axis=1) if N > 1 \
+            else np.zeros((hi - lo, 0), np.int32)
+        seg = np.zeros((hi - lo, T), dtype=wide)
+        for c in range(N - 1):
+            seg += (tgrid >= cuts[:, c:c + 1]).astype(wide)
+        sym = seg * wide(M // N) + rng.integers(0, spread, size=(hi - lo, T), dtype=wide)
+        shift = ((np.arange(lo, hi) // S) * 7).astype(wide)[:, None]
+        obs[lo:hi] = ((sym + shift) % wide(M)).astype(dt)
     offsets = np.arange(R + 1, dtype=np.int64) * T
     word_of_seq = np.repeat(np.arange(W, dtype=np.int32), S)
-    return obs, offsets, word_of_seq
+    return obs.reshape(-1), offsets, word_of_seq
 
 
 def mfcc_mixture(seed: int, F: int, K: int = 256) -> np.ndarray:

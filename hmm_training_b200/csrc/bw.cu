@@ -49,24 +49,18 @@ k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4
          const int32_t *__restrict__ len_sorted, const int32_t *__restrict__ order, const double *__restrict__ pi,
          const double *__restrict__ A, const double *__restrict__ Bt, int M, int W, double *__restrict__ ll_out) {
     extern __shared__ double sB[];
+    double *sBmax = sB + (size_t)M * 4;
     const int w = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {
-        const double2 *src = reinterpret_cast<const double2 *>(Bt + (size_t)w * M * 4);
-        double2 *dst = reinterpret_cast<double2 *>(sB);
-        for (int e = tid; e < M * 2; e += BW_THREADS) dst[e] = __ldg(src + e);
-    }
-    double a[BIDIAG ? 7 : 16], p[4];
-    load_A4<BIDIAG>(A + (size_t)w * 16, a);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) p[q] = __ldg(pi + (size_t)w * 4 + q);
+    double a[BIDIAG ? 7 : 16], p[4], rmax;
+    load_model4<BIDIAG>(pi, A, Bt, w, M, sB, sBmax, a, p, rmax);
     __syncthreads();
     const int b0 = blockIdx.x * blocks_per_cta;
     const int b1 = min(nblk, b0 + blocks_per_cta);
     for (int b = b0 + warp; b < b1; b += BW_WARPS) {
         const Blk bk = blks[b];
         const int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
-        const double ll = fwd4_run<BIDIAG, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, a, p, nullptr);
+        const double ll = fwd4_run<BIDIAG, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, a, p, rmax, nullptr);
         if (lane < bk.nseq) ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
     }
 }
@@ -587,8 +581,8 @@ template <bool BIDIAG>
 static int launch_special_estep(hmmb_bw *h) {
     SeqSet &s = h->s;
     if (s.ncta == 0) return HMMB_OK;
-    const size_t smem_f = (size_t)h->M * 4 * sizeof(double);
-    const size_t smem_b = smem_f * (1 + BW_WARPS) + (size_t)BW_THREADS * 4 * sizeof(double);
+    const size_t smem_f = (size_t)h->M * 5 * sizeof(double);
+    const size_t smem_b = (size_t)h->M * 4 * sizeof(double) * (1 + BW_WARPS) + (size_t)BW_THREADS * 4 * sizeof(double);
     HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwd4<BIDIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
                 s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag);
@@ -632,7 +626,8 @@ int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync
             h->n_backward_handover += nf;
             HMMB_CUDA(cudaMemsetAsync(h->d_newflags, 0, sizeof(int32_t), c.stream));
         }
-        HMMB_LAUNCH("bw_reduce", k_bw_reduce, h->W, RED_THREADS, 0, h->s.special4 ? h->d_partials : nullptr, h->pstride,
+        const dim3 rgrid((unsigned)h->W, h->s.special4 ? (unsigned)((h->nacc + RED_EX - 1) / RED_EX) : 1u);
+        HMMB_LAUNCH("bw_reduce", k_bw_reduce, rgrid, RED_THREADS, 0, h->s.special4 ? h->d_partials : nullptr, h->pstride,
                     h->d_cta_begin, h->d_llseq, h->d_seq_begin, h->d_accum, h->astride, h->nacc,
                     h->d_accum + (size_t)h->W * h->astride, h->rank, h->W, h->d_active);
         if (h->allreduce && h->world > 1) {
@@ -757,7 +752,7 @@ static int launch_score_special(SeqSet &s, int W, const double *d_pi, const doub
     bpc = (bpc + BW_WARPS - 1) / BW_WARPS * BW_WARPS;
     bpc = std::min(bpc, 64);
     dim3 g((unsigned)((s.nblk + bpc - 1) / bpc), (unsigned)W);
-    const size_t smem = (size_t)s.M * 4 * sizeof(double);
+    const size_t smem = (size_t)s.M * 5 * sizeof(double);
     HMMB_LAUNCH("score", k_score4<BIDIAG>, g, BW_THREADS, smem, s.d_blks, s.nblk, bpc, (const uint4 *)s.d_obs, s.d_len,
                 s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll);
     return HMMB_OK;

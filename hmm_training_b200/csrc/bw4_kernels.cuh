@@ -79,6 +79,13 @@ k_repack_blocks4(const InT *__restrict__ obs, const int64_t *__restrict__ off_so
 }
 
 // ---------------------------------------------------------------- forward
+// zero-or-denormal test for four non-negative doubles at once (integer pipe)
+__device__ __forceinline__ bool any_sub4(double x0, double x1, double x2, double x3) {
+    const unsigned m = min(min((unsigned)__double2hiint(x0), (unsigned)__double2hiint(x1)),
+                           min((unsigned)__double2hiint(x2), (unsigned)__double2hiint(x3)));
+    return m < 0x00100000u;
+}
+
 // a[] holds A row-major (dense) or {a00,a11,a22,a33,a01,a12,a23} (BIDIAG).
 template <bool BIDIAG>
 __device__ __forceinline__ void matvec_fwd(const double *a, double al0, double al1, double al2, double al3, double &n0,
@@ -102,25 +109,34 @@ __device__ __forceinline__ double a_at(const double *a, int i, int j) {
     return a[i * 4 + j];
 }
 
-// One sequence per lane.  p[j] = pi[j], sB[sym*4+j] = B[j][sym] (shared).  op / sp include the
-// lane offset.  Replaces calculate_log_alpha (HMM/hmm_training.py:122-160) and the alpha init
-// (:357-360); returns log P(O|lambda) (:376-377), -inf for a structurally impossible
-// sequence, or NaN when the precision guard asks for the exact log-space recomputation.
+// One sequence per lane.  p[j] = pi[j], sB[sym*4+j] = B[j][sym] (shared), sBmax[sym] =
+// max_j B[j][sym], rmax = largest row sum of A.  op / sp include the lane offset.  Replaces
+// calculate_log_alpha (HMM/hmm_training.py:122-160) and the alpha init (:357-360); returns
+// log P(O|lambda) (:376-377), -inf for a structurally impossible sequence, or NaN when the
+// precision guard asks for the exact log-space recomputation.
+//
+// Precision guard, N = 4 flavour: every alive state whose value is denormal / clamped adds
+// 2^-1074 (its worst-case absolute error) to a scalar bound E, which is propagated with
+//   E' <= (E * rmax * max_j b_j(o_t) + seeds) * scale   >=  sum_j |error of alpha_t(j)|
+// (units of 2^-1000).  E stays ~1e-320 relative unless the states that carried the sequence
+// die; when it exceeds 1e-12 of the step's mass the sequence is handed over.
 template <bool BIDIAG, bool SPILL>
 __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restrict__ op,
-                                           const double *__restrict__ sB, const double *a, const double (&p)[4],
+                                           const double *__restrict__ sB, const double *__restrict__ sBmax,
+                                           const double *a, const double (&p)[4], double rmax,
                                            double2 *__restrict__ sp) {
     using S16 = Sym<uint16_t>;
     double al0 = 0.0, al1 = 0.0, al2 = 0.0, al3 = 0.0;
-    double er0 = 0.0, er1 = 0.0, er2 = 0.0, er3 = 0.0;  // error bounds, units of 2^-1000
-    bool tainted = false;
+    double E = 0.0;  // error bound, units of 2^-1000
     long long esum = 0;
     bool stop = false;  // dead (impossible) or flagged for the exact path
     double ll = neg_inf();
     const int nch = (tmax + SPC4 - 1) / SPC4;
+    uint4 wnext = nch > 0 ? __ldg(op) : make_uint4(0, 0, 0, 0);
     for (int c = 0; c < nch; ++c) {
-        uint4 w = __ldg(op + (size_t)c * 32);
-#pragma unroll 4
+        uint4 w = wnext;
+        if (c + 1 < nch) wnext = __ldg(op + (size_t)(c + 1) * 32);  // prefetch the next 8 codewords
+#pragma unroll 2
         for (int s = 0; s < SPC4; ++s) {
             const int t = c * SPC4 + s;
             const unsigned sym = S16::pop_front(w) & SYM_MASK;
@@ -135,63 +151,51 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
                 }
                 double at0 = n0 * b01.x, at1 = n1 * b01.y, at2 = n2 * b23.x, at3 = n3 * b23.y;
                 double ssum = (at0 + at1) + (at2 + at3);
-                double ea0 = 0.0, ea1 = 0.0, ea2 = 0.0, ea3 = 0.0;
-                if (!(ssum >= TINY_STEP) | is_sub(at0) | is_sub(at1) | is_sub(at2) | is_sub(at3) | tainted) {
-                    // ---- slow paths.  Keep "n_j > 0 <=> state j structurally reachable":
+                double seeds = 0.0;
+                if (!(ssum >= TINY_STEP)) {
+                    // ---- the whole step is tiny (or impossible): exponent-split products
 #define HMMB_FIX_N(J, NJ)                                                                                      \
     if (NJ == 0.0 && t > 0 &&                                                                                  \
         ((al0 > 0.0 && a_at<BIDIAG>(a, 0, J) > 0.0) || (al1 > 0.0 && a_at<BIDIAG>(a, 1, J) > 0.0) ||           \
          (al2 > 0.0 && a_at<BIDIAG>(a, 2, J) > 0.0) || (al3 > 0.0 && a_at<BIDIAG>(a, 3, J) > 0.0)))            \
         NJ = tiny_pos();
                     HMMB_FIX_N(0, n0) HMMB_FIX_N(1, n1) HMMB_FIX_N(2, n2) HMMB_FIX_N(3, n3)
-#undef HMMB_FIX_N
-                    if (!(ssum >= TINY_STEP)) {
-                        // the whole step is tiny (or impossible): exponent-split products
-                        double o[4];
-                        int E;
-                        const int code = exact_products4(n0, n1, n2, n3, b01.x, b01.y, b23.x, b23.y, o, &E);
-                        if (code == 0) {
-                            stop = true;  // no state can emit o_t: log P = -inf
-                        } else if ((code == 2 && t > 0) || tainted) {
-                            stop = true;  // the surviving states had lost their bits: exact path
-                            ll = nan_mark();
-                        } else {
-                            esum += E;
-                            at0 = o[0]; at1 = o[1]; at2 = o[2]; at3 = o[3];
-                            ssum = (at0 + at1) + (at2 + at3);
-                        }
+                    double o[4];
+                    int Ex;
+                    const int code = exact_products4(n0, n1, n2, n3, b01.x, b01.y, b23.x, b23.y, o, &Ex);
+                    if (code == 0) {
+                        stop = true;  // no state can emit o_t: log P = -inf
+                    } else if ((code == 2 && t > 0) || E > 0.0) {
+                        stop = true;  // the surviving states had lost their bits: exact path
+                        ll = nan_mark();
                     } else {
-                        // seeds: a reachable state whose value is denormal / underflowed stays
-                        // (barely) positive and contributes its worst-case error to the bound
-                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                        if (n0 > 0.0 && b01.x > 0.0 && is_sub(at0)) { if (at0 == 0.0) at0 = tiny_pos(); s0 = ERR_UNIT; }
-                        if (n1 > 0.0 && b01.y > 0.0 && is_sub(at1)) { if (at1 == 0.0) at1 = tiny_pos(); s1 = ERR_UNIT; }
-                        if (n2 > 0.0 && b23.x > 0.0 && is_sub(at2)) { if (at2 == 0.0) at2 = tiny_pos(); s2 = ERR_UNIT; }
-                        if (n3 > 0.0 && b23.y > 0.0 && is_sub(at3)) { if (at3 == 0.0) at3 = tiny_pos(); s3 = ERR_UNIT; }
-                        if (tainted | (s0 + s1 + s2 + s3 > 0.0)) {
-                            if (t > 0) {
-                                matvec_fwd<BIDIAG>(a, er0, er1, er2, er3, ea0, ea1, ea2, ea3);
-                                ea0 *= b01.x; ea1 *= b01.y; ea2 *= b23.x; ea3 *= b23.y;
-                            }
-                            ea0 += s0; ea1 += s1; ea2 += s2; ea3 += s3;
-                            tainted = true;
-                        }
+                        esum += Ex;
+                        at0 = o[0]; at1 = o[1]; at2 = o[2]; at3 = o[3];
+                        ssum = (at0 + at1) + (at2 + at3);
                     }
+                } else if (any_sub4(at0, at1, at2, at3)) {
+                    // ---- some state is zero / denormal: keep "alpha_j > 0 <=> structurally
+                    // reachable" (clamp) and count the seeds of the error bound
+                    HMMB_FIX_N(0, n0) HMMB_FIX_N(1, n1) HMMB_FIX_N(2, n2) HMMB_FIX_N(3, n3)
+#undef HMMB_FIX_N
+                    if (n0 > 0.0 && b01.x > 0.0 && is_sub(at0)) { if (at0 == 0.0) at0 = tiny_pos(); seeds += ERR_UNIT; }
+                    if (n1 > 0.0 && b01.y > 0.0 && is_sub(at1)) { if (at1 == 0.0) at1 = tiny_pos(); seeds += ERR_UNIT; }
+                    if (n2 > 0.0 && b23.x > 0.0 && is_sub(at2)) { if (at2 == 0.0) at2 = tiny_pos(); seeds += ERR_UNIT; }
+                    if (n3 > 0.0 && b23.y > 0.0 && is_sub(at3)) { if (at3 == 0.0) at3 = tiny_pos(); seeds += ERR_UNIT; }
                 }
                 if (!stop) {
                     const double sc = pow2_rescale(ssum, esum);
                     al0 = at0 * sc; al1 = at1 * sc; al2 = at2 * sc; al3 = at3 * sc;
-                    if (tainted) {
-                        er0 = ea0 * sc; er1 = ea1 * sc; er2 = ea2 * sc; er3 = ea3 * sc;
-                        if (!((er0 + er1) + (er2 + er3) <= ERR_LIMIT)) {
+                    if ((E > 0.0) | (seeds > 0.0)) {
+                        E = (E * (rmax * sBmax[sym]) + seeds) * sc;
+                        if (!(E <= ERR_LIMIT)) {
                             stop = true;
                             ll = nan_mark();
                         }
                     }
                     if (t == T - 1 && !stop) ll = log((al0 + al1) + (al2 + al3)) + (double)esum * LN2;
-                } else {
-                    al0 = al1 = al2 = al3 = 0.0;
                 }
+                if (stop) al0 = al1 = al2 = al3 = 0.0;
                 if (SPILL) {
                     __stcs(sp + (size_t)t * 64, make_double2(al0, al1));
                     __stcs(sp + (size_t)t * 64 + 32, make_double2(al2, al3));
@@ -200,6 +204,39 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
         }
     }
     return ll;
+}
+
+// CTA prologue shared by the forward-type kernels: B^T of word w -> shared memory, per-codeword
+// max_j b_j, A and pi -> registers, rmax = largest row sum of A.
+template <bool BIDIAG>
+__device__ __forceinline__ void load_model4(const double *__restrict__ pi, const double *__restrict__ A,
+                                            const double *__restrict__ Bt, int w, int M, double *sB, double *sBmax,
+                                            double *a, double (&p)[4], double &rmax) {
+    const int tid = threadIdx.x;
+    const double2 *src = reinterpret_cast<const double2 *>(Bt + (size_t)w * M * 4);
+    double2 *dst = reinterpret_cast<double2 *>(sB);
+    for (int e = tid; e < M; e += BW_THREADS) {
+        const double2 x = __ldg(src + 2 * e), y = __ldg(src + 2 * e + 1);
+        dst[2 * e] = x;
+        dst[2 * e + 1] = y;
+        sBmax[e] = fmax(fmax(x.x, x.y), fmax(y.x, y.y));
+    }
+    const double *Aw = A + (size_t)w * 16;
+    rmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        rmax = fmax(rmax, (__ldg(Aw + i * 4) + __ldg(Aw + i * 4 + 1)) + (__ldg(Aw + i * 4 + 2) + __ldg(Aw + i * 4 + 3)));
+    if (BIDIAG) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = __ldg(Aw + i * 5);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) a[4 + i] = __ldg(Aw + i * 5 + 1);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) a[q] = __ldg(Aw + q);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) p[q] = __ldg(pi + (size_t)w * 4 + q);
 }
 
 template <bool BIDIAG>
@@ -221,25 +258,19 @@ k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
           const int32_t *__restrict__ len_sorted, const double *__restrict__ pi, const double *__restrict__ A,
           const double *__restrict__ Bt, int M, double2 *__restrict__ spill, double *__restrict__ ll_seq,
           const int32_t *__restrict__ active, uint8_t *__restrict__ flag) {
-    extern __shared__ double sB[];
+    extern __shared__ double sB[];  // [M][4] B^T, then [M] per-codeword max
+    double *sBmax = sB + (size_t)M * 4;
     const CtaWork cw = work[blockIdx.x];
     if (!active[cw.word]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {
-        const double2 *src = reinterpret_cast<const double2 *>(Bt + (size_t)cw.word * M * 4);
-        double2 *dst = reinterpret_cast<double2 *>(sB);
-        for (int e = tid; e < M * 2; e += BW_THREADS) dst[e] = __ldg(src + e);
-    }
-    double a[BIDIAG ? 7 : 16], p[4];
-    load_A4<BIDIAG>(A + (size_t)cw.word * 16, a);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) p[q] = __ldg(pi + (size_t)cw.word * 4 + q);
+    double a[BIDIAG ? 7 : 16], p[4], rmax;
+    load_model4<BIDIAG>(pi, A, Bt, cw.word, M, sB, sBmax, a, p, rmax);
     __syncthreads();
     for (int b = cw.blk_begin + warp; b < cw.blk_end; b += BW_WARPS) {
         const Blk bk = blks[b];
         int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
         if (T > 0 && flag[bk.first + lane]) T = 0;  // handled by the exact log-space kernel
-        const double ll = fwd4_run<BIDIAG, true>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, a, p,
+        const double ll = fwd4_run<BIDIAG, true>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, a, p, rmax,
                                                  spill + bk.spill_base * 64 + lane);
         if (T > 0) {
             ll_seq[bk.first + lane] = ll;
@@ -249,12 +280,15 @@ k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
 }
 
 // ---------------------------------------------------------------- backward + accumulate
-// Warp-private emission-count update in precomputed rank order (see k_repack_blocks4).
-__device__ __forceinline__ void cnt_update4(double *__restrict__ cw, bool act, unsigned sym, int rank, double g0,
-                                            double g1, double g2, double g3) {
+// Warp-private emission-count update in precomputed rank order (see k_repack_blocks4).  Lanes
+// of rank 0 (the common case) have distinct codewords; their read-modify-write is split
+// around the next step's arithmetic by the caller so the shared-memory latency is hidden.
+// Ranks >= 1 follow here, one conflict-free round per rank.
+__device__ __forceinline__ void cnt_update4_rest(double *__restrict__ cw, bool act, unsigned sym, int rank, double g0,
+                                                 double g1, double g2, double g3) {
     const int maxrank = __reduce_max_sync(0xffffffffu, act ? rank : 0);
     double2 *row = reinterpret_cast<double2 *>(cw + sym * 4);
-    for (int r = 0; r <= maxrank; ++r) {
+    for (int r = 1; r <= maxrank; ++r) {
         if (act && rank == r) {
             double2 c01 = row[0], c23 = row[1];
             c01.x += g0; c01.y += g1; c23.x += g2; c23.y += g3;
@@ -262,13 +296,6 @@ __device__ __forceinline__ void cnt_update4(double *__restrict__ cw, bool act, u
         }
         __syncwarp();
     }
-}
-
-// zero-or-denormal test for four non-negative doubles at once (integer pipe)
-__device__ __forceinline__ bool any_sub4(double x0, double x1, double x2, double x3) {
-    const unsigned m = min(min((unsigned)__double2hiint(x0), (unsigned)__double2hiint(x1)),
-                           min((unsigned)__double2hiint(x2), (unsigned)__double2hiint(x3)));
-    return m < 0x00100000u;
 }
 
 // all four non-negative doubles strictly positive? (integer pipe: x > 0 <=> hi|lo != 0)
@@ -445,8 +472,15 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         if (ttop < T) { pa01 = __ldcs(sp + (size_t)ttop * 64); pa23 = __ldcs(sp + (size_t)ttop * 64 + 32); }
         if (ttop >= 1 && ttop - 1 < T) { pb01 = __ldcs(sp + (size_t)(ttop - 1) * 64); pb23 = __ldcs(sp + (size_t)(ttop - 1) * 64 + 32); }
         const int nch = (bk.tmax + SPC4 - 1) / SPC4;
+        // emission-count update of the previous step, still pending (software pipelining)
+        bool pact = false;
+        unsigned psym = 0u;
+        int prank = 0;
+        double pg0 = 0.0, pg1 = 0.0, pg2 = 0.0, pg3 = 0.0;
+        uint4 wnext = __ldg(op + (size_t)(nch - 1) * 32);
         for (int c = nch - 1; c >= 0; --c) {
-            uint4 w = __ldg(op + (size_t)c * 32);
+            uint4 w = wnext;
+            if (c > 0) wnext = __ldg(op + (size_t)(c - 1) * 32);  // prefetch the next 8 codewords
 #pragma unroll 2
             for (int s = SPC4 - 1; s >= 0; --s) {
                 const int t = c * SPC4 + s;
@@ -455,6 +489,11 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                 const unsigned sym = packed & SYM_MASK;
                 const int rank = (int)(packed >> SYM_BITS);
                 const bool act = t < T;
+                // round 0 of the pending update: issue the shared-memory loads now ...
+                const bool p0 = pact && prank == 0;
+                double2 *prow = reinterpret_cast<double2 *>(cntw + psym * 4);
+                double2 r01 = make_double2(0.0, 0.0), r23 = r01;
+                if (p0) { r01 = prow[0]; r23 = prow[1]; }
                 const double al0 = pa01.x, al1 = pa01.y, al2 = pa23.x, al3 = pa23.y;
                 pa01 = pb01; pa23 = pb23;
                 if (t >= 2 && t - 2 < T) {
@@ -528,8 +567,26 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                         mypi[0] += g0; mypi[1] += g1; mypi[2] += g2; mypi[3] += g3;
                     }
                 }
-                cnt_update4(cntw, act, sym, rank, g0, g1, g2, g3);  // (:460-500 numerators)
+                // ... and finish it after this step's arithmetic  (:460-500 numerators)
+                if (p0) {
+                    r01.x += pg0; r01.y += pg1; r23.x += pg2; r23.y += pg3;
+                    prow[0] = r01; prow[1] = r23;
+                }
+                __syncwarp();
+                cnt_update4_rest(cntw, pact, psym, prank, pg0, pg1, pg2, pg3);
+                pact = act; psym = sym; prank = rank;
+                pg0 = g0; pg1 = g1; pg2 = g2; pg3 = g3;
             }
+        }
+        {   // drain the pipeline: the last step's update
+            double2 *prow = reinterpret_cast<double2 *>(cntw + psym * 4);
+            if (pact && prank == 0) {
+                double2 r01 = prow[0], r23 = prow[1];
+                r01.x += pg0; r01.y += pg1; r23.x += pg2; r23.y += pg3;
+                prow[0] = r01; prow[1] = r23;
+            }
+            __syncwarp();
+            cnt_update4_rest(cntw, pact, psym, prank, pg0, pg1, pg2, pg3);
         }
         if (st.imprecise) {  // sticky hand-over; the host redoes this E-step once (hmmb_bw_iterate)
             flag[bk.first + lane] = 1;

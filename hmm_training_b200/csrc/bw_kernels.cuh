@@ -270,24 +270,38 @@ k_bw_exact(const void *__restrict__ obs, const int64_t *__restrict__ base_sorted
 // per-sequence log-likelihoods, the two halves of log_sum_exp (:503), into
 // llstats[rank][w][2].
 constexpr int RED_THREADS = 256;
+constexpr int RED_EX = 32;  // accumulator entries per CTA of k_bw_reduce
+constexpr int RED_CY = RED_THREADS / RED_EX;
 
+// grid = (W, ceil(nacc / RED_EX)).  Thread (ex, cy) sums every RED_CY-th CTA partial of entry
+// e; the RED_CY partial sums are combined in fixed order, so the result is deterministic.
 __global__ void __launch_bounds__(RED_THREADS)
 k_bw_reduce(const double *__restrict__ partials, int64_t pstride, const int32_t *__restrict__ cta_begin,
             const double *__restrict__ ll_seq, const int64_t *__restrict__ seq_begin, double *__restrict__ accum,
             int64_t astride, int64_t nacc, double *__restrict__ llstats, int rank, int W,
             const int32_t *__restrict__ active) {
     __shared__ double sM[RED_THREADS / 32], sS[RED_THREADS / 32];
+    __shared__ double sPart[RED_CY][RED_EX];
     const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!active[w]) return;
     double *acc = accum + (size_t)w * astride;
     if (partials) {
+        const int ex = tid % RED_EX, cy = tid / RED_EX;
+        const int64_t e = (int64_t)blockIdx.y * RED_EX + ex;
         const int c0 = cta_begin[w], c1 = cta_begin[w + 1];
-        for (int64_t e = tid; e < nacc; e += RED_THREADS) {
-            double s = 0.0;
-            for (int c = c0; c < c1; ++c) s += partials[(size_t)c * pstride + e];
-            acc[e] += s;  // the exact log-space kernel may already have added flagged sequences
+        double s = 0.0;
+        if (e < nacc)
+            for (int c = c0 + cy; c < c1; c += RED_CY) s += partials[(size_t)c * pstride + e];
+        sPart[cy][ex] = s;
+        __syncthreads();
+        if (cy == 0 && e < nacc) {
+            double tot = 0.0;
+#pragma unroll
+            for (int q = 0; q < RED_CY; ++q) tot += sPart[q][ex];
+            acc[e] += tot;  // the exact log-space kernel may already have added flagged sequences
         }
     }
+    if (blockIdx.y != 0) return;
     const int64_t r0 = seq_begin[w], r1 = seq_begin[w + 1];
     double m = neg_inf();
     for (int64_t r = r0 + tid; r < r1; r += RED_THREADS) m = fmax(m, ll_seq[r]);

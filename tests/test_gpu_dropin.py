@@ -1,0 +1,149 @@
+"""The reference-shaped Python surface (same names / arguments / side effects as the
+reference's modules) on top of the CUDA path.  GPU required."""
+import contextlib
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_close, load_golden, split_corpus
+from hmm_training_b200 import codevector_functions as cvf
+from hmm_training_b200 import hmm_testing, hmm_training, synthetic
+from hmm_training_b200.codevector_classes import CentroidDataMFCC, DataStorage, RawDataMFCC
+from hmm_training_b200.hmm_classes import DataStorageHMM, HMMTrained
+from oracle import hmm_oracle as O
+from oracle import vq_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(X, name="rec"):
+    return [RawDataMFCC(raw_samples=np.array([]), mfcc=x.copy(), frame_number=i, recording=name) for i, x in enumerate(X)]
+
+
+def _centroids(C):
+    return [CentroidDataMFCC(mfcc=c.copy(), id=i) for i, c in enumerate(C)]
+
+
+def test_get_observations_matches_reference_golden():
+    g = load_golden("vq_2000x256")
+    frames = _frames(g["X"])
+    lens = g["rec_lens"]
+    recs, pos = [], 0
+    for n in lens:
+        recs.append(frames[pos:pos + n]); pos += n
+    recs.insert(1, [])  # an empty recording yields an empty array, like the reference
+    obs = hmm_training.get_observations(recs, _centroids(g["C"]))
+    assert len(obs) == len(recs) and len(obs[1]) == 0
+    assert obs[0].dtype == np.int64
+    assert np.array_equal(np.concatenate([obs[0], obs[2], obs[3]]), g["idx"])
+
+
+def test_hmm_training_signature_and_prints(tmp_path, monkeypatch):
+    g = load_golden("bw_converge_eps")
+    corpus = split_corpus(g)
+    monkeypatch.chdir(tmp_path)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        A, B, pi = hmm_training.hmm_training(corpus[0], N=4, M=16, epsilon=float(g["epsilon"]), max_iterations=60,
+                                             show_progress=True, word_name="nofile", load_initial_params=True)
+    out = buf.getvalue()
+    it = int(g["iters"][0])
+    assert "Could not load saved model for word 'nofile'" in out and "Using default transition matrix" in out
+    assert f"Converged after {it} iterations" in out and out.count("Iteration ") == it
+    assert f"Log-likelihood: {g['ll_hist'][0, it - 1]:.6f}" in out
+    assert_close(A, g["A"][0], "A"); assert_close(B, g["B"][0], "B"); assert_close(pi, g["pi"][0], "pi")
+    with pytest.raises(IndexError):  # the reference's defaults are 4-state literals
+        hmm_training.hmm_training(corpus[0], N=5, M=16, max_iterations=1, show_progress=False, load_initial_params=False)
+    with pytest.raises(IndexError):  # empty recording: hmm_training.py:376
+        hmm_training.hmm_training([np.array([], dtype=np.int64)], N=4, M=16, max_iterations=1, show_progress=False,
+                                  load_initial_params=False)
+
+
+def test_warm_start_file_route(tmp_path, monkeypatch):
+    """../Data/Eighty-five-percent_20/<word>.json relative to the CWD (hmm_training.py:278)."""
+    g = load_golden("bw_warm_n6_m32")
+    corpus = split_corpus(g)
+    (tmp_path / "HMM").mkdir(); d = tmp_path / "Data" / "Eighty-five-percent_20"; d.mkdir(parents=True)
+    DataStorageHMM.save_hmm(HMMTrained(6, 32, g["A0"][1], g["B0"][1], g["pi0"][1], "w1"), str(d), print_messages=False)
+    monkeypatch.chdir(tmp_path / "HMM")
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        A, B, pi = hmm_training.hmm_training(corpus[1], N=6, M=32, max_iterations=5, show_progress=True, word_name="w1",
+                                             load_initial_params=True)
+    assert "Loaded initial parameters from saved model for word 'w1'" in buf.getvalue()
+    assert "Reached maximum iterations (5)" in buf.getvalue()
+    assert_close(A, g["A"][1], "A"); assert_close(B, g["B"][1], "B"); assert_close(pi, g["pi"][1], "pi")
+
+
+def test_training_with_save_and_test_hmm_end_to_end(tmp_path, monkeypatch):
+    """VQ -> Baum-Welch -> JSON -> recognition through the reference's entry points, checked
+    against the same pipeline on the CPU oracle."""
+    (tmp_path / "HMM").mkdir(); (tmp_path / "Data" / "CodeVector").mkdir(parents=True)
+    monkeypatch.chdir(tmp_path / "HMM")
+    rng = np.random.default_rng(3)
+    K = 32
+    C = synthetic.random_codebook(9, K)
+    words = ["alpha", "beta", "gamma"]
+
+    def utterances(w, n):
+        out = []
+        for _ in range(n):
+            T = int(rng.integers(30, 45))
+            seg = np.sort(rng.integers(0, 4, size=T))
+            cid = (8 * seg + 3 * w + rng.integers(0, 5, size=T)) % K
+            X = C[cid] + rng.normal(size=(T, 13)) * 0.5
+            out.append(_frames(X, f"{words[w]}_{len(out)}"))
+        return out
+
+    train = {words[w]: utterances(w, 12) for w in range(3)}
+    test = {words[w]: utterances(w, 4) for w in range(3)}
+    cents = _centroids(C)
+    with contextlib.redirect_stdout(io.StringIO()):
+        DataStorage.save_centroids(cents, str(tmp_path / "Data" / "CodeVector" / "codevector.json"))
+        models = [hmm_training.training_with_save(train[w], cents, w, max_iterations=4, show_progress=False) for w in words]
+    for m in models:
+        saved = json.load(open(tmp_path / "Data" / "ResultsHMM" / f"{m.word}.json"))
+        assert saved["states"] == 4 and saved["symbols"] == K and saved["word"] == m.word
+        assert np.array_equal(np.array(saved["B"]), m.B)
+    # oracle pipeline
+    for w, m in zip(words, models):
+        obs = [vq_oracle.encode(np.array([f.mfcc for f in rec]), C).astype(np.int64) for rec in train[w]]
+        Ao, Bo, pio = O.hmm_training(obs, N=4, M=K, max_iterations=4)
+        assert_close(m.A, Ao, "A"); assert_close(m.B, Bo, "B"); assert_close(m.Pi, pio, "pi")
+    with contextlib.redirect_stdout(io.StringIO()):
+        loaded = DataStorageHMM.load_all_hmms(str(tmp_path / "Data" / "ResultsHMM"), print_messages=False)
+        true, pred = hmm_testing.test_hmm(loaded, test, base_dir=str(tmp_path / "Data"))
+    assert true == [w for w in words for _ in range(4)]
+    seqs = [vq_oracle.encode(np.array([f.mfcc for f in rec]), C).astype(np.int64) for w in words for rec in test[w]]
+    ref = O.score_batch(seqs, [(m.A, m.B, m.Pi) for m in loaded])
+    want = [loaded[k].word if k >= 0 else "unknown" for k in O.argmax_first(ref)]
+    assert pred == want
+    assert sum(t == p for t, p in zip(true, pred)) >= 10  # the synthetic words are separable
+    one = hmm_testing.calculate_log_likelihood(seqs[0], loaded[0])
+    assert_close(one, ref[0, 0], "calculate_log_likelihood")
+    # batched trainer == per-word trainer
+    with contextlib.redirect_stdout(io.StringIO()):
+        batched = hmm_training.train_hmm_batched(train, cents, max_iterations=4, save=False)
+    for a, b in zip(batched, models):
+        assert_close(a.A, b.A, "batched A", rtol=1e-12); assert_close(a.B, b.B, "batched B", rtol=1e-12)
+
+
+def test_create_code_vector_side_effects(tmp_path):
+    g = load_golden("lbg_600_k32")
+    frames = _frames(g["X"])
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        cents, gens = cvf.createCodeVector(frames, centroids_quantity=32, max_iterations=100, epsilon=0.001,
+                                           save_updates=True, output_dir=str(tmp_path / "cv"))
+    assert "Creating codevector with 32 centroids..." in buf.getvalue()
+    assert [c.id for c in cents] == list(range(32)) and [len(x) for x in gens] == [1, 2, 4, 8, 16, 32]
+    assert_close(np.array([c.mfcc for c in cents]), g["C"], "centroids", atol=1e-12)
+    assert np.array_equal([f.parent_centroid_id for f in frames], g["assign"])  # inputs mutated in place (:502)
+    assert all(f.generation == 5 for f in frames)                                # (:479-480)
+    summary = json.load(open(tmp_path / "cv" / "training_summary.json"))
+    assert summary["total_frames"] == 600 and summary["max_generation"] == 5
+    reloaded = DataStorage.load_raw_data_mfcc(str(tmp_path / "cv" / "codevector_frames_updated.json"), print_messages=False)
+    assert reloaded[7].parent_centroid_id == frames[7].parent_centroid_id and np.array_equal(reloaded[7].mfcc, frames[7].mfcc)
+    with pytest.raises(ValueError):
+        cvf.createCodeVector([])

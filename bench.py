@@ -314,7 +314,12 @@ def main():
         }
         line.update(extras)
         print(json.dumps(line), flush=True)
+    # orderly teardown: free device memory and the library's events before NCCL goes away
+    torch.cuda.synchronize()
+    lib.hmmb_set_stream(None)
+    lib.hmmb_shutdown()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

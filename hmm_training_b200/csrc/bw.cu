@@ -50,17 +50,19 @@ k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4
          const double *__restrict__ A, const double *__restrict__ Bt, int M, int W, double *__restrict__ ll_out) {
     extern __shared__ double sB[];
     double *sBmax = sB + (size_t)M * 4;
+    unsigned char *sBmask = reinterpret_cast<unsigned char *>(sBmax + M);
     const int w = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double a[BIDIAG ? 7 : 16], p[4], rmax;
-    load_model4<BIDIAG>(pi, A, Bt, w, M, sB, sBmax, a, p, rmax);
+    Masks4 mk;
+    load_model4<BIDIAG>(pi, A, Bt, w, M, sB, sBmax, sBmask, a, p, rmax, mk);
     __syncthreads();
     const int b0 = blockIdx.x * blocks_per_cta;
     const int b1 = min(nblk, b0 + blocks_per_cta);
     for (int b = b0 + warp; b < b1; b += BW_WARPS) {
         const Blk bk = blks[b];
         const int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
-        const double ll = fwd4_run<BIDIAG, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, a, p, rmax, nullptr);
+        const double ll = fwd4_run<BIDIAG, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, sBmask, a, p, rmax, mk, nullptr);
         if (lane < bk.nseq) ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
     }
 }
@@ -581,7 +583,7 @@ template <bool BIDIAG>
 static int launch_special_estep(hmmb_bw *h) {
     SeqSet &s = h->s;
     if (s.ncta == 0) return HMMB_OK;
-    const size_t smem_f = (size_t)h->M * 5 * sizeof(double);
+    const size_t smem_f = (size_t)h->M * 5 * sizeof(double) + (size_t)((h->M + 15) & ~15);
     const size_t smem_b = (size_t)h->M * 4 * sizeof(double) * (1 + BW_WARPS) + (size_t)BW_THREADS * 4 * sizeof(double);
     HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwd4<BIDIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
@@ -752,7 +754,7 @@ static int launch_score_special(SeqSet &s, int W, const double *d_pi, const doub
     bpc = (bpc + BW_WARPS - 1) / BW_WARPS * BW_WARPS;
     bpc = std::min(bpc, 64);
     dim3 g((unsigned)((s.nblk + bpc - 1) / bpc), (unsigned)W);
-    const size_t smem = (size_t)s.M * 5 * sizeof(double);
+    const size_t smem = (size_t)s.M * 5 * sizeof(double) + (size_t)((s.M + 15) & ~15);
     HMMB_LAUNCH("score", k_score4<BIDIAG>, g, BW_THREADS, smem, s.d_blks, s.nblk, bpc, (const uint4 *)s.d_obs, s.d_len,
                 s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll);
     return HMMB_OK;

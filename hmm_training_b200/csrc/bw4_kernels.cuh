@@ -109,28 +109,79 @@ __device__ __forceinline__ double a_at(const double *a, int i, int j) {
     return a[i * 4 + j];
 }
 
+// Structural masks of a 4-state model (which log values are finite), kept as 4-bit sets:
+//   rowmask[i]   = { j : a_ij > 0 }
+//   lutF(m)      = union of rowmask[i] over i in m          (states reachable from the set m)
+//   lutB(m)      = { i : rowmask[i] meets m }               (states that can continue into m)
+// packed as sixteen 4-bit entries in a 64-bit word.
+struct Masks4 {
+    unsigned long long lutF, lutB;
+    unsigned pmask;
+};
+__device__ __forceinline__ unsigned lut4(unsigned long long lut, unsigned m) {
+    return (unsigned)(lut >> (m * 4u)) & 0xFu;
+}
+__device__ __forceinline__ Masks4 make_masks4(const double *__restrict__ Aw, const double *__restrict__ piw) {
+    unsigned row[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        row[i] = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) row[i] |= (__ldg(Aw + i * 4 + j) > 0.0) ? (1u << j) : 0u;
+    }
+    Masks4 mk;
+    mk.lutF = mk.lutB = 0ull;
+    for (unsigned m = 0; m < 16; ++m) {
+        unsigned f = 0u, b = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if ((m >> i) & 1u) f |= row[i];
+            if (row[i] & m) b |= 1u << i;
+        }
+        mk.lutF |= (unsigned long long)f << (m * 4u);
+        mk.lutB |= (unsigned long long)b << (m * 4u);
+    }
+    mk.pmask = 0u;
+    if (piw) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mk.pmask |= (__ldg(piw + j) > 0.0) ? (1u << j) : 0u;
+    }
+    return mk;
+}
+// smallest denormal if bit `j` of `m` is set, else +0.0 (integer pipe)
+__device__ __forceinline__ double tiny_if(unsigned m, int j) { return __hiloint2double(0, (int)((m >> j) & 1u)); }
+
 // One sequence per lane.  p[j] = pi[j], sB[sym*4+j] = B[j][sym] (shared), sBmax[sym] =
-// max_j B[j][sym], rmax = largest row sum of A.  op / sp include the lane offset.  Replaces
-// calculate_log_alpha (HMM/hmm_training.py:122-160) and the alpha init (:357-360); returns
-// log P(O|lambda) (:376-377), -inf for a structurally impossible sequence, or NaN when the
-// precision guard asks for the exact log-space recomputation.
+// max_j B[j][sym], sBmask[sym] = {j : B[j][sym] > 0}, rmax = largest row sum of A.  op / sp
+// include the lane offset.  Replaces calculate_log_alpha (HMM/hmm_training.py:122-160) and
+// the alpha init (:357-360); returns log P(O|lambda) (:376-377), -inf for a structurally
+// impossible sequence, or NaN when the precision guard asks for the exact log-space path.
 //
-// Precision guard, N = 4 flavour: every alive state whose value is denormal / clamped adds
-// 2^-1074 (its worst-case absolute error) to a scalar bound E, which is propagated with
-//   E' <= (E * rmax * max_j b_j(o_t) + seeds) * scale   >=  sum_j |error of alpha_t(j)|
-// (units of 2^-1000).  E stays ~1e-320 relative unless the states that carried the sequence
-// die; when it exceeds 1e-12 of the step's mass the sequence is handed over.
+// Which alpha_t(j) are finite in the reference is pure structure: m_t = lutF(m_{t-1}) &
+// bmask(o_t), a handful of integer operations per step.  The arithmetic keeps
+// "alpha-hat_t(j) > 0 <=> j in m_t" without any test by feeding the smallest denormal into the
+// FMA chains as the addend of every alive state: a product that underflows stays (barely)
+// positive, a normal value is unchanged.
+//
+// Precision guard: each step adds 4 * 2^-1074 (worst-case absolute error of four
+// denormal / clamped values) to a scalar bound E, propagated with
+//   E' = (E * rmax * max_j b_j(o_t) + seeds) * scale  >=  sum_j |error of alpha-hat_t(j)|
+// (units of 2^-1000).  E stays ~1e-320 of the step's mass unless the states that carried the
+// sequence die; when it exceeds 1e-12 the sequence is handed over.
 template <bool BIDIAG, bool SPILL>
 __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restrict__ op,
                                            const double *__restrict__ sB, const double *__restrict__ sBmax,
-                                           const double *a, const double (&p)[4], double rmax,
+                                           const unsigned char *__restrict__ sBmask, const double *a,
+                                           const double (&p)[4], double rmax, const Masks4 &mk,
                                            double2 *__restrict__ sp) {
     using S16 = Sym<uint16_t>;
     double al0 = 0.0, al1 = 0.0, al2 = 0.0, al3 = 0.0;
     double E = 0.0;  // error bound, units of 2^-1000
     long long esum = 0;
+    unsigned m = 0u;    // alive set
     bool stop = false;  // dead (impossible) or flagged for the exact path
     double ll = neg_inf();
+    const double tiny = tiny_pos();
     const int nch = (tmax + SPC4 - 1) / SPC4;
     uint4 wnext = nch > 0 ? __ldg(op) : make_uint4(0, 0, 0, 0);
     for (int c = 0; c < nch; ++c) {
@@ -143,28 +194,51 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
             if (t < T && !stop) {
                 const double2 b01 = *reinterpret_cast<const double2 *>(sB + sym * 4);
                 const double2 b23 = *reinterpret_cast<const double2 *>(sB + sym * 4 + 2);
-                double n0, n1, n2, n3;
-                if (t == 0) {
-                    n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
+                const unsigned r = (t == 0) ? mk.pmask : lut4(mk.lutF, m);  // reachable before emission
+                m = r & (unsigned)sBmask[sym];
+                double n0, n1, n2, n3, at0, at1, at2, at3;
+                if (m == 0xFu) {
+                    // ---- every state alive (the usual case)
+                    if (t == 0) {
+                        n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
+                    } else if (BIDIAG) {
+                        n0 = fma(al0, a[0], tiny);
+                        n1 = fma(al1, a[1], fma(al0, a[4], tiny));
+                        n2 = fma(al2, a[2], fma(al1, a[5], tiny));
+                        n3 = fma(al3, a[3], fma(al2, a[6], tiny));
+                    } else {
+                        n0 = fma(al3, a[12], fma(al2, a[8], fma(al1, a[4], fma(al0, a[0], tiny))));
+                        n1 = fma(al3, a[13], fma(al2, a[9], fma(al1, a[5], fma(al0, a[1], tiny))));
+                        n2 = fma(al3, a[14], fma(al2, a[10], fma(al1, a[6], fma(al0, a[2], tiny))));
+                        n3 = fma(al3, a[15], fma(al2, a[11], fma(al1, a[7], fma(al0, a[3], tiny))));
+                    }
+                    at0 = fma(n0, b01.x, tiny); at1 = fma(n1, b01.y, tiny);
+                    at2 = fma(n2, b23.x, tiny); at3 = fma(n3, b23.y, tiny);
+                } else if (m == 0u) {
+                    stop = true;  // no state can emit o_t: log P = -inf (:155-160)
+                    n0 = n1 = n2 = n3 = at0 = at1 = at2 = at3 = 0.0;
                 } else {
-                    matvec_fwd<BIDIAG>(a, al0, al1, al2, al3, n0, n1, n2, n3);
+                    // ---- some states structurally dead: masked addends keep them exactly 0
+                    const double r0 = tiny_if(r, 0), r1 = tiny_if(r, 1), r2 = tiny_if(r, 2), r3 = tiny_if(r, 3);
+                    if (t == 0) {
+                        n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
+                    } else {
+                        n0 = fma(al3, a_at<BIDIAG>(a, 3, 0), fma(al2, a_at<BIDIAG>(a, 2, 0), fma(al1, a_at<BIDIAG>(a, 1, 0), fma(al0, a_at<BIDIAG>(a, 0, 0), r0))));
+                        n1 = fma(al3, a_at<BIDIAG>(a, 3, 1), fma(al2, a_at<BIDIAG>(a, 2, 1), fma(al1, a_at<BIDIAG>(a, 1, 1), fma(al0, a_at<BIDIAG>(a, 0, 1), r1))));
+                        n2 = fma(al3, a_at<BIDIAG>(a, 3, 2), fma(al2, a_at<BIDIAG>(a, 2, 2), fma(al1, a_at<BIDIAG>(a, 1, 2), fma(al0, a_at<BIDIAG>(a, 0, 2), r2))));
+                        n3 = fma(al3, a_at<BIDIAG>(a, 3, 3), fma(al2, a_at<BIDIAG>(a, 2, 3), fma(al1, a_at<BIDIAG>(a, 1, 3), fma(al0, a_at<BIDIAG>(a, 0, 3), r3))));
+                    }
+                    at0 = fma(n0, b01.x, tiny_if(m, 0)); at1 = fma(n1, b01.y, tiny_if(m, 1));
+                    at2 = fma(n2, b23.x, tiny_if(m, 2)); at3 = fma(n3, b23.y, tiny_if(m, 3));
                 }
-                double at0 = n0 * b01.x, at1 = n1 * b01.y, at2 = n2 * b23.x, at3 = n3 * b23.y;
                 double ssum = (at0 + at1) + (at2 + at3);
-                double seeds = 0.0;
-                if (!(ssum >= TINY_STEP)) {
-                    // ---- the whole step is tiny (or impossible): exponent-split products
-#define HMMB_FIX_N(J, NJ)                                                                                      \
-    if (NJ == 0.0 && t > 0 &&                                                                                  \
-        ((al0 > 0.0 && a_at<BIDIAG>(a, 0, J) > 0.0) || (al1 > 0.0 && a_at<BIDIAG>(a, 1, J) > 0.0) ||           \
-         (al2 > 0.0 && a_at<BIDIAG>(a, 2, J) > 0.0) || (al3 > 0.0 && a_at<BIDIAG>(a, 3, J) > 0.0)))            \
-        NJ = tiny_pos();
-                    HMMB_FIX_N(0, n0) HMMB_FIX_N(1, n1) HMMB_FIX_N(2, n2) HMMB_FIX_N(3, n3)
+                if (!stop && !(ssum >= TINY_STEP)) {
+                    // ---- the whole step is tiny: exponent-split products (rare)
                     double o[4];
                     int Ex;
                     const int code = exact_products4(n0, n1, n2, n3, b01.x, b01.y, b23.x, b23.y, o, &Ex);
                     if (code == 0) {
-                        stop = true;  // no state can emit o_t: log P = -inf
+                        stop = true;
                     } else if ((code == 2 && t > 0) || E > 0.0) {
                         stop = true;  // the surviving states had lost their bits: exact path
                         ll = nan_mark();
@@ -173,25 +247,14 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
                         at0 = o[0]; at1 = o[1]; at2 = o[2]; at3 = o[3];
                         ssum = (at0 + at1) + (at2 + at3);
                     }
-                } else if (any_sub4(at0, at1, at2, at3)) {
-                    // ---- some state is zero / denormal: keep "alpha_j > 0 <=> structurally
-                    // reachable" (clamp) and count the seeds of the error bound
-                    HMMB_FIX_N(0, n0) HMMB_FIX_N(1, n1) HMMB_FIX_N(2, n2) HMMB_FIX_N(3, n3)
-#undef HMMB_FIX_N
-                    if (n0 > 0.0 && b01.x > 0.0 && is_sub(at0)) { if (at0 == 0.0) at0 = tiny_pos(); seeds += ERR_UNIT; }
-                    if (n1 > 0.0 && b01.y > 0.0 && is_sub(at1)) { if (at1 == 0.0) at1 = tiny_pos(); seeds += ERR_UNIT; }
-                    if (n2 > 0.0 && b23.x > 0.0 && is_sub(at2)) { if (at2 == 0.0) at2 = tiny_pos(); seeds += ERR_UNIT; }
-                    if (n3 > 0.0 && b23.y > 0.0 && is_sub(at3)) { if (at3 == 0.0) at3 = tiny_pos(); seeds += ERR_UNIT; }
                 }
                 if (!stop) {
                     const double sc = pow2_rescale(ssum, esum);
                     al0 = at0 * sc; al1 = at1 * sc; al2 = at2 * sc; al3 = at3 * sc;
-                    if ((E > 0.0) | (seeds > 0.0)) {
-                        E = (E * (rmax * sBmax[sym]) + seeds) * sc;
-                        if (!(E <= ERR_LIMIT)) {
-                            stop = true;
-                            ll = nan_mark();
-                        }
+                    E = fma(E, rmax * sBmax[sym], 4.0 * ERR_UNIT) * sc;
+                    if (!(E <= ERR_LIMIT)) {
+                        stop = true;
+                        ll = nan_mark();
                     }
                     if (t == T - 1 && !stop) ll = log((al0 + al1) + (al2 + al3)) + (double)esum * LN2;
                 }
@@ -206,12 +269,13 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
     return ll;
 }
 
-// CTA prologue shared by the forward-type kernels: B^T of word w -> shared memory, per-codeword
-// max_j b_j, A and pi -> registers, rmax = largest row sum of A.
+// CTA prologue shared by the forward-type kernels: B^T of word w -> shared memory with the
+// per-codeword max_j b_j and support mask, A and pi -> registers, rmax = largest row sum of A.
 template <bool BIDIAG>
 __device__ __forceinline__ void load_model4(const double *__restrict__ pi, const double *__restrict__ A,
                                             const double *__restrict__ Bt, int w, int M, double *sB, double *sBmax,
-                                            double *a, double (&p)[4], double &rmax) {
+                                            unsigned char *sBmask, double *a, double (&p)[4], double &rmax,
+                                            Masks4 &mk) {
     const int tid = threadIdx.x;
     const double2 *src = reinterpret_cast<const double2 *>(Bt + (size_t)w * M * 4);
     double2 *dst = reinterpret_cast<double2 *>(sB);
@@ -220,6 +284,7 @@ __device__ __forceinline__ void load_model4(const double *__restrict__ pi, const
         dst[2 * e] = x;
         dst[2 * e + 1] = y;
         sBmax[e] = fmax(fmax(x.x, x.y), fmax(y.x, y.y));
+        sBmask[e] = (unsigned char)((x.x > 0.0 ? 1 : 0) | (x.y > 0.0 ? 2 : 0) | (y.x > 0.0 ? 4 : 0) | (y.y > 0.0 ? 8 : 0));
     }
     const double *Aw = A + (size_t)w * 16;
     rmax = 0.0;
@@ -237,6 +302,7 @@ __device__ __forceinline__ void load_model4(const double *__restrict__ pi, const
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) p[q] = __ldg(pi + (size_t)w * 4 + q);
+    mk = make_masks4(Aw, pi + (size_t)w * 4);
 }
 
 template <bool BIDIAG>
@@ -258,20 +324,22 @@ k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
           const int32_t *__restrict__ len_sorted, const double *__restrict__ pi, const double *__restrict__ A,
           const double *__restrict__ Bt, int M, double2 *__restrict__ spill, double *__restrict__ ll_seq,
           const int32_t *__restrict__ active, uint8_t *__restrict__ flag) {
-    extern __shared__ double sB[];  // [M][4] B^T, then [M] per-codeword max
+    extern __shared__ double sB[];  // [M][4] B^T, [M] per-codeword max, [M] support masks (u8)
     double *sBmax = sB + (size_t)M * 4;
+    unsigned char *sBmask = reinterpret_cast<unsigned char *>(sBmax + M);
     const CtaWork cw = work[blockIdx.x];
     if (!active[cw.word]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double a[BIDIAG ? 7 : 16], p[4], rmax;
-    load_model4<BIDIAG>(pi, A, Bt, cw.word, M, sB, sBmax, a, p, rmax);
+    Masks4 mk;
+    load_model4<BIDIAG>(pi, A, Bt, cw.word, M, sB, sBmax, sBmask, a, p, rmax, mk);
     __syncthreads();
     for (int b = cw.blk_begin + warp; b < cw.blk_end; b += BW_WARPS) {
         const Blk bk = blks[b];
         int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
         if (T > 0 && flag[bk.first + lane]) T = 0;  // handled by the exact log-space kernel
-        const double ll = fwd4_run<BIDIAG, true>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, a, p, rmax,
-                                                 spill + bk.spill_base * 64 + lane);
+        const double ll = fwd4_run<BIDIAG, true>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, sBmask, a, p, rmax,
+                                                 mk, spill + bk.spill_base * 64 + lane);
         if (T > 0) {
             ll_seq[bk.first + lane] = ll;
             if (ll != ll) flag[bk.first + lane] = 1;  // precision guard: hand over (sticky)
@@ -280,15 +348,13 @@ k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
 }
 
 // ---------------------------------------------------------------- backward + accumulate
-// Warp-private emission-count update in precomputed rank order (see k_repack_blocks4).  Lanes
-// of rank 0 (the common case) have distinct codewords; their read-modify-write is split
-// around the next step's arithmetic by the caller so the shared-memory latency is hidden.
-// Ranks >= 1 follow here, one conflict-free round per rank.
-__device__ __forceinline__ void cnt_update4_rest(double *__restrict__ cw, bool act, unsigned sym, int rank, double g0,
-                                                 double g1, double g2, double g3) {
+// Warp-private emission-count update in precomputed rank order (see k_repack_blocks4): one
+// conflict-free read-modify-write round per rank, rank 0 (distinct codewords) being the bulk.
+__device__ __forceinline__ void cnt_update4(double *__restrict__ cw, bool act, unsigned sym, int rank, double g0,
+                                            double g1, double g2, double g3) {
     const int maxrank = __reduce_max_sync(0xffffffffu, act ? rank : 0);
     double2 *row = reinterpret_cast<double2 *>(cw + sym * 4);
-    for (int r = 1; r <= maxrank; ++r) {
+    for (int r = 0; r <= maxrank; ++r) {
         if (act && rank == r) {
             double2 c01 = row[0], c23 = row[1];
             c01.x += g0; c01.y += g1; c23.x += g2; c23.y += g3;
@@ -415,6 +481,9 @@ __device__ __noinline__ void bwd4_step_slow(Bwd4State<BIDIAG> &st, const double 
 }
 
 // Partial layout per CTA (and accumulator layout per word): [pi N][xi N*N][cnt M*N].
+//
+// The time loop is unrolled by two with fixed roles per parity of t, so that the two-deep
+// alpha-hat prefetch (P0 / P1) needs no register-to-register copies.
 template <bool BIDIAG>
 __global__ void __launch_bounds__(BW_THREADS, BIDIAG ? 4 : 3)
 k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
@@ -443,7 +512,12 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     }
     double a[BIDIAG ? 7 : 16];
     load_A4<BIDIAG>(A + (size_t)cw.word * 16, a);
-    const bool lean_ok = b_has_zero[cw.word] == 0;  // B > 0 everywhere: v_j > 0 <=> beta_j > 0
+    // lean path precondition (structure only): B > 0 everywhere and no all-zero row in A, so
+    // every beta_t(i) and every v_j is finite in the reference; whether every alpha_t(i) is
+    // finite is read off the spilled values
+    const Masks4 mk = make_masks4(A + (size_t)cw.word * 16, nullptr);
+    const bool lean_ok = (b_has_zero[cw.word] == 0) && (lut4(mk.lutB, 0xFu) == 0xFu);
+    const double tiny = tiny_pos();
     __syncthreads();
 
     double *cntw = sCnt + (size_t)warp * M * 4;
@@ -466,128 +540,114 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         st.vpos = false;
         const uint4 *op = obs_blk + bk.obs_base + lane;
         const double2 *sp = spill + bk.spill_base * 64 + lane;
-        // alpha-hat prefetch, two steps deep: (pa*, t = tcur) and (pb*, t = tcur - 1)
-        const int ttop = bk.tmax - 1;
-        double2 pa01 = make_double2(0.0, 0.0), pa23 = pa01, pb01 = pa01, pb23 = pa01;
-        if (ttop < T) { pa01 = __ldcs(sp + (size_t)ttop * 64); pa23 = __ldcs(sp + (size_t)ttop * 64 + 32); }
-        if (ttop >= 1 && ttop - 1 < T) { pb01 = __ldcs(sp + (size_t)(ttop - 1) * 64); pb23 = __ldcs(sp + (size_t)(ttop - 1) * 64 + 32); }
         const int nch = (bk.tmax + SPC4 - 1) / SPC4;
-        // emission-count update of the previous step, still pending (software pipelining)
-        bool pact = false;
-        unsigned psym = 0u;
-        int prank = 0;
-        double pg0 = 0.0, pg1 = 0.0, pg2 = 0.0, pg3 = 0.0;
+        // alpha-hat prefetch: P0 holds the next even time step, P1 the next odd one
+        double2 P0_01 = make_double2(0.0, 0.0), P0_23 = P0_01, P1_01 = P0_01, P1_23 = P0_01;
+        {
+            const int ta = bk.tmax - 1, tb = bk.tmax - 2;  // the first two steps of the block
+            double2 xa01 = P0_01, xa23 = P0_01, xb01 = P0_01, xb23 = P0_01;
+            if (ta < T) { xa01 = __ldcs(sp + (size_t)ta * 64); xa23 = __ldcs(sp + (size_t)ta * 64 + 32); }
+            if (tb >= 0 && tb < T) { xb01 = __ldcs(sp + (size_t)tb * 64); xb23 = __ldcs(sp + (size_t)tb * 64 + 32); }
+            if (ta & 1) { P1_01 = xa01; P1_23 = xa23; P0_01 = xb01; P0_23 = xb23; }
+            else        { P0_01 = xa01; P0_23 = xa23; P1_01 = xb01; P1_23 = xb23; }
+        }
         uint4 wnext = __ldg(op + (size_t)(nch - 1) * 32);
+
+// One backward step at time T_ (parity C_ = T_ & 1 is a literal; O_ = the other parity).
+#define HMMB_BWD_STEP(T_, C_, O_)                                                                                   \
+    {                                                                                                               \
+        const int t = (T_);                                                                                         \
+        const unsigned packed = S16::pop_back(w);                                                                   \
+        if (t < bk.tmax) { /* warp-uniform */                                                                       \
+            const unsigned sym = packed & SYM_MASK;                                                                 \
+            const bool act = t < T;                                                                                 \
+            const double al0 = P##C_##_01.x, al1 = P##C_##_01.y, al2 = P##C_##_23.x, al3 = P##C_##_23.y;            \
+            if (t >= 2 && t - 2 < T) {                                                                              \
+                P##C_##_01 = __ldcs(sp + (size_t)(t - 2) * 64);                                                     \
+                P##C_##_23 = __ldcs(sp + (size_t)(t - 2) * 64 + 32);                                                \
+            }                                                                                                       \
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;                                                          \
+            if (act) {                                                                                              \
+                bool done = false;                                                                                  \
+                if (lean_ok && st.vpos && t != T - 1) {                                                             \
+                    /* lean path: beta_t(i) ~ q_i = sum_j a_ij v_j (:163-199); gamma_t(i) = al_i q_i / norm   */   \
+                    /* (:389-394); xi_t(i,j) = al_i a_ij v_j / norm (:397-410); norm = sum_i al_i q_i.  The    */   \
+                    /* denormal addends keep a finite-but-underflowed log value (barely) positive.            */   \
+                    const double v0 = st.v0, v1 = st.v1, v2 = st.v2, v3 = st.v3;                                    \
+                    double q0, q1, q2, q3;                                                                          \
+                    if (BIDIAG) {                                                                                   \
+                        q0 = fma(a[4], v1, fma(a[0], v0, tiny));                                                    \
+                        q1 = fma(a[5], v2, fma(a[1], v1, tiny));                                                    \
+                        q2 = fma(a[6], v3, fma(a[2], v2, tiny));                                                    \
+                        q3 = fma(a[3], v3, tiny);                                                                   \
+                    } else {                                                                                        \
+                        q0 = fma(a[3], v3, fma(a[2], v2, fma(a[1], v1, fma(a[0], v0, tiny))));                      \
+                        q1 = fma(a[7], v3, fma(a[6], v2, fma(a[5], v1, fma(a[4], v0, tiny))));                      \
+                        q2 = fma(a[11], v3, fma(a[10], v2, fma(a[9], v1, fma(a[8], v0, tiny))));                    \
+                        q3 = fma(a[15], v3, fma(a[14], v2, fma(a[13], v1, fma(a[12], v0, tiny))));                  \
+                    }                                                                                               \
+                    const double qs = (q0 + q1) + (q2 + q3);                                                        \
+                    const double c0 = al0 * q0, c1 = al1 * q1, c2 = al2 * q2, c3 = al3 * q3;                        \
+                    const double norm = (c0 + c1) + (c2 + c3);                                                      \
+                    const double sc = pow2_rescale_noacc(qs);                                                       \
+                    const double h0 = q0 * sc, h1 = q1 * sc, h2 = q2 * sc, h3 = q3 * sc; /* beta-hat_t */          \
+                    const double2 b01 = *reinterpret_cast<const double2 *>(sB + sym * 4);                           \
+                    const double2 b23 = *reinterpret_cast<const double2 *>(sB + sym * 4 + 2);                       \
+                    const double nv0 = fma(b01.x, h0, tiny), nv1 = fma(b01.y, h1, tiny);                            \
+                    const double nv2 = fma(b23.x, h2, tiny), nv3 = fma(b23.y, h3, tiny);                            \
+                    const double vs = (nv0 + nv1) + (nv2 + nv3);                                                    \
+                    if ((norm >= LEAN_MIN) & (qs >= LEAN_MIN) & (vs >= LEAN_MIN) & all_pos4(al0, al1, al2, al3)) {  \
+                        const double r = 1.0 / norm;                                                                \
+                        g0 = fma(c0, r, tiny); g1 = fma(c1, r, tiny); g2 = fma(c2, r, tiny); g3 = fma(c3, r, tiny); \
+                        const double u0 = al0 * r, u1 = al1 * r, u2 = al2 * r, u3 = al3 * r;                        \
+                        if (BIDIAG) {                                                                               \
+                            st.X[0] = fma(u0, v0, st.X[0]); st.X[1] = fma(u1, v1, st.X[1]);                         \
+                            st.X[2] = fma(u2, v2, st.X[2]); st.X[3] = fma(u3, v3, st.X[3]);                         \
+                            st.X[4] = fma(u0, v1, st.X[4]); st.X[5] = fma(u1, v2, st.X[5]);                         \
+                            st.X[6] = fma(u2, v3, st.X[6]);                                                         \
+                        } else {                                                                                    \
+                            st.X[0] = fma(u0, v0, st.X[0]);   st.X[1] = fma(u0, v1, st.X[1]);                       \
+                            st.X[2] = fma(u0, v2, st.X[2]);   st.X[3] = fma(u0, v3, st.X[3]);                       \
+                            st.X[4] = fma(u1, v0, st.X[4]);   st.X[5] = fma(u1, v1, st.X[5]);                       \
+                            st.X[6] = fma(u1, v2, st.X[6]);   st.X[7] = fma(u1, v3, st.X[7]);                       \
+                            st.X[8] = fma(u2, v0, st.X[8]);   st.X[9] = fma(u2, v1, st.X[9]);                       \
+                            st.X[10] = fma(u2, v2, st.X[10]); st.X[11] = fma(u2, v3, st.X[11]);                     \
+                            st.X[12] = fma(u3, v0, st.X[12]); st.X[13] = fma(u3, v1, st.X[13]);                     \
+                            st.X[14] = fma(u3, v2, st.X[14]); st.X[15] = fma(u3, v3, st.X[15]);                     \
+                        }                                                                                           \
+                        st.seenX = 0xffffu; /* every alpha_i > 0 and every v_j > 0 */                               \
+                        st.v0 = nv0; st.v1 = nv1; st.v2 = nv2; st.v3 = nv3;                                         \
+                        done = true;                                                                                \
+                    }                                                                                               \
+                }                                                                                                   \
+                if (!done) {                                                                                        \
+                    /* the careful step works on a stack copy so that `st` itself never has its address */         \
+                    /* taken and stays in registers on the lean path                                     */         \
+                    Bwd4State<BIDIAG> tmp = st;                                                                     \
+                    double g[4];                                                                                    \
+                    bwd4_step_slow<BIDIAG>(tmp, a, sB, sym, t == T - 1, al0, al1, al2, al3, g);                     \
+                    st = tmp;                                                                                       \
+                    g0 = g[0]; g1 = g[1]; g2 = g[2]; g3 = g[3];                                                     \
+                }                                                                                                   \
+                if (t == 0) { /* (:415-426) */                                                                      \
+                    mypi[0] += g0; mypi[1] += g1; mypi[2] += g2; mypi[3] += g3;                                     \
+                }                                                                                                   \
+            }                                                                                                       \
+            /* emission-count numerators (:460-500): warp-private rows, conflict-free rank order */                \
+            cnt_update4(cntw, act, sym, (int)(packed >> SYM_BITS), g0, g1, g2, g3);                                 \
+        }                                                                                                           \
+    }
+
         for (int c = nch - 1; c >= 0; --c) {
             uint4 w = wnext;
             if (c > 0) wnext = __ldg(op + (size_t)(c - 1) * 32);  // prefetch the next 8 codewords
-#pragma unroll 2
-            for (int s = SPC4 - 1; s >= 0; --s) {
-                const int t = c * SPC4 + s;
-                const unsigned packed = S16::pop_back(w);
-                if (t >= bk.tmax) continue;  // warp-uniform
-                const unsigned sym = packed & SYM_MASK;
-                const int rank = (int)(packed >> SYM_BITS);
-                const bool act = t < T;
-                // round 0 of the pending update: issue the shared-memory loads now ...
-                const bool p0 = pact && prank == 0;
-                double2 *prow = reinterpret_cast<double2 *>(cntw + psym * 4);
-                double2 r01 = make_double2(0.0, 0.0), r23 = r01;
-                if (p0) { r01 = prow[0]; r23 = prow[1]; }
-                const double al0 = pa01.x, al1 = pa01.y, al2 = pa23.x, al3 = pa23.y;
-                pa01 = pb01; pa23 = pb23;
-                if (t >= 2 && t - 2 < T) {
-                    pb01 = __ldcs(sp + (size_t)(t - 2) * 64);
-                    pb23 = __ldcs(sp + (size_t)(t - 2) * 64 + 32);
-                }
-                double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
-                if (act) {
-                    bool done = false;
-                    if (lean_ok && st.vpos && t != T - 1) {
-                        // ---- lean path: every state of the step alive, sums far from underflow.
-                        // beta_t(i) ~ q_i = sum_j a_ij v_j  (:163-199);  gamma_t(i) = al_i q_i / norm
-                        // (:389-394);  xi_t(i,j) = al_i a_ij v_j / norm  (:397-410), norm = sum_i al_i q_i
-                        const double v0 = st.v0, v1 = st.v1, v2 = st.v2, v3 = st.v3;
-                        double q0, q1, q2, q3;
-                        if (BIDIAG) {
-                            q0 = a[0] * v0 + a[4] * v1;
-                            q1 = a[1] * v1 + a[5] * v2;
-                            q2 = a[2] * v2 + a[6] * v3;
-                            q3 = a[3] * v3;
-                        } else {
-                            q0 = a[0] * v0 + a[1] * v1 + a[2] * v2 + a[3] * v3;
-                            q1 = a[4] * v0 + a[5] * v1 + a[6] * v2 + a[7] * v3;
-                            q2 = a[8] * v0 + a[9] * v1 + a[10] * v2 + a[11] * v3;
-                            q3 = a[12] * v0 + a[13] * v1 + a[14] * v2 + a[15] * v3;
-                        }
-                        const double qs = (q0 + q1) + (q2 + q3);
-                        double c0 = al0 * q0, c1 = al1 * q1, c2 = al2 * q2, c3 = al3 * q3;
-                        const double norm = (c0 + c1) + (c2 + c3);
-                        const double sc = pow2_rescale_noacc(qs);
-                        const double h0 = q0 * sc, h1 = q1 * sc, h2 = q2 * sc, h3 = q3 * sc;  // beta-hat_t
-                        const double2 b01 = *reinterpret_cast<const double2 *>(sB + sym * 4);
-                        const double2 b23 = *reinterpret_cast<const double2 *>(sB + sym * 4 + 2);
-                        double nv0 = b01.x * h0, nv1 = b01.y * h1, nv2 = b23.x * h2, nv3 = b23.y * h3;
-                        const double vs = (nv0 + nv1) + (nv2 + nv3);
-                        if ((norm >= LEAN_MIN) & (qs >= LEAN_MIN) & (vs >= LEAN_MIN) & all_pos4(al0, al1, al2, al3) &
-                            all_pos4(q0, q1, q2, q3)) {
-                            const double r = 1.0 / norm;
-                            // a finite log value that underflows stays (barely) positive
-                            g0 = zero_to_tiny(c0 * r); g1 = zero_to_tiny(c1 * r);
-                            g2 = zero_to_tiny(c2 * r); g3 = zero_to_tiny(c3 * r);
-                            const double u0 = al0 * r, u1 = al1 * r, u2 = al2 * r, u3 = al3 * r;
-                            if (BIDIAG) {
-                                st.X[0] = fma(u0, v0, st.X[0]); st.X[1] = fma(u1, v1, st.X[1]);
-                                st.X[2] = fma(u2, v2, st.X[2]); st.X[3] = fma(u3, v3, st.X[3]);
-                                st.X[4] = fma(u0, v1, st.X[4]); st.X[5] = fma(u1, v2, st.X[5]);
-                                st.X[6] = fma(u2, v3, st.X[6]);
-                            } else {
-                                st.X[0] = fma(u0, v0, st.X[0]);   st.X[1] = fma(u0, v1, st.X[1]);   st.X[2] = fma(u0, v2, st.X[2]);   st.X[3] = fma(u0, v3, st.X[3]);
-                                st.X[4] = fma(u1, v0, st.X[4]);   st.X[5] = fma(u1, v1, st.X[5]);   st.X[6] = fma(u1, v2, st.X[6]);   st.X[7] = fma(u1, v3, st.X[7]);
-                                st.X[8] = fma(u2, v0, st.X[8]);   st.X[9] = fma(u2, v1, st.X[9]);   st.X[10] = fma(u2, v2, st.X[10]); st.X[11] = fma(u2, v3, st.X[11]);
-                                st.X[12] = fma(u3, v0, st.X[12]); st.X[13] = fma(u3, v1, st.X[13]); st.X[14] = fma(u3, v2, st.X[14]); st.X[15] = fma(u3, v3, st.X[15]);
-                            }
-                            st.seenX = 0xffffu;  // every alpha_i > 0 and (vpos) every v_j > 0
-                            // B > 0 and beta-hat > 0: v stays positive (clamped if the product underflows)
-                            st.v0 = zero_to_tiny(nv0); st.v1 = zero_to_tiny(nv1);
-                            st.v2 = zero_to_tiny(nv2); st.v3 = zero_to_tiny(nv3);
-                            done = true;
-                        }
-                    }
-                    if (!done) {
-                        // the careful step works on a stack copy so that `st` itself never has
-                        // its address taken and stays in registers on the lean path
-                        Bwd4State<BIDIAG> tmp = st;
-                        double g[4];
-                        bwd4_step_slow<BIDIAG>(tmp, a, sB, sym, t == T - 1, al0, al1, al2, al3, g);
-                        st = tmp;
-                        g0 = g[0]; g1 = g[1]; g2 = g[2]; g3 = g[3];
-                    }
-                    if (t == 0) {  // (:415-426)
-                        mypi[0] += g0; mypi[1] += g1; mypi[2] += g2; mypi[3] += g3;
-                    }
-                }
-                // ... and finish it after this step's arithmetic  (:460-500 numerators)
-                if (p0) {
-                    r01.x += pg0; r01.y += pg1; r23.x += pg2; r23.y += pg3;
-                    prow[0] = r01; prow[1] = r23;
-                }
-                __syncwarp();
-                cnt_update4_rest(cntw, pact, psym, prank, pg0, pg1, pg2, pg3);
-                pact = act; psym = sym; prank = rank;
-                pg0 = g0; pg1 = g1; pg2 = g2; pg3 = g3;
+#pragma unroll 1
+            for (int pr = SPC4 / 2 - 1; pr >= 0; --pr) {
+                HMMB_BWD_STEP(c * SPC4 + 2 * pr + 1, 1, 0)
+                HMMB_BWD_STEP(c * SPC4 + 2 * pr, 0, 1)
             }
         }
-        {   // drain the pipeline: the last step's update
-            double2 *prow = reinterpret_cast<double2 *>(cntw + psym * 4);
-            if (pact && prank == 0) {
-                double2 r01 = prow[0], r23 = prow[1];
-                r01.x += pg0; r01.y += pg1; r23.x += pg2; r23.y += pg3;
-                prow[0] = r01; prow[1] = r23;
-            }
-            __syncwarp();
-            cnt_update4_rest(cntw, pact, psym, prank, pg0, pg1, pg2, pg3);
-        }
+#undef HMMB_BWD_STEP
         if (st.imprecise) {  // sticky hand-over; the host redoes this E-step once (hmmb_bw_iterate)
             flag[bk.first + lane] = 1;
             atomicAdd(new_flags, 1);

@@ -62,7 +62,8 @@ k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4
     for (int b = b0 + warp; b < b1; b += BW_WARPS) {
         const Blk bk = blks[b];
         const int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
-        const double ll = fwd4_run<BIDIAG, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, sBmask, a, p, rmax, mk, nullptr);
+        const double ll = fwd4_run<BIDIAG, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, reinterpret_cast<const double2 *>(sB),
+                                                  reinterpret_cast<const double2 *>(sB) + M, sBmax, sBmask, a, p, rmax, mk, nullptr);
         if (lane < bk.nseq) ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
     }
 }

@@ -151,7 +151,9 @@ __device__ __forceinline__ Masks4 make_masks4(const double *__restrict__ Aw, con
 // smallest denormal if bit `j` of `m` is set, else +0.0 (integer pipe)
 __device__ __forceinline__ double tiny_if(unsigned m, int j) { return __hiloint2double(0, (int)((m >> j) & 1u)); }
 
-// One sequence per lane.  p[j] = pi[j], sB[sym*4+j] = B[j][sym] (shared), sBmax[sym] =
+// One sequence per lane.  p[j] = pi[j]; B^T of the word in shared memory as two arrays of
+// double2, sB01[sym] = (b_0, b_1)(sym) and sB23[sym] = (b_2, b_3)(sym) — 16-byte rows give a
+// random gather 8 distinct bank slots instead of 4 with 32-byte rows; sBmax[sym] =
 // max_j B[j][sym], sBmask[sym] = {j : B[j][sym] > 0}, rmax = largest row sum of A.  op / sp
 // include the lane offset.  Replaces calculate_log_alpha (HMM/hmm_training.py:122-160) and
 // the alpha init (:357-360); returns log P(O|lambda) (:376-377), -inf for a structurally
@@ -170,7 +172,8 @@ __device__ __forceinline__ double tiny_if(unsigned m, int j) { return __hiloint2
 // sequence die; when it exceeds 1e-12 the sequence is handed over.
 template <bool BIDIAG, bool SPILL>
 __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restrict__ op,
-                                           const double *__restrict__ sB, const double *__restrict__ sBmax,
+                                           const double2 *__restrict__ sB01, const double2 *__restrict__ sB23,
+                                           const double *__restrict__ sBmax,
                                            const unsigned char *__restrict__ sBmask, const double *a,
                                            const double (&p)[4], double rmax, const Masks4 &mk,
                                            double2 *__restrict__ sp) {
@@ -192,8 +195,7 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
             const int t = c * SPC4 + s;
             const unsigned sym = S16::pop_front(w) & SYM_MASK;
             if (t < T && !stop) {
-                const double2 b01 = *reinterpret_cast<const double2 *>(sB + sym * 4);
-                const double2 b23 = *reinterpret_cast<const double2 *>(sB + sym * 4 + 2);
+                const double2 b01 = sB01[sym], b23 = sB23[sym];
                 const unsigned r = (t == 0) ? mk.pmask : lut4(mk.lutF, m);  // reachable before emission
                 m = r & (unsigned)sBmask[sym];
                 double n0, n1, n2, n3, at0, at1, at2, at3;
@@ -281,8 +283,8 @@ __device__ __forceinline__ void load_model4(const double *__restrict__ pi, const
     double2 *dst = reinterpret_cast<double2 *>(sB);
     for (int e = tid; e < M; e += BW_THREADS) {
         const double2 x = __ldg(src + 2 * e), y = __ldg(src + 2 * e + 1);
-        dst[2 * e] = x;
-        dst[2 * e + 1] = y;
+        dst[e] = x;      // sB01
+        dst[M + e] = y;  // sB23
         sBmax[e] = fmax(fmax(x.x, x.y), fmax(y.x, y.y));
         sBmask[e] = (unsigned char)((x.x > 0.0 ? 1 : 0) | (x.y > 0.0 ? 2 : 0) | (y.x > 0.0 ? 4 : 0) | (y.y > 0.0 ? 8 : 0));
     }
@@ -338,7 +340,8 @@ k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         const Blk bk = blks[b];
         int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
         if (T > 0 && flag[bk.first + lane]) T = 0;  // handled by the exact log-space kernel
-        const double ll = fwd4_run<BIDIAG, true>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, sBmask, a, p, rmax,
+        const double ll = fwd4_run<BIDIAG, true>(T, bk.tmax, obs_blk + bk.obs_base + lane, reinterpret_cast<const double2 *>(sB),
+                                                 reinterpret_cast<const double2 *>(sB) + M, sBmax, sBmask, a, p, rmax,
                                                  mk, spill + bk.spill_base * 64 + lane);
         if (T > 0) {
             ll_seq[bk.first + lane] = ll;
@@ -350,15 +353,14 @@ k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
 // ---------------------------------------------------------------- backward + accumulate
 // Warp-private emission-count update in precomputed rank order (see k_repack_blocks4): one
 // conflict-free read-modify-write round per rank, rank 0 (distinct codewords) being the bulk.
-__device__ __forceinline__ void cnt_update4(double *__restrict__ cw, bool act, unsigned sym, int rank, double g0,
-                                            double g1, double g2, double g3) {
+__device__ __forceinline__ void cnt_update4(double2 *__restrict__ cw01, double2 *__restrict__ cw23, bool act,
+                                            unsigned sym, int rank, double g0, double g1, double g2, double g3) {
     const int maxrank = __reduce_max_sync(0xffffffffu, act ? rank : 0);
-    double2 *row = reinterpret_cast<double2 *>(cw + sym * 4);
     for (int r = 0; r <= maxrank; ++r) {
         if (act && rank == r) {
-            double2 c01 = row[0], c23 = row[1];
+            double2 c01 = cw01[sym], c23 = cw23[sym];
             c01.x += g0; c01.y += g1; c23.x += g2; c23.y += g3;
-            row[0] = c01; row[1] = c23;
+            cw01[sym] = c01; cw23[sym] = c23;
         }
         __syncwarp();
     }
@@ -377,6 +379,8 @@ __device__ __forceinline__ double zero_to_tiny(double x) {
     const int hi = __double2hiint(x), lo = __double2loint(x);
     return __hiloint2double(hi, lo | (((hi | lo) == 0) ? 1 : 0));
 }
+constexpr int BWD_L2_PREFETCH = 12;  // steps ahead of use for prefetch.global.L2 of the alpha spill
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr double LEAN_MIN = 0x1p-500;  // the lean backward step needs its three sums above this
 
 // State of one lane's backward recursion.
@@ -393,7 +397,8 @@ struct Bwd4State {
 // Taken when the lean path's two group tests fail, at the first step of a sequence, and for
 // words whose B holds exact zeros.  Returns gamma in g[], updates st (v, X, seenX).
 template <bool BIDIAG>
-__device__ __noinline__ void bwd4_step_slow(Bwd4State<BIDIAG> &st, const double *a, const double *__restrict__ sB,
+__device__ __noinline__ void bwd4_step_slow(Bwd4State<BIDIAG> &st, const double *a, const double2 *__restrict__ sB01,
+                                            const double2 *__restrict__ sB23,
                                             unsigned sym, bool last, double al0, double al1, double al2, double al3,
                                             double *g) {
     double v0 = st.v0, v1 = st.v1, v2 = st.v2, v3 = st.v3;
@@ -460,8 +465,7 @@ __device__ __noinline__ void bwd4_step_slow(Bwd4State<BIDIAG> &st, const double 
                     (al3 > 0.0 ? mv << 12 : 0u);
     }
     // v_j = b_j(o_t) beta-hat_t(j) for step t-1
-    const double2 b01 = *reinterpret_cast<const double2 *>(sB + sym * 4);
-    const double2 b23 = *reinterpret_cast<const double2 *>(sB + sym * 4 + 2);
+    const double2 b01 = sB01[sym], b23 = sB23[sym];
     v0 = b01.x * h0; v1 = b01.y * h1; v2 = b23.x * h2; v3 = b23.y * h3;
     const double vs = (v0 + v1) + (v2 + v3);
     if (!(vs >= TINY_STEP)) {
@@ -493,8 +497,8 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
           uint8_t *__restrict__ flag, int32_t *__restrict__ new_flags) {
     using S16 = Sym<uint16_t>;
     extern __shared__ double smem[];
-    double *sB = smem;                              // [M][4]
-    double *sCnt = smem + (size_t)M * 4;            // [4 warps][M][4]
+    double *sB = smem;                              // B^T: [M] double2 (b0,b1) then [M] double2 (b2,b3)
+    double *sCnt = smem + (size_t)M * 4;            // [4 warps] x { [M] double2 (j=0,1), [M] double2 (j=2,3) }
     double *sPi = sCnt + (size_t)M * 4 * BW_WARPS;  // [128 threads][4] gamma_0 sums
     __shared__ double sRed[BW_WARPS][20];
     __shared__ unsigned sSeen;
@@ -506,7 +510,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     {
         const double2 *src = reinterpret_cast<const double2 *>(Bt + (size_t)cw.word * M * 4);
         double2 *dst = reinterpret_cast<double2 *>(sB);
-        for (int e = tid; e < M * 2; e += BW_THREADS) dst[e] = __ldg(src + e);
+        for (int e = tid; e < M * 2; e += BW_THREADS) dst[(e & 1) * M + (e >> 1)] = __ldg(src + e);
         for (int e = tid; e < M * 4 * BW_WARPS + BW_THREADS * 4; e += BW_THREADS) sCnt[e] = 0.0;  // counts + sPi
         if (tid == 0) sSeen = 0u;
     }
@@ -520,7 +524,8 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     const double tiny = tiny_pos();
     __syncthreads();
 
-    double *cntw = sCnt + (size_t)warp * M * 4;
+    double2 *cntw01 = reinterpret_cast<double2 *>(sCnt + (size_t)warp * M * 4), *cntw23 = cntw01 + M;
+    const double2 *sB01 = reinterpret_cast<const double2 *>(sB), *sB23 = sB01 + M;
     double *mypi = sPi + (size_t)tid * 4;
     Bwd4State<BIDIAG> st;
 #pragma unroll
@@ -566,6 +571,10 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                 P##C_##_01 = __ldcs(sp + (size_t)(t - 2) * 64);                                                     \
                 P##C_##_23 = __ldcs(sp + (size_t)(t - 2) * 64 + 32);                                                \
             }                                                                                                       \
+            if (t >= BWD_L2_PREFETCH && t - BWD_L2_PREFETCH < T) { /* pull the spill towards L2 well ahead */      \
+                prefetch_l2(sp + (size_t)(t - BWD_L2_PREFETCH) * 64);                                               \
+                prefetch_l2(sp + (size_t)(t - BWD_L2_PREFETCH) * 64 + 32);                                          \
+            }                                                                                                       \
             double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;                                                          \
             if (act) {                                                                                              \
                 bool done = false;                                                                                  \
@@ -591,8 +600,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                     const double norm = (c0 + c1) + (c2 + c3);                                                      \
                     const double sc = pow2_rescale_noacc(qs);                                                       \
                     const double h0 = q0 * sc, h1 = q1 * sc, h2 = q2 * sc, h3 = q3 * sc; /* beta-hat_t */          \
-                    const double2 b01 = *reinterpret_cast<const double2 *>(sB + sym * 4);                           \
-                    const double2 b23 = *reinterpret_cast<const double2 *>(sB + sym * 4 + 2);                       \
+                    const double2 b01 = sB01[sym], b23 = sB23[sym];                                                 \
                     const double nv0 = fma(b01.x, h0, tiny), nv1 = fma(b01.y, h1, tiny);                            \
                     const double nv2 = fma(b23.x, h2, tiny), nv3 = fma(b23.y, h3, tiny);                            \
                     const double vs = (nv0 + nv1) + (nv2 + nv3);                                                    \
@@ -625,7 +633,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                     /* taken and stays in registers on the lean path                                     */         \
                     Bwd4State<BIDIAG> tmp = st;                                                                     \
                     double g[4];                                                                                    \
-                    bwd4_step_slow<BIDIAG>(tmp, a, sB, sym, t == T - 1, al0, al1, al2, al3, g);                     \
+                    bwd4_step_slow<BIDIAG>(tmp, a, sB01, sB23, sym, t == T - 1, al0, al1, al2, al3, g);             \
                     st = tmp;                                                                                       \
                     g0 = g[0]; g1 = g[1]; g2 = g[2]; g3 = g[3];                                                     \
                 }                                                                                                   \
@@ -634,7 +642,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                 }                                                                                                   \
             }                                                                                                       \
             /* emission-count numerators (:460-500): warp-private rows, conflict-free rank order */                \
-            cnt_update4(cntw, act, sym, (int)(packed >> SYM_BITS), g0, g1, g2, g3);                                 \
+            cnt_update4(cntw01, cntw23, act, sym, (int)(packed >> SYM_BITS), g0, g1, g2, g3);                       \
         }                                                                                                           \
     }
 
@@ -694,7 +702,11 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         part[tid] = v;
     }
     for (int e = tid; e < M * 4; e += BW_THREADS)
-        part[20 + e] = ((sCnt[e] + sCnt[(size_t)M * 4 + e]) + sCnt[(size_t)M * 8 + e]) + sCnt[(size_t)M * 12 + e];
+    {
+        const int sym = e >> 2, j = e & 3;
+        const size_t o = (size_t)(j >> 1) * 2 * M + (size_t)sym * 2 + (j & 1);  // split (j=0,1) / (j=2,3) arrays
+        part[20 + e] = ((sCnt[o] + sCnt[(size_t)M * 4 + o]) + sCnt[(size_t)M * 8 + o]) + sCnt[(size_t)M * 12 + o];
+    }
 }
 
 }  // namespace hmmb

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhmmb200.so")
 SOURCES = ["context.cu", "vq.cu", "bw.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC,-fopenmp", "-shared", "--use_fast_math=false"]
 
 
 def _nvcc() -> str:

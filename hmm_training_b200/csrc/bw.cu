@@ -1,6 +1,7 @@
 // Host side of the Baum-Welch trainer and the forward scorer: sequence sorting/blocking,
 // device layout, the EM loop, and the C ABI declared in include/hmmb200.h.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <numeric>
 
@@ -156,14 +157,14 @@ struct SeqSet {
     int tmax_all = 0;                 // longest sequence
     // device
     void *d_obs = nullptr;            // special: uint4 blocks; generic: canonical symbols
+    void *d_meta = nullptr;           // one allocation behind d_off / d_foff / d_len / d_word / d_order
     int64_t *d_off = nullptr, *d_foff = nullptr;  // d_foff: frame prefix (generic) / uint4 row of the lane (N = 4 path)
     int32_t *d_len = nullptr, *d_word = nullptr, *d_order = nullptr;
     Blk *d_blks = nullptr;
     CtaWork *d_work = nullptr;
     void release() {
-        dev_free(d_obs); dev_free(d_off); dev_free(d_foff); dev_free(d_len); dev_free(d_word); dev_free(d_order);
-        dev_free(d_blks); dev_free(d_work);
-        d_obs = nullptr; d_off = d_foff = nullptr; d_len = d_word = d_order = nullptr; d_blks = nullptr; d_work = nullptr;
+        dev_free(d_obs); dev_free(d_meta); dev_free(d_blks); dev_free(d_work);
+        d_obs = d_meta = nullptr; d_off = d_foff = nullptr; d_len = d_word = d_order = nullptr; d_blks = nullptr; d_work = nullptr;
     }
 };
 
@@ -190,9 +191,15 @@ static int launch_prepare(SeqSet &s, const InT *d_in, int64_t nsym, int *d_bad, 
 // Sort sequences by (word, length desc), build blocks / CTA work items, move the codewords
 // to the device in the layout the kernels read.  word_of_seq == nullptr: a single "word"
 // (scoring: every utterance is scored against every model).
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets,
                         const int32_t *word_of_seq, int64_t R, int W, int N, int M, bool allow_special) {
     Ctx &c = ctx();
+    const bool timing = getenv("HMMB_TIMING") != nullptr;
+    const double t0 = now_ms();
     if (R < 0 || W <= 0 || !offsets || (R > 0 && !obs)) { set_error("bad sequence arguments"); return HMMB_ERR_ARG; }
     if (N < 1 || N > HMMB_MAX_STATES) { set_error("N=%d outside supported range 1..%d", N, HMMB_MAX_STATES); return HMMB_ERR_UNSUPPORTED; }
     if (M < 1 || M > 65536) { set_error("M=%d outside supported range 1..65536", M); return HMMB_ERR_UNSUPPORTED; }
@@ -201,51 +208,97 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     s.sym_bytes = M <= 256 ? 1 : 2;
     s.special4 = allow_special && N == 4 && M <= BW4_MAX_M && !getenv("HMMB_FORCE_GENERIC");
 
+    // Per-sequence metadata is staged in ONE pinned host buffer (cached in the context) and goes
+    // to the device with a single copy: [off int64 | foff int64 | len int32 | word int32 | order int32].
+    const size_t nR = (size_t)std::max<int64_t>(R, 1);
+    const size_t meta_bytes = nR * (2 * sizeof(int64_t) + 3 * sizeof(int32_t));
+    if (c.stage_bytes < meta_bytes) {
+        if (c.stage) cudaFreeHost(c.stage);
+        c.stage = nullptr;
+        c.stage_bytes = 0;
+        if (cudaHostAlloc(&c.stage, meta_bytes + (meta_bytes >> 2), cudaHostAllocDefault) != cudaSuccess) {
+            (void)cudaGetLastError();
+            set_error("pinned staging allocation of %zu bytes failed", meta_bytes);
+            return HMMB_ERR_OOM;
+        }
+        c.stage_bytes = meta_bytes + (meta_bytes >> 2);
+    }
+    int64_t *off_s = reinterpret_cast<int64_t *>(c.stage);
+    int64_t *foff_s = off_s + nR;
+    int32_t *len_s = reinterpret_cast<int32_t *>(foff_s + nR);
+    int32_t *word_s = len_s + nR;
+    int32_t *order_s = word_s + nR;
+
     std::vector<int32_t> len(R);
+    int bad_kind = 0;
+    int64_t bad_at = -1;
+#pragma omp parallel for schedule(static) if (R > 65536)
     for (int64_t r = 0; r < R; ++r) {
         const int64_t T = offsets[r + 1] - offsets[r];
-        if (T <= 0) {
-            // reference: IndexError at hmm_training.py:376 / hmm_testing.py:75 for an empty recording
-            set_error(T == 0 ? "sequence %lld is empty (T == 0)" : "offsets not monotone at sequence %lld", (long long)r);
-            return T == 0 ? HMMB_ERR_EMPTY : HMMB_ERR_ARG;
+        int kind = 0;
+        if (T == 0) kind = 1;
+        else if (T < 0) kind = 2;
+        else if (T > (1 << 30)) kind = 3;
+        else if (word_of_seq && (word_of_seq[r] < 0 || word_of_seq[r] >= W)) kind = 4;
+        if (kind) {
+#pragma omp critical
+            if (bad_at < 0 || r < bad_at) { bad_at = r; bad_kind = kind; }
         }
-        if (T > (1 << 30)) { set_error("sequence %lld too long", (long long)r); return HMMB_ERR_UNSUPPORTED; }
-        if (word_of_seq && (word_of_seq[r] < 0 || word_of_seq[r] >= W)) {
-            set_error("word_of_seq[%lld]=%d outside [0,%d)", (long long)r, word_of_seq[r], W);
-            return HMMB_ERR_ARG;
-        }
-        len[r] = (int32_t)T;
+        len[r] = (int32_t)(T > 0 && T <= (1 << 30) ? T : 0);
+    }
+    if (bad_kind == 1) {
+        // reference: IndexError at hmm_training.py:376 / hmm_testing.py:75 for an empty recording
+        set_error("sequence %lld is empty (T == 0)", (long long)bad_at);
+        return HMMB_ERR_EMPTY;
+    } else if (bad_kind == 2) {
+        set_error("offsets not monotone at sequence %lld", (long long)bad_at);
+        return HMMB_ERR_ARG;
+    } else if (bad_kind == 3) {
+        set_error("sequence %lld too long", (long long)bad_at);
+        return HMMB_ERR_UNSUPPORTED;
+    } else if (bad_kind == 4) {
+        set_error("word_of_seq[%lld]=%d outside [0,%d)", (long long)bad_at, word_of_seq[bad_at], W);
+        return HMMB_ERR_ARG;
     }
     s.frames = R > 0 ? offsets[R] - offsets[0] : 0;
-    s.order.resize(R);
-    std::iota(s.order.begin(), s.order.end(), 0);
-    bool sorted = true;
-    for (int64_t r = 1; r < R && sorted; ++r) {
+    int unsorted = 0;
+#pragma omp parallel for schedule(static) reduction(| : unsorted) if (R > 65536)
+    for (int64_t r = 1; r < R; ++r) {
         const int wa = word_of_seq ? word_of_seq[r - 1] : 0, wb = word_of_seq ? word_of_seq[r] : 0;
-        if (wa > wb || (wa == wb && len[r - 1] < len[r])) sorted = false;
+        if (wa > wb || (wa == wb && len[r - 1] < len[r])) unsorted |= 1;
     }
-    if (!sorted)
-        std::stable_sort(s.order.begin(), s.order.end(), [&](int32_t x, int32_t y) {
+    if (unsorted) {
+        std::iota(order_s, order_s + R, 0);
+        std::stable_sort(order_s, order_s + R, [&](int32_t x, int32_t y) {
             const int wx = word_of_seq ? word_of_seq[x] : 0, wy = word_of_seq ? word_of_seq[y] : 0;
             if (wx != wy) return wx < wy;
             return len[x] > len[y];
         });
+    }
     const int nwords = word_of_seq ? W : 1;
-    std::vector<int64_t> off_s(R), foff_s(R);
-    std::vector<int32_t> len_s(R), word_s(R);
     s.seq_begin.assign(nwords + 1, 0);
-    int64_t facc = 0;
+    int tmax_all = 0;
+#pragma omp parallel for schedule(static) reduction(max : tmax_all) if (R > 65536)
     for (int64_t i = 0; i < R; ++i) {
-        const int32_t r = s.order[i];
+        const int32_t r = unsorted ? order_s[i] : (int32_t)i;
+        order_s[i] = r;
         off_s[i] = offsets[r] - offsets[0];
         len_s[i] = len[r];
         word_s[i] = word_of_seq ? word_of_seq[r] : 0;
-        foff_s[i] = facc;
-        facc += len[r];
-        s.tmax_all = std::max(s.tmax_all, (int)len[r]);
-        s.seq_begin[word_s[i] + 1]++;
+        tmax_all = std::max(tmax_all, (int)len[r]);
     }
-    for (int w = 0; w < nwords; ++w) s.seq_begin[w + 1] += s.seq_begin[w];
+    s.tmax_all = tmax_all;
+    // sequences of a word are contiguous in the sorted order: word boundaries by binary search
+    for (int w = 0; w < nwords; ++w)
+        s.seq_begin[w + 1] = std::upper_bound(word_s, word_s + R, (int32_t)w) - word_s;
+    s.order.assign(order_s, order_s + R);
+    if (!s.special4) {
+        int64_t facc = 0;  // frame prefix (generic path only; the N = 4 path stores block rows here)
+        for (int64_t i = 0; i < R; ++i) {
+            foff_s[i] = facc;
+            facc += len_s[i];
+        }
+    }
 
     std::vector<Blk> blks;
     std::vector<CtaWork> work;
@@ -291,20 +344,15 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         s.ncta = (int)work.size();
     }
 
+    const double t1 = now_ms();
     // ---- device buffers
-    const size_t nR = (size_t)std::max<int64_t>(R, 1);
-    HMMB_TRY(dev_alloc_t(&s.d_off, nR));
-    HMMB_TRY(dev_alloc_t(&s.d_foff, nR));
-    HMMB_TRY(dev_alloc_t(&s.d_len, nR));
-    HMMB_TRY(dev_alloc_t(&s.d_word, nR));
-    HMMB_TRY(dev_alloc_t(&s.d_order, nR));
-    if (R > 0) {
-        HMMB_CUDA(cudaMemcpyAsync(s.d_off, off_s.data(), R * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
-        HMMB_CUDA(cudaMemcpyAsync(s.d_foff, foff_s.data(), R * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
-        HMMB_CUDA(cudaMemcpyAsync(s.d_len, len_s.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
-        HMMB_CUDA(cudaMemcpyAsync(s.d_word, word_s.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
-        HMMB_CUDA(cudaMemcpyAsync(s.d_order, s.order.data(), R * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
-    }
+    HMMB_TRY(dev_alloc(&s.d_meta, meta_bytes));
+    s.d_off = reinterpret_cast<int64_t *>(s.d_meta);
+    s.d_foff = s.d_off + nR;
+    s.d_len = reinterpret_cast<int32_t *>(s.d_foff + nR);
+    s.d_word = s.d_len + nR;
+    s.d_order = s.d_word + nR;
+    if (R > 0) HMMB_CUDA(cudaMemcpyAsync(s.d_meta, c.stage, meta_bytes, cudaMemcpyHostToDevice, c.stream));
     if (s.special4) {
         HMMB_TRY(dev_alloc_t(&s.d_blks, std::max<size_t>(blks.size(), 1)));
         HMMB_TRY(dev_alloc_t(&s.d_work, std::max<size_t>(work.size(), 1)));
@@ -350,6 +398,9 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     }
     dev_free(d_tmp);
     dev_free(d_bad);
+    if (timing)
+        fprintf(stderr, "[hmmb] seqset_build: host sort/blocking %.2f ms, upload + repack %.2f ms (R=%lld, frames=%lld)\n",
+                t1 - t0, now_ms() - t1, (long long)R, (long long)s.frames);
     if (rc != HMMB_OK) return rc;
     if (bad) {
         set_error("codeword out of range: some observation is >= M=%d (reference: IndexError)", M);
@@ -455,11 +506,6 @@ int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_d
         CUDAF(cudaMemcpyAsync(h->d_cta_begin, s.cta_begin.data(), (W + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
     } else {
         spill_bytes = (size_t)std::max<int64_t>(s.frames, 1) * N * sizeof(double);
-    }
-    {
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        (void)total_b;
     }
     rc = dev_alloc((void **)&h->d_spill, spill_bytes);
     if (rc != HMMB_OK) {

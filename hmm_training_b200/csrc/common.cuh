@@ -58,6 +58,9 @@ struct Ctx {
     // caching allocator
     std::multimap<size_t, void *> free_blocks;
     std::map<void *, size_t> live_blocks;
+    // pinned host staging buffer (per-sequence metadata of the last build)
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
 };
 
 Ctx &ctx();

@@ -173,6 +173,9 @@ int hmmb_shutdown(void) {
     dev_release_cache();
     for (auto &kv : c.live_blocks) cudaFree(kv.first);
     c.live_blocks.clear();
+    if (c.stage) cudaFreeHost(c.stage);
+    c.stage = nullptr;
+    c.stage_bytes = 0;
     for (auto ev : c.event_pool) cudaEventDestroy(ev);
     c.event_pool.clear();
     if (c.own_stream) cudaStreamDestroy(c.own_stream);

@@ -179,18 +179,33 @@ __device__ __forceinline__ double fwdG_run(int T, int Tw, int N, int j, int gbas
     bool stop = false, tainted = false;
     double ll = neg_inf();
     int par = 0;
+    // software pipeline of the two dependent loads: codeword two steps ahead, B one step ahead
+    unsigned sym_n = (T > 1) ? (unsigned)obs[1] : 0u;                                 // o_{t+1}
+    double b_n = (T > 0 && j < N) ? __ldg(Btw + (size_t)obs[0] * N + j) : 0.0;          // b_j(o_t)
     for (int t = 0; t < Tw; ++t) {
         const bool act = t < T && !stop;
         double at = 0.0, b = 0.0, n = 0.0;
+        if (t < T) {
+            b = b_n;
+            if (t + 1 < T) {
+                b_n = (j < N) ? __ldg(Btw + (size_t)sym_n * N + j) : 0.0;
+                if (t + 2 < T) sym_n = obs[t + 2];
+            }
+        }
         if (act) {
-            const unsigned sym = obs[t];
-            b = (j < N) ? __ldg(Btw + (size_t)sym * N + j) : 0.0;
             if (t == 0) {
                 n = pj;
             } else {
                 const double *prev = stage + par * 32 + gbase;
+                double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;  // four chains: shorter dependency
 #pragma unroll
-                for (int i = 0; i < NP; ++i) n = fma(prev[i], acol[i], n);
+                for (int i = 0; i < NP; i += 4) {
+                    n0 = fma(prev[i], acol[i], n0);
+                    n1 = fma(prev[i + 1], acol[i + 1], n1);
+                    n2 = fma(prev[i + 2], acol[i + 2], n2);
+                    n3 = fma(prev[i + 3], acol[i + 3], n3);
+                }
+                n = (n0 + n1) + (n2 + n3);
                 if (n == 0.0) {  // keep "n > 0 <=> structurally reachable"
                     bool reach = false;
                     for (int i = 0; i < NP; ++i) reach |= (prev[i] > 0.0 && acol[i] > 0.0);

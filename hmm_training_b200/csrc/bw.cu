@@ -6,6 +6,7 @@
 #include <numeric>
 
 #include "bw_kernels.cuh"
+#include "bwltr_kernels.cuh"
 
 namespace hmmb {
 
@@ -148,7 +149,9 @@ k_score_exact(const void *__restrict__ obs, const int64_t *__restrict__ base_sor
 struct SeqSet {
     int64_t R = 0, frames = 0;
     int N = 0, M = 0, NP = 0, sym_bytes = 1;
-    bool special4 = false;
+    bool special4 = false;            // blocked layout (32 same-word sequences per block), N = 4 kernels
+    int ltr_ns = 0;                   // blocked layout for the left-to-right kernels with NS = ltr_ns states
+    bool blocked() const { return special4 || ltr_ns != 0; }
     std::vector<int32_t> order;       // sorted -> original
     std::vector<int64_t> seq_begin;   // per word [W+1] (sorted order)
     std::vector<int32_t> cta_begin;   // per word [W+1]
@@ -173,7 +176,7 @@ static int pick_np(int N) { return N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : 32
 template <typename InT>
 static int launch_prepare(SeqSet &s, const InT *d_in, int64_t nsym, int *d_bad, const std::vector<Blk> &blks) {
     Ctx &c = ctx();
-    if (s.special4) {
+    if (s.blocked()) {
         HMMB_LAUNCH("prepare", k_repack_blocks4<InT>, s.nblk, 256, 0, d_in, s.d_off, s.d_len, s.d_blks, s.nblk,
                     (uint4 *)s.d_obs, s.M, d_bad);
     } else {
@@ -195,8 +198,19 @@ static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+enum SeqLayout { LAYOUT_GENERIC = 0, LAYOUT_AUTO = 1, LAYOUT_LTR = 2 };
+
+// can the left-to-right kernels (bwltr_kernels.cuh) hold this model shape?
+static bool ltr_shape_ok(int N, int M) {
+    if (N != 8 && N != 16) return false;
+    if (M > LTR_MAX_SYM) return false;
+    const size_t stage = (size_t)LTR_WARPS * 2 * 32 * (N * 8 + 16);
+    const size_t smem_b = (size_t)M * N * 8 + stage + (size_t)2 * N * 8 + (size_t)LTR_WARPS * 2 * N * 8 + 64;
+    return smem_b <= ctx().smem_optin && !getenv("HMMB_FORCE_GENERIC") && !getenv("HMMB_NO_LTR");
+}
+
 static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets,
-                        const int32_t *word_of_seq, int64_t R, int W, int N, int M, bool allow_special) {
+                        const int32_t *word_of_seq, int64_t R, int W, int N, int M, int layout) {
     Ctx &c = ctx();
     const bool timing = getenv("HMMB_TIMING") != nullptr;
     const double t0 = now_ms();
@@ -206,7 +220,8 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     if (idx_bytes != 1 && idx_bytes != 2 && idx_bytes != 4 && idx_bytes != 8) { set_error("idx_bytes must be 1, 2, 4 or 8"); return HMMB_ERR_ARG; }
     s.R = R; s.N = N; s.M = M; s.NP = pick_np(N);
     s.sym_bytes = M <= 256 ? 1 : 2;
-    s.special4 = allow_special && N == 4 && M <= BW4_MAX_M && !getenv("HMMB_FORCE_GENERIC");
+    s.special4 = layout == LAYOUT_AUTO && N == 4 && M <= BW4_MAX_M && !getenv("HMMB_FORCE_GENERIC");
+    s.ltr_ns = (layout == LAYOUT_LTR) ? N : 0;
 
     // Per-sequence metadata is staged in ONE pinned host buffer (cached in the context) and goes
     // to the device with a single copy: [off int64 | foff int64 | len int32 | word int32 | order int32].
@@ -292,7 +307,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     for (int w = 0; w < nwords; ++w)
         s.seq_begin[w + 1] = std::upper_bound(word_s, word_s + R, (int32_t)w) - word_s;
     s.order.assign(order_s, order_s + R);
-    if (!s.special4) {
+    if (!s.blocked()) {
         int64_t facc = 0;  // frame prefix (generic path only; the N = 4 path stores block rows here)
         for (int64_t i = 0; i < R; ++i) {
             foff_s[i] = facc;
@@ -303,8 +318,9 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     std::vector<Blk> blks;
     std::vector<CtaWork> work;
     int64_t obs_rows = 0;
-    if (s.special4) {
+    if (s.blocked()) {
         const int SPC = SPC4;  // packed u16 entries (codeword | conflict rank) per uint4
+        const int cta_warps = s.special4 ? BW_WARPS : LTR_WARPS;
         std::vector<int> word_blk_begin(nwords + 1, 0);
         for (int w = 0; w < nwords; ++w) {
             word_blk_begin[w] = (int)blks.size();
@@ -324,10 +340,11 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         }
         word_blk_begin[nwords] = (int)blks.size();
         s.nblk = (int)blks.size();
-        // CTA work items: ~8 CTAs per SM in total, at least one warp-round (4 blocks) each
-        const int target = c.sm_count * 8;
+        // CTA work items: ~8 CTAs per SM in total (N = 4; the left-to-right kernels run one
+        // 8-warp CTA per SM: ~4 per SM), at least one warp-round each
+        const int target = s.special4 ? c.sm_count * 8 : c.sm_count * 4;
         int bpc = std::max(1, (s.nblk + target - 1) / target);
-        if (bpc > 1) bpc = (bpc + BW_WARPS - 1) / BW_WARPS * BW_WARPS;
+        if (bpc > 1 || !s.special4) bpc = (bpc + cta_warps - 1) / cta_warps * cta_warps;
         s.cta_begin.assign(nwords + 1, 0);
         for (int w = 0; w < nwords; ++w) {
             s.cta_begin[w] = (int)work.size();
@@ -353,7 +370,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     s.d_word = s.d_len + nR;
     s.d_order = s.d_word + nR;
     if (R > 0) HMMB_CUDA(cudaMemcpyAsync(s.d_meta, c.stage, meta_bytes, cudaMemcpyHostToDevice, c.stream));
-    if (s.special4) {
+    if (s.blocked()) {
         HMMB_TRY(dev_alloc_t(&s.d_blks, std::max<size_t>(blks.size(), 1)));
         HMMB_TRY(dev_alloc_t(&s.d_work, std::max<size_t>(work.size(), 1)));
         if (!blks.empty()) {
@@ -415,7 +432,13 @@ using namespace hmmb;
 
 // ---------------------------------------------------------------- the trainer handle
 struct hmmb_bw {
-    SeqSet s;
+    SeqSet s;                     // N = 4: blocked layout; otherwise the generic (lanes = states) layout
+    SeqSet sl;                    // N = 8 / 16: additional blocked layout for the left-to-right kernels
+    bool has_ltr = false;         // sl was built
+    bool use_ltr = false;         // every word's A is upper-bidiagonal (checked in set_params): run the sl kernels
+    uint8_t *d_allfull = nullptr; // per sequence: every spilled alpha-hat > 0 (written by k_bw_fwdL)
+    void *d_raw = nullptr;        // raw codewords uploaded once when both layouts are built
+    SeqSet &cur() { return use_ltr ? sl : s; }
     int W = 0, N = 0, M = 0;
     double *d_pi = nullptr, *d_A = nullptr, *d_Bt = nullptr;
     double *d_spill = nullptr, *d_llseq = nullptr, *d_accum = nullptr, *d_partials = nullptr;
@@ -442,6 +465,9 @@ struct hmmb_bw {
 
 static void bw_release(hmmb_bw *h) {
     h->s.release();
+    h->sl.release();
+    dev_free(h->d_allfull);
+    dev_free(h->d_raw);
     dev_free(h->d_pi); dev_free(h->d_A); dev_free(h->d_Bt); dev_free(h->d_spill); dev_free(h->d_llseq);
     dev_free(h->d_accum); dev_free(h->d_partials); dev_free(h->d_prev); dev_free(h->d_hist); dev_free(h->d_active);
     dev_free(h->d_iters); dev_free(h->d_any); dev_free(h->d_cta_begin); dev_free(h->d_seq_begin);
@@ -465,12 +491,33 @@ int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_d
     Ctx &c = ctx();
     hmmb_bw *h = new hmmb_bw();
     h->W = W; h->N = N; h->M = M;
-    int rc = seqset_build(h->s, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, true);
     auto fail = [&](int code) { bw_release(h); delete h; return code; };
+    int rc;
+    h->has_ltr = ltr_shape_ok(N, M);
+    if (h->has_ltr && !obs_on_device && R > 0 && offsets && obs && offsets[R] > offsets[0]) {
+        // both layouts are built from the codewords: upload them once
+        const size_t in_bytes = (size_t)(offsets[R] - offsets[0]) * idx_bytes;
+        rc = dev_alloc(&h->d_raw, in_bytes);
+        if (rc != HMMB_OK) return fail(rc);
+        cudaError_t e = cudaMemcpyAsync(h->d_raw, (const char *)obs + (size_t)offsets[0] * idx_bytes, in_bytes,
+                                        cudaMemcpyHostToDevice, c.stream);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "codeword upload", __FILE__, __LINE__));
+        // seqset_build indexes a device stream from offsets[0]
+        obs = (const char *)h->d_raw - (size_t)offsets[0] * idx_bytes;
+        obs_on_device = 1;
+    }
+    rc = seqset_build(h->s, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_AUTO);
     if (rc != HMMB_OK) return fail(rc);
+    if (h->has_ltr) {
+        rc = seqset_build(h->sl, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_LTR);
+        if (rc != HMMB_OK) return fail(rc);
+        dev_free(h->d_raw);
+        h->d_raw = nullptr;
+    }
     SeqSet &s = h->s;
     h->nacc = (int64_t)N + (int64_t)N * N + (int64_t)M * N;
-    h->astride = (h->nacc + 1 + 1) & ~int64_t(1);
+    // stride multiple of 16 doubles: every word's count rows start on a 128-byte line (TMA bulk reductions)
+    h->astride = (h->nacc + 1 + 15) & ~int64_t(15);
     h->pstride = h->nacc;
     h->hist_cap = 0;
 #define TRYF(expr) do { int _r = (expr); if (_r != HMMB_OK) return fail(_r); } while (0)
@@ -506,6 +553,10 @@ int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_d
         CUDAF(cudaMemcpyAsync(h->d_cta_begin, s.cta_begin.data(), (W + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
     } else {
         spill_bytes = (size_t)std::max<int64_t>(s.frames, 1) * N * sizeof(double);
+        if (h->has_ltr) {
+            spill_bytes = std::max(spill_bytes, (size_t)std::max<int64_t>(h->sl.spill_steps, 1) * 32 * N * sizeof(double));
+            TRYF(dev_alloc_t(&h->d_allfull, (size_t)std::max<int64_t>(R, 1)));
+        }
     }
     rc = dev_alloc((void **)&h->d_spill, spill_bytes);
     if (rc != HMMB_OK) {
@@ -530,6 +581,13 @@ int hmmb_bw_destroy(hmmb_bw_t *h) {
 
 int64_t hmmb_bw_total_frames(hmmb_bw_t *h) { return h ? h->s.frames : 0; }
 
+const char *hmmb_bw_kernel_family(hmmb_bw_t *h) {
+    if (!h) return "";
+    if (h->use_ltr) return "left_to_right";
+    if (h->s.special4) return h->bidiag ? "n4_left_to_right" : "n4_dense";
+    return "generic";
+}
+
 int hmmb_bw_set_params(hmmb_bw_t *h, const double *pi0, const double *A0, const double *B0) {
     HMMB_TRY(require_init());
     if (!h || !pi0 || !A0 || !B0) { set_error("hmmb_bw_set_params: null argument"); return HMMB_ERR_ARG; }
@@ -553,6 +611,12 @@ int hmmb_bw_set_params(hmmb_bw_t *h, const double *pi0, const double *A0, const 
             if (j != i && j != i + 1 && A0[e] > 0.0) h->bidiag = false;
         }
         if (getenv("HMMB_FORCE_DENSE_A")) h->bidiag = false;
+        h->use_ltr = h->has_ltr;
+        for (size_t e = 0; e < nA && h->use_ltr; ++e) {
+            const int ij = (int)(e % (size_t)(N * N)), i = ij / N, j = ij % N;
+            if (j != i && j != i + 1 && A0[e] > 0.0) h->use_ltr = false;
+        }
+        if (getenv("HMMB_FORCE_DENSE_A")) h->use_ltr = false;
     }
     HMMB_LAUNCH("bw_load", k_load_clamped, (unsigned)std::min<size_t>((nA + 255) / 256, 1024), 256, 0, tmp + nB, (int64_t)nA, h->d_A);
     HMMB_LAUNCH("bw_load", k_load_clamped, (unsigned)std::min<size_t>((nP + 255) / 256, 1024), 256, 0, tmp + nB + nA, (int64_t)nP, h->d_pi);
@@ -599,7 +663,7 @@ static int bw_ensure_hist(hmmb_bw *h, int cap) {
 
 template <typename SymT, bool BLOCKED>
 static int launch_exact(hmmb_bw *h) {
-    SeqSet &s = h->s;
+    SeqSet &s = h->cur();
     HMMB_LAUNCH("bw_exact", (k_bw_exact<SymT, BLOCKED>), h->exact_grid, BW_THREADS, 0, s.d_obs, BLOCKED ? s.d_foff : s.d_off,
                 s.d_len, s.d_word, s.R, h->N, h->M, h->d_pi, h->d_A, h->d_Bt, h->d_llseq, h->d_active, h->d_flag,
                 h->d_exact_scratch, h->exact_stride, h->d_accum, h->astride, h->d_nexact);
@@ -642,7 +706,27 @@ static int launch_special_estep(hmmb_bw *h) {
     return HMMB_OK;
 }
 
+template <int NS>
+static int launch_ltr_estep(hmmb_bw *h) {
+    SeqSet &s = h->sl;
+    if (s.ncta == 0) return HMMB_OK;
+    const int M = h->M;
+    const size_t smem_f = (size_t)M * NS * 8 + (size_t)M * 8 + (size_t)M * 2;
+    const size_t smem_b = (size_t)M * NS * 8 + (size_t)LTR_WARPS * 2 * 32 * Ltr<NS>::ROWB + (size_t)2 * NS * 8 +
+                          (size_t)LTR_WARPS * 2 * NS * 8;
+    HMMB_CUDA(cudaFuncSetAttribute(k_bw_fwdL<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+    HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwdL<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    HMMB_LAUNCH("bw_forward", k_bw_fwdL<NS>, s.ncta, LTR_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs, s.d_len,
+                h->d_pi, h->d_A, h->d_Bt, M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag, h->d_allfull);
+    HMMB_TRY((launch_exact<uint16_t, true>(h)));
+    HMMB_LAUNCH("bw_backward", k_bw_bwdL<NS>, s.ncta, LTR_THREADS, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs, s.d_len,
+                h->d_A, h->d_Bt, M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero, h->d_allfull,
+                h->d_accum, h->astride, h->d_flag, h->d_newflags);
+    return HMMB_OK;
+}
+
 static int bw_estep(hmmb_bw *h) {
+    if (h->use_ltr) return h->N == 16 ? launch_ltr_estep<16>(h) : launch_ltr_estep<8>(h);
     SeqSet &s = h->s;
     if (s.special4) return h->bidiag ? launch_special_estep<true>(h) : launch_special_estep<false>(h);
 #define GEN(NPV)                                                                               \
@@ -760,7 +844,7 @@ int hmmb_bw_get_seq_ll(hmmb_bw_t *h, double *ll_seq) {
         HMMB_CUDA(cudaMemcpyAsync(tmp.data(), h->d_llseq, h->s.R * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         HMMB_CUDA(cudaStreamSynchronize(c.stream));
     }
-    for (int64_t i = 0; i < h->s.R; ++i) ll_seq[h->s.order[i]] = tmp[i];
+    for (int64_t i = 0; i < h->s.R; ++i) ll_seq[h->cur().order[i]] = tmp[i];
     return HMMB_OK;
 }
 

@@ -164,6 +164,10 @@ class BaumWelch:
         check(self._lib.hmmb_bw_get_history(self._h, ptr(hist), hist.shape[1], ptr(iters)))
         return hist, iters
 
+    def kernel_family(self) -> str:
+        """E-step kernel family selected by the current parameters (see hmmb_bw_kernel_family)."""
+        return self._lib.hmmb_bw_kernel_family(self._h).decode()
+
     def diagnostics(self):
         """(sequence passes recomputed by the exact log-space kernel, backward hand-overs)."""
         a, b = ctypes.c_int64(0), ctypes.c_int64(0)

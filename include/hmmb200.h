@@ -120,6 +120,10 @@ int hmmb_bw_get_history(hmmb_bw_t *h, double *ll_hist, int hist_cap, int32_t *it
 /* per-sequence log P(O|lambda) of the last E-step, in input order [R] (:376-377)         */
 int hmmb_bw_get_seq_ll(hmmb_bw_t *h, double *ll_seq);
 int64_t hmmb_bw_total_frames(hmmb_bw_t *h);
+/* which E-step kernels the parameters set by hmmb_bw_set_params select: "n4_left_to_right" /
+ * "n4_dense" (one sequence per thread, N = 4), "left_to_right" (one sequence per thread,
+ * N = 8 / 16 with upper-bidiagonal A) or "generic" (lanes per state, N <= 32)            */
+const char *hmmb_bw_kernel_family(hmmb_bw_t *h);
 /* precision-guard counters since hmmb_bw_set_params: sequence passes recomputed by the exact
  * log-space kernel, and sequences handed over by the backward pass (each costs one E-step
  * redo when hmmb_bw_iterate runs with sync_each != 0; with sync_each == 0 they are only

@@ -111,6 +111,78 @@ def test_baum_welch_matches_oracle_seeded(N, M, T):
         assert np.array_equal(floored_set(B[w], M), floored_set(Bo, M))
 
 
+def _ltr_init(rng, W, N, M, kind):
+    """Left-to-right (upper-bidiagonal A) initial models: 'default' = the generalised reference
+    defaults, 'random' = random self/next probabilities and random dense B, 'zeros' = B with
+    exact zeros and pi concentrated on state 0 (forces the careful / masked steps)."""
+    pi0 = np.zeros((W, N)); A0 = np.zeros((W, N, N)); B0 = np.zeros((W, N, M))
+    for w in range(W):
+        if kind == "default":
+            pi0[w], A0[w], B0[w] = engine.default_init(N, M)
+            continue
+        stay = rng.uniform(0.3, 0.9, size=N)
+        for i in range(N - 1):
+            A0[w, i, i] = stay[i]; A0[w, i, i + 1] = 1 - stay[i]
+        A0[w, N - 1, N - 1] = 1.0
+        B0[w] = rng.dirichlet(np.ones(M), size=N)
+        if kind == "zeros":
+            pi0[w, 0] = 1.0
+            B0[w][rng.random((N, M)) < 0.15] = 0.0
+            B0[w, :, 0] = 1e-3  # keep at least one symbol every state can emit
+        else:
+            pi0[w] = rng.dirichlet(np.ones(N))
+    return pi0, A0, B0
+
+
+@pytest.mark.parametrize("N,M,kind", [(16, 1024, "default"), (16, 1024, "random"), (16, 300, "zeros"),
+                                      (8, 64, "default"), (8, 2048, "random"), (8, 40, "zeros")])
+def test_baum_welch_left_to_right_kernels(N, M, kind, monkeypatch):
+    """N = 8 / 16 with upper-bidiagonal A goes through the one-sequence-per-thread left-to-right
+    kernels (bwltr_kernels.cuh: TMA bulk-reduce count accumulation); checked against the numpy
+    oracle and against the generic lanes-per-state kernels on ragged input (T from 1 up)."""
+    rng = np.random.default_rng(N * 7 + M)
+    W = 3
+    corpus = []
+    for w in range(W):
+        seqs = synthetic.clustered_sequences(rng, 41 + 3 * w, N=N, M=M, tmin=3, tmax=70, shift=5 * w,
+                                             spread=max(2, M // (2 * N)))
+        seqs[0] = seqs[0][:1]   # T == 1
+        seqs[1] = seqs[1][:2]
+        if kind == "zeros":
+            seqs[2] = np.zeros(9, np.int64)  # only symbol 0: possible under every state
+        corpus.append(seqs)
+    obs, offsets, wos = synthetic.pack_corpus(corpus, M)
+    pi0, A0, B0 = _ltr_init(rng, W, N, M, kind)
+    iters_max = 4
+    monkeypatch.delenv("HMMB_NO_LTR", raising=False)
+    with engine.BaumWelch(obs, offsets, wos, W, N, M) as bw:
+        bw.set_params(pi0, A0, B0)
+        assert bw.kernel_family() == "left_to_right"
+        bw.iterate(iters_max, 1e-6, iters_max)
+        pi, A, B = bw.params()
+        hist, iters = bw.history(iters_max)
+        ll_seq = bw.seq_ll()
+    for w in range(W):
+        Ao, Bo, pio, h, it = O.hmm_training(corpus[w], N=N, M=M, max_iterations=iters_max,
+                                            init=(pi0[w], A0[w], B0[w]), return_history=True)
+        assert it == iters[w]
+        assert_close(hist[w, :it], h, f"N{N} M{M} w{w} ll")
+        assert_close(A[w], Ao, f"N{N} M{M} w{w} A")
+        assert_close(B[w], Bo, f"N{N} M{M} w{w} B")
+        assert_close(pi[w], pio, f"N{N} M{M} w{w} pi")
+        assert_same_support(A[w], Ao); assert_same_support(pi[w], pio)
+        assert np.array_equal(floored_set(B[w], M), floored_set(Bo, M))
+    monkeypatch.setenv("HMMB_NO_LTR", "1")
+    with engine.BaumWelch(obs, offsets, wos, W, N, M) as bw:
+        bw.set_params(pi0, A0, B0)
+        assert bw.kernel_family() == "generic"
+        bw.iterate(iters_max, 1e-6, iters_max)
+        pig, Ag, Bg = bw.params()
+        llg = bw.seq_ll()
+    assert_close(A, Ag, "ltr vs generic A"); assert_close(B, Bg, "ltr vs generic B"); assert_close(pi, pig, "ltr vs generic pi")
+    assert_close(ll_seq, llg, "ltr vs generic per-sequence LL")
+
+
 def test_baum_welch_is_deterministic():
     g = load_golden("bw_clustered_s2_it1")
     N, M, W = 4, 256, 3

@@ -42,6 +42,17 @@ WORKLOADS = {
 }
 
 
+def measured_traffic(workload: str, kernel: str, frames: int):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum per frame of the captured launch, scaled to this
+    launch's frame count); None if no capture is recorded for the workload."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload][kernel]
+        return rec["dram_bytes_per_frame"] * frames, rec.get("source")
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -54,7 +65,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons sampled DURING the timed region (B200_PROFILING.md):
+    NVML every ~2 ms from a thread (the timed region of the default workload is tens of
+    milliseconds, shorter than one nvidia-smi call); nvidia-smi is the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -62,25 +75,84 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.samples = []          # (sm_mhz, power_w, reasons bitmask)
+        self.sm_max = None
+        self.source = None
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+            self.source = "nvidia-smi"
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+        except Exception:
+            pw = None
+        try:
+            rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:
+            try:
+                rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+            except Exception:
+                rs = 0
+        self.samples.append((sm, pw, rs))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        if len(parts) >= 7:
+            bits = 0
+            for i, b in enumerate((0x8, 0x40, 0x20, 0x4)):  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+                if parts[3 + i].lower().startswith("active"):
+                    bits |= b
+            self.sm_max = float(parts[1])
+            self.samples.append((float(parts[0]), float(parts[2]), bits))
 
     def _run(self):
+        try:  # first NVML query of a thread is slow: take (and drop) it before the timed region starts
+            if self._nvml:
+                self._sample_nvml()
+                self.samples.clear()
+        except Exception:
+            pass
+        self._ready.set()
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                if self._nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.002 if self._nvml else 0.2)
 
     def __enter__(self):
+        self.samples = []
+        self._stop.clear()
+        self._ready = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
+        self._ready.wait(5.0)
         return self
 
     def __exit__(self, *exc):
@@ -89,14 +161,16 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "source": self.source}
+        sm = sorted(s[0] for s in self.samples)
+        pw = [s[1] for s in self.samples if s[1] is not None]
+        bits = 0
+        for s in self.samples:
+            bits |= s[2]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = [n for b, n in names.items() if bits & b]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "power_w_max": max(pw) if pw else None,
+                "reasons": reasons, "samples": len(self.samples), "source": self.source}
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -140,7 +214,7 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    spw = int(os.environ.get("HMMB_CPU_SEQ_PER_WORD", "60" if cfg["N"] <= 4 else "4"))
+    spw = int(os.environ.get("HMMB_CPU_SEQ_PER_WORD", "2000" if cfg["N"] <= 4 else "150"))
     for _ in range(max(args.warmup, 0) and 1):
         cpu_baum_welch(cfg, max(spw // 4, 1), 1, cores)
     vals = []
@@ -234,6 +308,7 @@ def main():
             phases[name] = {"ms_per_launch": pms / n, "launches": n}
     _lib.check(lib.hmmb_set_profiling(0))
     exact_passes, bwd_handover = bw.diagnostics()
+    bw_family = bw.kernel_family()
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -251,8 +326,13 @@ def main():
     if dom:
         ach = alg[dom] / (phases[dom]["ms_per_launch"] * 1e-3) / 1e9
         estep_ms = sum(phases[k]["ms_per_launch"] for k in ("bw_forward", "bw_backward") if k in phases)
-        roofline = {"bound": "hbm", "kernel": "k_bw_bwd" if dom == "bw_backward" else "k_bw_fwd", "achieved": ach,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+        family = bw_family
+        kname = {"n4_left_to_right": "k_bw_%s4<true>", "n4_dense": "k_bw_%s4<false>", "left_to_right": "k_bw_%sL",
+                 "generic": "k_bw_%sG"}.get(family, "k_bw_%s") % ("bwd" if dom == "bw_backward" else "fwd")
+        traffic, traffic_src = measured_traffic(args.workload, dom, frames_rank)
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": ach,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                    "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg[dom],
                     "estep": {"algorithmic_bytes_per_frame": 2 * sym_b + 16 * N,
                               "achieved": frames_rank * (2 * sym_b + 16 * N) / (estep_ms * 1e-3) / 1e9,
@@ -295,7 +375,8 @@ def main():
     cpu_baseline = None
     if world == 1 and not args.no_extras:
         cores = os.cpu_count() or 1
-        spw = int(os.environ.get("HMMB_CPU_SEQ_PER_WORD", "60" if N <= 4 else "4"))
+        # bounded sample of the same workload: ~10 s of CPU work on all host cores
+        spw = int(os.environ.get("HMMB_CPU_SEQ_PER_WORD", "6000" if N <= 4 else "500"))
         v, dt, sample = cpu_baum_welch(cfg, spw, 1, cores)
         cpu_baseline = {"value": v, "unit": "frames/s/iter", "cores": cores, "kind": "port", "sample": sample,
                         "seconds": dt}

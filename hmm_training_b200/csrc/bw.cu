@@ -204,7 +204,7 @@ enum SeqLayout { LAYOUT_GENERIC = 0, LAYOUT_AUTO = 1, LAYOUT_LTR = 2 };
 static bool ltr_shape_ok(int N, int M) {
     if (N != 8 && N != 16) return false;
     if (M > LTR_MAX_SYM) return false;
-    const size_t stage = (size_t)LTR_WARPS * 2 * 32 * (N * 8 + 16);
+    const size_t stage = (size_t)LTR_WARPS * LTR_STAGE_BUFS * 32 * (N * 8 + 16);
     const size_t smem_b = (size_t)M * N * 8 + stage + (size_t)2 * N * 8 + (size_t)LTR_WARPS * 2 * N * 8 + 64;
     return smem_b <= ctx().smem_optin && !getenv("HMMB_FORCE_GENERIC") && !getenv("HMMB_NO_LTR");
 }
@@ -712,7 +712,7 @@ static int launch_ltr_estep(hmmb_bw *h) {
     if (s.ncta == 0) return HMMB_OK;
     const int M = h->M;
     const size_t smem_f = (size_t)M * NS * 8 + (size_t)M * 8 + (size_t)M * 2;
-    const size_t smem_b = (size_t)M * NS * 8 + (size_t)LTR_WARPS * 2 * 32 * Ltr<NS>::ROWB + (size_t)2 * NS * 8 +
+    const size_t smem_b = (size_t)M * NS * 8 + (size_t)LTR_WARPS * LTR_STAGE_BUFS * 32 * Ltr<NS>::ROWB + (size_t)2 * NS * 8 +
                           (size_t)LTR_WARPS * 2 * NS * 8;
     HMMB_CUDA(cudaFuncSetAttribute(k_bw_fwdL<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
     HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwdL<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));

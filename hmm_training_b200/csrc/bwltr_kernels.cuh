@@ -14,13 +14,14 @@
 //               16-byte chunks XOR-swizzled so that 32 random rows spread over all banks);
 //               alpha-hat spilled [block][t][chunk][lane] as coalesced 16-byte streaming stores.
 //   k_bw_bwdL   backward pass fused with gamma / xi / emission-count accumulation.  Each lane's
-//               gamma_t row (NS fp64 = 128 B at NS = 16) is staged in shared memory and ADDED
-//               to the word's count row in the global accumulator by ONE TMA bulk reduction
-//               (cp.reduce.async.bulk.global.shared::cta .add.f64, SASS UBLKRED): the
-//               scatter-add runs in the L2 atomic units, off the SM's LSU pipe, and frees
-//               the shared memory a [M][NS] count table would need for B^T.  Measured on B200
-//               (scripts/microbench2.cu): 7.6 clk per row per SM vs 8.9 (shared table + row
-//               locks), 11.8 (shared CAS atomics), 24.4 (per-element global RED).
+//               gamma_t row (NS fp64 = 128 B at NS = 16) is staged in shared memory (padded
+//               rows, conflict-free) and added to the word's count row in the global
+//               accumulator by the L2 atomic units, which frees the shared memory a [M][NS]
+//               count table would need for B^T.  Measured on B200 (scripts/microbench2.cu,
+//               clk per row per SM): coalesced RED rows with lanes = states 7.8, one TMA bulk
+//               reduction per lane (cp.reduce.async.bulk .add.f64) 7.6, shared table + row
+//               locks 8.9, shared CAS atomics 11.8, per-element global RED 24.4.  The RED
+//               rows are the default (see HMMB_LTR_TMA below).
 //
 // Numerics are those of the N = 4 kernels (bw4_kernels.cuh): exact power-of-two rescale,
 // smallest-denormal FMA addends that keep "value > 0 <=> the reference's log value is
@@ -32,10 +33,23 @@
 
 namespace hmmb {
 
+// Emission-count scatter-add of the backward pass: 0 (default) = coalesced fp64 REDs of the staged
+// gamma rows re-read with lanes = states; 1 = one TMA bulk reduction (cp.reduce.async.bulk
+// .add.f64, SASS UBLKRED) per lane.  Both bottom out at ~7.6-7.8 clk per row per SM in the L2
+// atomic units (scripts/microbench2.cu), but the TMA instruction takes its operands from
+// uniform registers, so a warp issues its 32 reductions in a serial ELECT / R2UR / UBLKRED loop
+// (ncu, profiles/r1i_*: 42 % of the kernel's instructions, each waiting on the previous one):
+// config 4 backward 5.55 ms with TMA vs the RED rows below.
+#ifndef HMMB_LTR_TMA
+#define HMMB_LTR_TMA 0
+#endif
+constexpr int LTR_STAGE_BUFS = HMMB_LTR_TMA ? 2 : 1;
 constexpr int LTR_WARPS = 8;
 constexpr int LTR_THREADS = LTR_WARPS * 32;
 constexpr int LTR_MAX_SYM = 1 << SYM_BITS;   // codewords share the packed u16 layout of the N = 4 path
-constexpr int BWDL_L2_PREFETCH = 6;          // steps ahead of use for the alpha-hat L2 prefetch
+// steps ahead of use for the alpha-hat L2 prefetch (3 / 6 / 12 and an extra L1 prefetch measured
+// within 6 % of each other on config 4: the backward pass is not waiting on the spill)
+constexpr int BWDL_L2_PREFETCH = 6;
 
 template <int NS>
 struct Ltr {
@@ -422,8 +436,8 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     using S16 = Sym<uint16_t>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *sB = reinterpret_cast<double2 *>(smem_raw);                                  // [M * CPR] swizzled B^T
-    unsigned char *sStage = reinterpret_cast<unsigned char *>(sB + (size_t)M * L::CPR);    // [warps][2][32][ROWB]
-    double *sA = reinterpret_cast<double *>(sStage + (size_t)LTR_WARPS * 2 * 32 * L::ROWB);  // a_ii [NS], a_i,i+1 [NS]
+    unsigned char *sStage = reinterpret_cast<unsigned char *>(sB + (size_t)M * L::CPR);    // [warps][bufs][32][ROWB]
+    double *sA = reinterpret_cast<double *>(sStage + (size_t)LTR_WARPS * LTR_STAGE_BUFS * 32 * L::ROWB);  // a_ii [NS], a_i,i+1 [NS]
     double *sRed = sA + 2 * NS;                                                            // [warps][2 * NS]
     __shared__ unsigned sSeen[2];
 
@@ -447,13 +461,22 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     const double tiny = tiny_pos();
     double *accw = accum + (size_t)cw.word * astride;
     double *acc_cnt = accw + NS + NS * NS;
-    unsigned char *stage_w = sStage + (size_t)warp * 2 * 32 * L::ROWB + (size_t)lane * L::ROWB;
+    unsigned char *stage_w = sStage + (size_t)warp * LTR_STAGE_BUFS * 32 * L::ROWB + (size_t)lane * L::ROWB;
+#if !HMMB_LTR_TMA
+    // count flush with lanes = states: lane (fo, jj) reads state jj of staged rows fo, fo + FPI, ...
+    const int flush_jj = lane % NS, flush_fo = lane / NS;
+    const unsigned char *flush_src = sStage + (size_t)warp * LTR_STAGE_BUFS * 32 * L::ROWB + (size_t)flush_fo * L::ROWB + flush_jj * 8;
+    const int flush_sym_off = NS * 8 - flush_jj * 8;  // from the lane's element to the row's padding word
+    double *flush_dst = acc_cnt + flush_jj;
+#endif
 
     double v[NS], Xs[NS], Xn[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) Xs[i] = Xn[i] = 0.0;
     unsigned seenS = 0u, seenN = 0u;
+#if HMMB_LTR_TMA
     int step_parity = 0;
+#endif
 
     for (int b = cw.blk_begin + warp; b < cw.blk_end; b += LTR_WARPS) {
         const Blk bk = blks[b];
@@ -482,10 +505,14 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                 const unsigned sym = S16::pop_back(w) & SYM_MASK;
                 if (t >= bk.tmax) continue;  // warp-uniform
                 const bool act = t < T;
+#if HMMB_LTR_TMA
                 // the staging buffer used two steps ago must have been read by the TMA unit
                 asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 unsigned char *stage = stage_w + (size_t)step_parity * 32 * L::ROWB;
                 step_parity ^= 1;
+#else
+                unsigned char *stage = stage_w;
+#endif
                 if (t >= BWDL_L2_PREFETCH && lane * 128 < NS * 8 * 32)  // pull the spill towards L2 well ahead
                     prefetch_l2(sp_line + (size_t)(t - BWDL_L2_PREFETCH) * (NS * 8 * 32));
                 if (act) {
@@ -580,13 +607,54 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
 #pragma unroll
                         for (int p = 0; p < L::CPR; ++p) sg[p] = make_double2(g[2 * p], g[2 * p + 1]);
                     }
+#if HMMB_LTR_TMA
                     // emission-count numerators (:460-500) and, at t = 0, the pi sums (:415-426): the lane's
                     // gamma row is added to the word's accumulator rows by the TMA unit (L2 fp64 atomics)
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     bulk_reduce_add_f64(acc_cnt + (size_t)sym * NS, smem_addr(stage), NS * 8);
                     if (t == 0) bulk_reduce_add_f64(accw, smem_addr(stage), NS * 8);
+#endif
                 }
+#if HMMB_LTR_TMA
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#else
+                // emission-count numerators (:460-500) and, at t = 0, the pi sums (:415-426): the staged
+                // gamma rows are re-read with lanes = states (NS lanes per row, 32 / NS rows per
+                // instruction) and added to the word's accumulator rows with coalesced fp64 REDs
+                if (act) *reinterpret_cast<unsigned *>(stage + NS * 8) = sym;  // the row's codeword, in the row padding
+                __syncwarp();
+                {
+                    // lane (fo, jj) of iteration k handles state jj of staged row k * FPI + fo; everything but
+                    // the codeword is a compile-time offset from per-lane bases set up before the time loop
+                    const unsigned actmask = __ballot_sync(0xffffffffu, act);
+                    constexpr int FPI = 32 / NS;  // frames (rows) per warp instruction
+                    if (actmask == 0xffffffffu) {
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) {
+                            const unsigned char *row = flush_src + (size_t)k * FPI * L::ROWB;
+                            const unsigned sf = *reinterpret_cast<const unsigned *>(row + flush_sym_off);
+                            atomicAdd(flush_dst + (size_t)sf * NS, *reinterpret_cast<const double *>(row));
+                        }
+                    } else {
+#pragma unroll 2
+                        for (int k = 0; k < NS; ++k) {
+                            if ((actmask >> (k * FPI + flush_fo)) & 1u) {
+                                const unsigned char *row = flush_src + (size_t)k * FPI * L::ROWB;
+                                const unsigned sf = *reinterpret_cast<const unsigned *>(row + flush_sym_off);
+                                atomicAdd(flush_dst + (size_t)sf * NS, *reinterpret_cast<const double *>(row));
+                            }
+                        }
+                    }
+                    if (t == 0) {  // warp-uniform
+#pragma unroll 2
+                        for (int k = 0; k < NS; ++k) {
+                            if ((actmask >> (k * FPI + flush_fo)) & 1u)
+                                atomicAdd(accw + flush_jj, *reinterpret_cast<const double *>(flush_src + (size_t)k * FPI * L::ROWB));
+                        }
+                    }
+                }
+                __syncwarp();
+#endif
             }
         }
         if (imprecise) {  // sticky hand-over; the host redoes this E-step once (hmmb_bw_iterate)
@@ -594,7 +662,9 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
             atomicAdd(new_flags, 1);
         }
     }
+#if HMMB_LTR_TMA
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
 
     // ---- CTA flush of the xi sums: warp shuffle tree, then one fp64 RED per entry
     double *red = sRed + (size_t)warp * 2 * NS;

@@ -173,13 +173,55 @@ struct SeqSet {
 
 static int pick_np(int N) { return N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : 32)); }
 
+// Raw codewords of a pinned host buffer are uploaded on the copy stream in a few chunks, started
+// before the host-side sorting / blocking so that PCIe time hides it; when the input is already in
+// sorted order a chunk's blocks are repacked as soon as the chunk has landed.
+struct EarlyUpload {
+    static constexpr int MAX_CHUNKS = 8;
+    void *d_raw = nullptr;
+    int nchunk = 0;
+    size_t hi[MAX_CHUNKS] = {};     // end byte of each chunk
+    cudaEvent_t ev[MAX_CHUNKS] = {};
+    bool active() const { return nchunk > 0; }
+    ~EarlyUpload() {
+        if (nchunk > 0) cudaStreamSynchronize(ctx().copy_stream);
+        for (int k = 0; k < nchunk; ++k) event_put(ev[k]);
+        dev_free(d_raw);
+    }
+};
+
 template <typename InT>
-static int launch_prepare(SeqSet &s, const InT *d_in, int64_t nsym, int *d_bad, const std::vector<Blk> &blks) {
+static int launch_prepare(SeqSet &s, const InT *d_in, int64_t nsym, int *d_bad, const std::vector<Blk> &blks,
+                          const EarlyUpload &up, bool in_sorted_order, const int64_t *off_s, const int32_t *len_s) {
     Ctx &c = ctx();
     if (s.blocked()) {
-        HMMB_LAUNCH("prepare", k_repack_blocks4<InT>, s.nblk, 256, 0, d_in, s.d_off, s.d_len, s.d_blks, s.nblk,
-                    (uint4 *)s.d_obs, s.M, d_bad);
+        int done = 0;
+        if (up.active() && in_sorted_order) {
+            for (int k = 0; k < up.nchunk; ++k) {
+                int end = done;
+                if (k == up.nchunk - 1) {
+                    end = s.nblk;
+                } else {
+                    while (end < s.nblk) {
+                        const Blk &b = blks[end];
+                        const int64_t last = (int64_t)b.first + b.nseq - 1;
+                        if ((size_t)(off_s[last] + len_s[last]) * sizeof(InT) > up.hi[k]) break;
+                        ++end;
+                    }
+                }
+                HMMB_CUDA(cudaStreamWaitEvent(c.stream, up.ev[k], 0));
+                if (end > done)
+                    HMMB_LAUNCH("prepare", k_repack_blocks4<InT>, end - done, 256, 0, d_in, s.d_off, s.d_len, s.d_blks, done,
+                                s.nblk, (uint4 *)s.d_obs, s.M, d_bad);
+                done = end;
+            }
+        } else {
+            if (up.active()) HMMB_CUDA(cudaStreamWaitEvent(c.stream, up.ev[up.nchunk - 1], 0));
+            HMMB_LAUNCH("prepare", k_repack_blocks4<InT>, s.nblk, 256, 0, d_in, s.d_off, s.d_len, s.d_blks, 0, s.nblk,
+                        (uint4 *)s.d_obs, s.M, d_bad);
+        }
     } else {
+        if (up.active()) HMMB_CUDA(cudaStreamWaitEvent(c.stream, up.ev[up.nchunk - 1], 0));
         int grid = (int)std::min<int64_t>((nsym + 255) / 256, (int64_t)c.sm_count * 8);
         if (grid < 1) grid = 1;
         if (s.sym_bytes == 1)
@@ -187,7 +229,6 @@ static int launch_prepare(SeqSet &s, const InT *d_in, int64_t nsym, int *d_bad, 
         else
             HMMB_LAUNCH("prepare", (k_convert_obs<InT, uint16_t>), grid, 256, 0, d_in, nsym, (uint16_t *)s.d_obs, s.M, d_bad);
     }
-    (void)blks;
     return HMMB_OK;
 }
 
@@ -222,6 +263,33 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     s.sym_bytes = M <= 256 ? 1 : 2;
     s.special4 = layout == LAYOUT_AUTO && N == 4 && M <= BW4_MAX_M && !getenv("HMMB_FORCE_GENERIC");
     s.ltr_ns = (layout == LAYOUT_LTR) ? N : 0;
+
+    EarlyUpload up;
+    if (!obs_on_device && R > 0 && offsets[R] > offsets[0] && offsets[R] - offsets[0] < (int64_t(1) << 40)) {
+        const char *src = (const char *)obs + (size_t)offsets[0] * idx_bytes;
+        const size_t in_bytes = (size_t)(offsets[R] - offsets[0]) * idx_bytes;
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        (void)cudaGetLastError();
+        if (pinned && in_bytes >= (size_t(4) << 20)) {
+            HMMB_TRY(dev_alloc(&up.d_raw, in_bytes));
+            // the recycled block may still be in use by work queued on the compute stream
+            cudaEvent_t fence = event_get();
+            HMMB_CUDA(cudaEventRecord(fence, c.stream));
+            HMMB_CUDA(cudaStreamWaitEvent(c.copy_stream, fence, 0));
+            event_put(fence);
+            const int nchunk = (int)std::min<size_t>(EarlyUpload::MAX_CHUNKS, std::max<size_t>(1, in_bytes >> 24));
+            for (int k = 0; k < nchunk; ++k) {
+                const size_t lo = k == 0 ? 0 : up.hi[k - 1];
+                const size_t hi = k == nchunk - 1 ? in_bytes : ((in_bytes / nchunk) * (k + 1)) & ~size_t(255);
+                HMMB_CUDA(cudaMemcpyAsync((char *)up.d_raw + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, c.copy_stream));
+                up.ev[k] = event_get();
+                up.hi[k] = hi;
+                up.nchunk = k + 1;
+                HMMB_CUDA(cudaEventRecord(up.ev[k], c.copy_stream));
+            }
+        }
+    }
 
     // Per-sequence metadata is staged in ONE pinned host buffer (cached in the context) and goes
     // to the device with a single copy: [off int64 | foff int64 | len int32 | word int32 | order int32].
@@ -387,7 +455,9 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     const size_t in_bytes = (size_t)s.frames * idx_bytes;
     if (R > 0) {
         const char *src = (const char *)obs + (size_t)offsets[0] * idx_bytes;
-        if (!obs_on_device) {
+        if (up.active()) {
+            d_in = up.d_raw;  // already on its way (copy stream); launch_prepare waits on the chunk events
+        } else if (!obs_on_device) {
             HMMB_TRY(dev_alloc(&d_tmp, in_bytes));
             HMMB_CUDA(cudaMemcpyAsync(d_tmp, src, in_bytes, cudaMemcpyHostToDevice, c.stream));
             d_in = d_tmp;
@@ -401,10 +471,10 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     int rc = HMMB_OK;
     if (R > 0) {
         switch (idx_bytes) {
-            case 1: rc = launch_prepare(s, (const uint8_t *)d_in, s.frames, d_bad, blks); break;
-            case 2: rc = launch_prepare(s, (const uint16_t *)d_in, s.frames, d_bad, blks); break;
-            case 4: rc = launch_prepare(s, (const uint32_t *)d_in, s.frames, d_bad, blks); break;
-            default: rc = launch_prepare(s, (const unsigned long long *)d_in, s.frames, d_bad, blks); break;
+            case 1: rc = launch_prepare(s, (const uint8_t *)d_in, s.frames, d_bad, blks, up, !unsorted, off_s, len_s); break;
+            case 2: rc = launch_prepare(s, (const uint16_t *)d_in, s.frames, d_bad, blks, up, !unsorted, off_s, len_s); break;
+            case 4: rc = launch_prepare(s, (const uint32_t *)d_in, s.frames, d_bad, blks, up, !unsorted, off_s, len_s); break;
+            default: rc = launch_prepare(s, (const unsigned long long *)d_in, s.frames, d_bad, blks, up, !unsorted, off_s, len_s); break;
         }
     }
     int bad = 0;

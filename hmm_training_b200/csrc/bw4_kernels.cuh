@@ -36,10 +36,10 @@ constexpr int BW4_MAX_M = 512;   // warp-private count copies must fit in shared
 template <typename InT>
 __global__ void __launch_bounds__(256)
 k_repack_blocks4(const InT *__restrict__ obs, const int64_t *__restrict__ off_sorted,
-                 const int32_t *__restrict__ len_sorted, const Blk *__restrict__ blks, int nblk,
+                 const int32_t *__restrict__ len_sorted, const Blk *__restrict__ blks, int blk_base, int nblk,
                  uint4 *__restrict__ obs_blk, int M, int *__restrict__ bad) {
     __shared__ unsigned short sSym[SPC4][32];
-    const int b = blockIdx.x;
+    const int b = blk_base + blockIdx.x;
     if (b >= nblk) return;
     const Blk bk = blks[b];
     const int nch = (bk.tmax + SPC4 - 1) / SPC4;

@@ -48,6 +48,7 @@ struct Ctx {
     int64_t global_mem = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of raw codewords, overlapped with host prep and repack
     int64_t launches = 0;
     bool profiling = false;
     std::vector<std::string> phase_names;
@@ -74,6 +75,8 @@ int phase_id(const char *name);
 void phase_begin(int id);
 void phase_end(int id);
 int phase_collect();  // synchronises and folds pending event pairs into phase_ms
+cudaEvent_t event_get();          // pooled events (no timing semantics implied)
+void event_put(cudaEvent_t e);
 
 template <typename T>
 inline int dev_alloc_t(T **p, size_t n) {

@@ -90,6 +90,9 @@ static cudaEvent_t get_event() {
     return e;
 }
 
+cudaEvent_t event_get() { return get_event(); }
+void event_put(cudaEvent_t e) { g_ctx.event_pool.push_back(e); }
+
 void phase_begin(int id) {
     Ctx &c = g_ctx;
     PhaseRec r;
@@ -161,6 +164,7 @@ int hmmb_init(int device) {
     c.global_mem = (int64_t)prop.totalGlobalMem;
     HMMB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
+    HMMB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     c.inited = true;
     return HMMB_OK;
 }
@@ -179,7 +183,8 @@ int hmmb_shutdown(void) {
     for (auto ev : c.event_pool) cudaEventDestroy(ev);
     c.event_pool.clear();
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
-    c.own_stream = c.stream = nullptr;
+    if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
+    c.own_stream = c.stream = c.copy_stream = nullptr;
     c.inited = false;
     return HMMB_OK;
 }

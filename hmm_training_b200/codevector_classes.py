@@ -125,9 +125,36 @@ class DataStorage:
         return data
 
 
+def load_mfcc_matrix(filepath: str) -> np.ndarray:
+    """[F, 13] fp64 matrix of the "mfcc_vector" fields of a frame file written by
+    DataStorage.save_raw_data (reference :438-444), in file order, WITHOUT building F
+    RawDataMFCC objects: the text is scanned once by the native loader
+    (hmmb_frames_json_scan, csrc/loader.cu).  Values are bit-identical to
+    ``[f.mfcc for f in DataStorage.load_raw_data_mfcc(filepath)]`` of this package."""
+    import ctypes
+    from . import _lib
+    with open(filepath, "rb") as f:
+        text = f.read()
+    cap = len(text) // 100 + 1  # a frame object is far longer than 100 bytes of text
+    out = np.empty((cap, 13), dtype=np.float64)
+    n = _lib.load().hmmb_frames_json_scan(text, len(text), out.ctypes.data_as(ctypes.c_void_p), cap)
+    if n < 0:
+        msg = _lib.load().hmmb_last_error().decode(errors="replace")
+        raise ValueError(msg)
+    if n > cap:  # cannot happen for files written by save_raw_data; keep the contract anyway
+        out = np.empty((n, 13), dtype=np.float64)
+        n = _lib.load().hmmb_frames_json_scan(text, len(text), out.ctypes.data_as(ctypes.c_void_p), n)
+    return np.ascontiguousarray(out[:n])
+
+
 def frames_matrix(frames) -> np.ndarray:
     """[F, 13] fp64 matrix of the frames' .mfcc (duck-typed: the reference's own RawDataMFCC
     objects work as well)."""
+    if isinstance(frames, np.ndarray):  # already a packed [F, 13] matrix (load_mfcc_matrix)
+        X = np.ascontiguousarray(frames, dtype=np.float64)
+        if X.ndim != 2 or X.shape[1] != 13:
+            raise ValueError("Vectors must be of size 13.")
+        return X
     F = len(frames)
     X = np.empty((F, 13), dtype=np.float64)
     for i, fr in enumerate(frames):

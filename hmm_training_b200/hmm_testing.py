@@ -2,8 +2,8 @@
 
     calculate_log_likelihood   HMM/hmm_testing.py:49-104
     test_hmm                   HMM/hmm_testing.py:107-163
-plus ``score_all`` (every utterance against every model in one launch).  The
-confusion-matrix plotting (:166-218) is reporting, out of scope.
+    create_confusion_matrix    HMM/hmm_testing.py:166-218
+plus ``score_all`` (every utterance against every model in one launch).
 """
 from __future__ import annotations
 
@@ -81,3 +81,87 @@ def test_hmm(all_hmm: List[HMMTrained], test_recordings_dict: Dict[str, List[Lis
             predicted_labels.append(predicted if predicted else "unknown")
             pos += 1
     return true_labels, predicted_labels
+
+
+def confusion_counts(true_labels: Sequence[str], predicted_labels: Sequence[str]):
+    """(cm [L,L] int64, labels): rows = true word, columns = predicted word, labels sorted as in
+    the reference (hmm_testing.py:182-185; same matrix as sklearn's confusion_matrix)."""
+    labels = sorted(set(true_labels) | set(predicted_labels))
+    index = {w: i for i, w in enumerate(labels)}
+    L = len(labels)
+    t = np.fromiter((index[w] for w in true_labels), dtype=np.int64, count=len(true_labels))
+    p = np.fromiter((index[w] for w in predicted_labels), dtype=np.int64, count=len(predicted_labels))
+    cm = np.bincount(t * L + p, minlength=L * L).reshape(L, L) if L else np.zeros((0, 0), np.int64)
+    return cm.astype(np.int64), labels
+
+
+def classification_report_text(cm: np.ndarray, labels: Sequence[str], digits: int = 2) -> str:
+    """Per-word precision / recall / f1 / support table in the layout of
+    sklearn.metrics.classification_report (what the reference prints, hmm_testing.py:214),
+    computed from the confusion counts; 0/0 ratios are reported as 0 like sklearn does."""
+    cm = np.asarray(cm, dtype=np.float64)
+    tp = np.diag(cm)
+    support = cm.sum(axis=1)
+    pred = cm.sum(axis=0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        prec = np.where(pred > 0, tp / pred, 0.0)
+        rec = np.where(support > 0, tp / support, 0.0)
+        f1 = np.where(prec + rec > 0, 2 * prec * rec / (prec + rec), 0.0)
+    total = support.sum()
+    names = [str(x) for x in labels]
+    width = max([len(n) for n in names] + [len("weighted avg"), digits])
+    head = "{:>{w}s} ".format("", w=width) + "".join(" {:>9}".format(h) for h in ("precision", "recall", "f1-score", "support"))
+    lines = [head, ""]
+    row = "{:>{w}s} " + " {:>9.{d}f}" * 3 + " {:>9}"
+    for n, p_, r_, f_, s_ in zip(names, prec, rec, f1, support):
+        lines.append(row.format(n, p_, r_, f_, int(s_), w=width, d=digits))
+    lines.append("")
+    acc = tp.sum() / total if total else 0.0
+    lines.append("{:>{w}s} ".format("accuracy", w=width) + " {:>9}".format("") * 2 + " {:>9.{d}f}".format(acc, d=digits) +
+                 " {:>9}".format(int(total)))
+    wavg = lambda x: float((x * support).sum() / total) if total else 0.0
+    lines.append(row.format("macro avg", prec.mean() if len(prec) else 0.0, rec.mean() if len(rec) else 0.0,
+                            f1.mean() if len(f1) else 0.0, int(total), w=width, d=digits))
+    lines.append(row.format("weighted avg", wavg(prec), wavg(rec), wavg(f1), int(total), w=width, d=digits))
+    return "\n".join(lines) + "\n"
+
+
+def create_confusion_matrix(true_labels: List[str], predicted_labels: List[str], base_dir="../Data"):
+    """hmm_testing.py:166-218: confusion matrix over the sorted label set, accuracy, the
+    classification report, and the matrix saved under <base_dir>/Plots.  The reference draws a
+    seaborn heat map (confusion_matrix.png); that is done when matplotlib + seaborn are
+    importable, and the counts are always written as confusion_matrix.csv.  Returns (cm, labels)."""
+    plots_dir = os.path.join(base_dir, "Plots")
+    os.makedirs(plots_dir, exist_ok=True)
+    cm, unique_labels = confusion_counts(true_labels, predicted_labels)
+    accuracy = (cm.diagonal().sum() / cm.sum()) * 100 if cm.sum() else float("nan")
+    csv_path = os.path.join(plots_dir, "confusion_matrix.csv")
+    with open(csv_path, "w") as f:
+        f.write("true\\predicted," + ",".join(unique_labels) + "\n")
+        for w, row in zip(unique_labels, cm):
+            f.write(w + "," + ",".join(str(int(x)) for x in row) + "\n")
+    plot_path = csv_path
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+        import seaborn as sns
+        plt.figure(figsize=(10, 8))
+        sns.heatmap(cm, annot=True, fmt="d", cmap="Blues", xticklabels=unique_labels, yticklabels=unique_labels,
+                    cbar_kws={"label": "Number of Recordings"})
+        plt.title(f"HMM Classification Confusion Matrix\nAccuracy: {accuracy:.2f}%", fontsize=14, fontweight="bold")
+        plt.xlabel("Predicted Word", fontsize=12)
+        plt.ylabel("True Word", fontsize=12)
+        plt.xticks(rotation=45, ha="right")
+        plt.yticks(rotation=0)
+        plt.tight_layout()
+        plot_path = os.path.join(plots_dir, "confusion_matrix.png")
+        plt.savefig(plot_path, dpi=300, bbox_inches="tight")
+        plt.close()
+    except ImportError:
+        pass
+    print("\nClassification Report:")
+    print(classification_report_text(cm, unique_labels))
+    print(f"\nConfusion matrix saved to: {plot_path}")
+    print(f"Overall Accuracy: {accuracy:.2f}%")
+    return cm, unique_labels

@@ -58,10 +58,11 @@ def get_observations(recordings: List[List[RawDataMFCC]], centroids: List[Centro
     ``np.ndarray`` of int64 centroid indices per recording.  All recordings go to the GPU
     in a single hmmb_vq_encode call."""
     lens = [len(r) for r in recordings]
-    flat = [f for r in recordings for f in r]
-    if not flat:
+    if sum(lens) == 0:
         return [np.array([]) for _ in recordings]  # np.array([]) is what the reference builds for an empty recording
-    X = frames_matrix(flat)
+    # a recording is a list of RawDataMFCC (the reference's layout) or a packed [T, 13] matrix
+    # (codevector_classes.load_mfcc_matrix: the fast loader that skips the per-frame objects)
+    X = np.concatenate([frames_matrix(r) for r in recordings if len(r)], axis=0)
     C = frames_matrix(centroids)
     idx = engine.vq_encode(X, C).astype(np.int64)
     out, pos = [], 0
@@ -178,7 +179,7 @@ def training_with_save(word_recordings: List[RawDataMFCC], centroids: List[Centr
 
 def train_hmm_batched(recordings_by_word: Dict[str, List[List[RawDataMFCC]]], centroids: List[CentroidDataMFCC],
                       max_iterations: int = 100, show_progress: bool = False, save: bool = True,
-                      base_dir: str = "../Data/ResultsHMM") -> List[HMMTrained]:
+                      base_dir: str = "../Data/ResultsHMM", load_initial_params: bool = False) -> List[HMMTrained]:
     """Batched equivalent of the loop in the reference's HMM/main.py:train_hmm (:133-164):
     one VQ-encode call and one Baum-Welch call for the whole vocabulary."""
     words = list(recordings_by_word.keys())
@@ -190,8 +191,13 @@ def train_hmm_batched(recordings_by_word: Dict[str, List[List[RawDataMFCC]]], ce
         by_word.append(obs[pos:pos + n])
         pos += n
     M = len(centroids)
-    A, B, pi, hist, iters = hmm_training_batched(by_word, 4, M, 1e-6, max_iterations, show_progress=show_progress,
-                                                 word_names=words)
+    init = None
+    if load_initial_params:
+        # per-word warm start exactly as hmm_training does it (:270-320), defaults where no file matches
+        ps, As, Bs = zip(*[_initial_params(4, M, w, True, show_progress) for w in words])
+        init = (np.stack(ps), np.stack(As), np.stack(Bs))
+    A, B, pi, hist, iters = hmm_training_batched(by_word, 4, M, 1e-6, max_iterations, init=init,
+                                                 show_progress=show_progress, word_names=words)
     models = []
     for i, w in enumerate(words):
         m = HMMTrained(states=4, symbols=M, A=A[i], B=B[i], Pi=pi[i], word=w)

@@ -146,6 +146,17 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
                int W, int N, int M, const double *pi, const double *A, const double *B,
                double *ll_out, int32_t *argmax_out);
 
+/* ------------------------------------------------------------------ frame-file loader (host only)
+ * Replaces the json.load + RawDataMFCC.from_dict loop of DataStorage.load_raw_data_mfcc,
+ * CodeVector/codevector_classes.py:478-495, for the one field the hot path reads: scans the
+ * text of a frame file (a JSON list of RawDataMFCC.to_dict() objects, :252-264) and writes
+ * every "mfcc_vector" (13 fp64, bit-identical to Python's float parsing) to mfcc_out
+ * [cap_frames,13] in file order.  Returns the number of frames found (frames beyond
+ * cap_frames are counted but not stored; mfcc_out may be NULL to count only) or a negative
+ * error (HMMB_ERR_RANGE: a vector that does not have 13 entries — the reference raises
+ * ValueError("Vectors must be of size 13."), codevector_functions.py:83-84).  No CUDA needed. */
+int64_t hmmb_frames_json_scan(const char *text, int64_t len, double *mfcc_out, int64_t cap_frames);
+
 #ifdef __cplusplus
 }
 #endif

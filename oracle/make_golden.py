@@ -175,8 +175,71 @@ def case_lbg(ref):
     _lbg_case(ref, "lbg_k24_nonpow2", S.mfcc_mixture(8, 200, K=8), 24, 10)
 
 
+def case_frames(ref):
+    """Frame file written by the reference's own DataStorage.save_raw_data (codevector_classes.py:
+    438-444) — the input of the native loader (hmmb_frames_json_scan).  raw_samples stay empty so
+    that __post_init__ does not call librosa (:217-220); names and values are chosen to be awkward."""
+    Raw = ref.cvc.RawDataMFCC
+    rng = np.random.default_rng(21)
+    X = S.mfcc_mixture(9, 40, K=4)
+    X[3] = [0.0, -0.0, 5e-324, 1e-320, 2.2250738585072014e-308, 1.7976931348623157e308, -1e300, 1.0, 3.0, 1e22,
+            123456789012345680.0, 0.1, 1 / 3]
+    X[7] = np.round(X[7])  # integral floats print as "12.0"
+    names = ['finish-04', 'say "mfcc_vector": [1, 2]', 'back\\slash\\', 'quote\\"end', "üñí", "mfcc_vector"]
+    frames = [Raw(raw_samples=np.array([]), mfcc=X[i].copy(), frame_number=i, recording=names[i % len(names)],
+                  parent_centroid_id=int(rng.integers(0, 256)), generation=int(rng.integers(0, 9)))
+              for i in range(len(X))]
+    path = os.path.join(OUT, "frames_ref.json")
+    ref.cvc.DataStorage.save_raw_data(frames, path)
+    np.savez_compressed(os.path.join(OUT, "frames_ref.npz"), X=X)
+
+
+def case_pipeline(ref):
+    """The callers either side of the hot path, run by the reference itself on a small Data/ tree:
+    training_with_save per word (HMM/main.py:147-154) then test_hmm (HMM/hmm_testing.py:107-163)."""
+    Raw, Cen = ref.cvc.RawDataMFCC, ref.cvc.CentroidDataMFCC
+    rng = np.random.default_rng(33)
+    W, S_tr, S_te, K = 3, 6, 4, 16
+    C = S.random_codebook(12, K)
+    words = ["alpha", "bravo", "charlie"]
+
+    def recording(w):
+        T = int(rng.integers(18, 34))
+        seg = np.sort(rng.integers(0, 4, size=T))
+        cent = C[(4 * w + seg + rng.integers(0, 2, size=T)) % K]
+        return cent + rng.normal(size=(T, 13)) * np.concatenate([[30.0], np.linspace(4.0, 0.5, 12)])
+
+    train = [[recording(w) for _ in range(S_tr)] for w in range(W)]
+    test = [[recording(w) for _ in range(S_te)] for w in range(W)]
+    centroids = [Cen(mfcc=C[k].copy(), id=k) for k in range(K)]
+    to_frames = lambda rec: [Raw(raw_samples=np.array([]), mfcc=x.copy()) for x in rec]
+    cwd = os.getcwd()
+    models = []
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "HMM"))
+        os.makedirs(os.path.join(tmp, "Data", "CodeVector"))
+        os.chdir(os.path.join(tmp, "HMM"))
+        try:
+            with ref_shim.quiet():
+                ref.cvc.DataStorage.save_centroids(centroids, os.path.join(tmp, "Data", "CodeVector", "codevector.json"))
+                for w in range(W):
+                    models.append(ref.training.training_with_save([to_frames(r) for r in train[w]], centroids, words[w],
+                                                                  max_iterations=3, show_progress=False))
+                true, pred = ref.testing.test_hmm(models, {words[w]: [to_frames(r) for r in test[w]] for w in range(W)},
+                                                  base_dir=os.path.join(tmp, "Data"))
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "pipeline_ref.npz"), C=C, words=np.array(words),
+                        train=np.concatenate([r for word in train for r in word]),
+                        train_len=np.array([[len(r) for r in word] for word in train]),
+                        test=np.concatenate([r for word in test for r in word]),
+                        test_len=np.array([[len(r) for r in word] for word in test]),
+                        A=np.stack([m.A for m in models]), B=np.stack([m.B for m in models]),
+                        pi=np.stack([m.Pi for m in models]), true=np.array(true), pred=np.array(pred))
+
+
 CASES = {"bw_c1": case_bw_c1, "bw_small": case_bw_small, "bw_warm": case_bw_warm,
-         "vq": case_vq, "lbg": case_lbg}
+         "vq": case_vq, "lbg": case_lbg, "frames": case_frames, "pipeline": case_pipeline}
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)

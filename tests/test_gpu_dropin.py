@@ -147,3 +147,52 @@ def test_create_code_vector_side_effects(tmp_path):
     assert reloaded[7].parent_centroid_id == frames[7].parent_centroid_id and np.array_equal(reloaded[7].mfcc, frames[7].mfcc)
     with pytest.raises(ValueError):
         cvf.createCodeVector([])
+
+
+def _write_tree(tmp, g, save_raw):
+    """Data/ tree of the reference's layout from the pipeline golden."""
+    from hmm_training_b200.codevector_classes import CentroidDataMFCC, DataStorage, RawDataMFCC
+    words = [str(w) for w in g["words"]]
+    data = os.path.join(tmp, "Data")
+    os.makedirs(os.path.join(data, "CodeVector"))
+    os.makedirs(os.path.join(tmp, "HMM"))
+    DataStorage.save_centroids([CentroidDataMFCC(mfcc=c, id=k) for k, c in enumerate(g["C"])],
+                               os.path.join(data, "CodeVector", "codevector.json"))
+    for purpose, key, fname in (("TrainHMM", "train", "hmm_frames.json"), ("Test", "test", "test_frames.json")):
+        pos = 0
+        for w, word in enumerate(words):
+            for r, T in enumerate(g[key + "_len"][w]):
+                d = os.path.join(data, purpose, word, f"{word}-{r:02d}")
+                os.makedirs(d)
+                frames = [RawDataMFCC(raw_samples=save_raw(T, i), mfcc=x, frame_number=i, recording=f"{word}-{r:02d}")
+                          for i, x in enumerate(g[key][pos:pos + T])]
+                DataStorage.save_raw_data(frames, os.path.join(d, fname))
+                pos += T
+    return words
+
+
+@pytest.mark.parametrize("batched,fast", [(True, True), (False, False)])
+def test_train_and_test_callers_match_reference_pipeline(batched, fast, tmp_path, monkeypatch, capsys):
+    """HMM/main.py train_hmm + test on a Data/ tree, against models and predictions produced by
+    the reference's own training_with_save / test_hmm on the same frames (pipeline_ref.npz)."""
+    from helpers import assert_close, load_golden
+    from hmm_training_b200 import main as hmain
+    g = load_golden("pipeline_ref")
+    rng = np.random.default_rng(1)
+    words = _write_tree(str(tmp_path), g, lambda T, i: rng.normal(size=8) if fast else np.array([]))
+    monkeypatch.chdir(tmp_path / "HMM")  # the reference's paths are relative to the CWD (../Data/...)
+    models = hmain.train_hmm(show_progress=False, max_iterations=3, batched=batched, fast=fast)
+    assert models is not None and sorted(m.word for m in models) == sorted(words)
+    by_word = {m.word: m for m in models}
+    for w, word in enumerate(words):
+        m = by_word[word]
+        assert_close(m.A, g["A"][w], f"{word} A"); assert_close(m.B, g["B"][w], f"{word} B")
+        assert_close(m.Pi, g["pi"][w], f"{word} pi")
+        assert os.path.exists(tmp_path / "Data" / "ResultsHMM" / f"{word}.json")
+    true, pred = hmain.test(fast=fast)
+    order = np.argsort(np.array(true), kind="stable")  # directory iteration order is arbitrary
+    gorder = np.argsort(g["true"], kind="stable")
+    assert [true[i] for i in order] == [str(x) for x in g["true"][gorder]]
+    assert [pred[i] for i in order] == [str(x) for x in g["pred"][gorder]]
+    out = capsys.readouterr().out
+    assert "Overall Accuracy: 100.00%" in out and os.path.exists(tmp_path / "Data" / "Plots" / "confusion_matrix.csv")

@@ -64,8 +64,9 @@ k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4
     for (int b = b0 + warp; b < b1; b += BW_WARPS) {
         const Blk bk = blks[b];
         const int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
+        bool af;
         const double ll = fwd4_run<BIDIAG, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, reinterpret_cast<const double2 *>(sB),
-                                                  reinterpret_cast<const double2 *>(sB) + M, sBmax, sBmask, a, p, rmax, mk, nullptr);
+                                                  reinterpret_cast<const double2 *>(sB) + M, sBmax, sBmask, a, p, rmax, mk, nullptr, af);
         if (lane < bk.nseq) ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
     }
 }
@@ -620,6 +621,7 @@ int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_d
         spill_bytes = (size_t)std::max<int64_t>(s.spill_steps, 1) * 64 * sizeof(double2);
         TRYF(dev_alloc_t(&h->d_partials, (size_t)std::max(s.ncta, 1) * h->pstride));
         TRYF(dev_alloc_t(&h->d_cta_begin, (size_t)W + 1));
+        TRYF(dev_alloc_t(&h->d_allfull, (size_t)std::max<int64_t>(R, 1)));
         CUDAF(cudaMemcpyAsync(h->d_cta_begin, s.cta_begin.data(), (W + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
     } else {
         spill_bytes = (size_t)std::max<int64_t>(s.frames, 1) * N * sizeof(double);
@@ -768,11 +770,12 @@ static int launch_special_estep(hmmb_bw *h) {
     const size_t smem_b = (size_t)h->M * 4 * sizeof(double) * (1 + BW_WARPS) + (size_t)BW_THREADS * 4 * sizeof(double);
     HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwd4<BIDIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
-                s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag);
+                s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag,
+                h->d_allfull);
     HMMB_TRY((launch_exact<uint16_t, true>(h)));
     HMMB_LAUNCH("bw_backward", k_bw_bwd4<BIDIAG>, s.ncta, BW_THREADS, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
                 s.d_len, h->d_A, h->d_Bt, h->M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero,
-                h->d_partials, h->pstride, h->d_flag, h->d_newflags);
+                h->d_allfull, h->d_partials, h->pstride, h->d_flag, h->d_newflags);
     return HMMB_OK;
 }
 

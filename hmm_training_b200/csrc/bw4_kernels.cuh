@@ -176,13 +176,14 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
                                            const double *__restrict__ sBmax,
                                            const unsigned char *__restrict__ sBmask, const double *a,
                                            const double (&p)[4], double rmax, const Masks4 &mk,
-                                           double2 *__restrict__ sp) {
+                                           double2 *__restrict__ sp, bool &allfull) {
     using S16 = Sym<uint16_t>;
     double al0 = 0.0, al1 = 0.0, al2 = 0.0, al3 = 0.0;
     double E = 0.0;  // error bound, units of 2^-1000
     long long esum = 0;
     unsigned m = 0u;    // alive set
     bool stop = false;  // dead (impossible) or flagged for the exact path
+    bool allf = true;   // every step so far had all four states alive and a scale >= 1: every alpha-hat > 0
     double ll = neg_inf();
     const double tiny = tiny_pos();
     const int nch = (tmax + SPC4 - 1) / SPC4;
@@ -199,11 +200,9 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
                 const unsigned r = (t == 0) ? mk.pmask : lut4(mk.lutF, m);  // reachable before emission
                 m = r & (unsigned)sBmask[sym];
                 double n0, n1, n2, n3, at0, at1, at2, at3;
-                if (m == 0xFu) {
-                    // ---- every state alive (the usual case)
-                    if (t == 0) {
-                        n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
-                    } else if (BIDIAG) {
+                if (m == 0xFu && t > 0) {
+                    // ---- every state alive (the usual case; the first step takes the masked branch)
+                    if (BIDIAG) {
                         n0 = fma(al0, a[0], tiny);
                         n1 = fma(al1, a[1], fma(al0, a[4], tiny));
                         n2 = fma(al2, a[2], fma(al1, a[5], tiny));
@@ -220,7 +219,8 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
                     stop = true;  // no state can emit o_t: log P = -inf (:155-160)
                     n0 = n1 = n2 = n3 = at0 = at1 = at2 = at3 = 0.0;
                 } else {
-                    // ---- some states structurally dead: masked addends keep them exactly 0
+                    // ---- first step, or some states structurally dead: masked addends keep them exactly 0
+                    allf = allf && (m == 0xFu);
                     const double r0 = tiny_if(r, 0), r1 = tiny_if(r, 1), r2 = tiny_if(r, 2), r3 = tiny_if(r, 3);
                     if (t == 0) {
                         n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
@@ -249,9 +249,11 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
                         at0 = o[0]; at1 = o[1]; at2 = o[2]; at3 = o[3];
                         ssum = (at0 + at1) + (at2 + at3);
                     }
+                    allf = false;
                 }
                 if (!stop) {
                     const double sc = pow2_rescale(ssum, esum);
+                    allf = allf && (__double2hiint(sc) >= 0x3ff00000);  // scale >= 1 cannot flush a denormal alpha
                     al0 = at0 * sc; al1 = at1 * sc; al2 = at2 * sc; al3 = at3 * sc;
                     E = fma(E, rmax * sBmax[sym], 4.0 * ERR_UNIT) * sc;
                     if (!(E <= ERR_LIMIT)) {
@@ -260,14 +262,16 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
                     }
                     if (t == T - 1 && !stop) ll = log((al0 + al1) + (al2 + al3)) + (double)esum * LN2;
                 }
-                if (stop) al0 = al1 = al2 = al3 = 0.0;
-                if (SPILL) {
+                // a stopped sequence (impossible, or handed to the exact kernel) is skipped by the backward
+                // pass, so nothing of it needs to be spilled from here on
+                if (SPILL && !stop) {
                     __stcs(sp + (size_t)t * 64, make_double2(al0, al1));
                     __stcs(sp + (size_t)t * 64 + 32, make_double2(al2, al3));
                 }
             }
         }
     }
+    allfull = allf && !stop;
     return ll;
 }
 
@@ -320,12 +324,16 @@ __device__ __forceinline__ void load_A4(const double *__restrict__ Aw, double *a
     }
 }
 
+// 4 CTAs per SM: with 5 (96 registers) the forward pass measured 8 % slower on config 3
+#ifndef FWD4_MIN_CTAS
+#define FWD4_MIN_CTAS 4
+#endif
 template <bool BIDIAG>
-__global__ void __launch_bounds__(BW_THREADS)
+__global__ void __launch_bounds__(BW_THREADS, FWD4_MIN_CTAS)
 k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
           const int32_t *__restrict__ len_sorted, const double *__restrict__ pi, const double *__restrict__ A,
           const double *__restrict__ Bt, int M, double2 *__restrict__ spill, double *__restrict__ ll_seq,
-          const int32_t *__restrict__ active, uint8_t *__restrict__ flag) {
+          const int32_t *__restrict__ active, uint8_t *__restrict__ flag, uint8_t *__restrict__ allfull) {
     extern __shared__ double sB[];  // [M][4] B^T, [M] per-codeword max, [M] support masks (u8)
     double *sBmax = sB + (size_t)M * 4;
     unsigned char *sBmask = reinterpret_cast<unsigned char *>(sBmax + M);
@@ -340,11 +348,13 @@ k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         const Blk bk = blks[b];
         int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
         if (T > 0 && flag[bk.first + lane]) T = 0;  // handled by the exact log-space kernel
+        bool af = false;
         const double ll = fwd4_run<BIDIAG, true>(T, bk.tmax, obs_blk + bk.obs_base + lane, reinterpret_cast<const double2 *>(sB),
                                                  reinterpret_cast<const double2 *>(sB) + M, sBmax, sBmask, a, p, rmax,
-                                                 mk, spill + bk.spill_base * 64 + lane);
+                                                 mk, spill + bk.spill_base * 64 + lane, af);
         if (T > 0) {
             ll_seq[bk.first + lane] = ll;
+            allfull[bk.first + lane] = af ? 1 : 0;
             if (ll != ll) flag[bk.first + lane] = 1;  // precision guard: hand over (sticky)
         }
     }
@@ -493,8 +503,8 @@ __global__ void __launch_bounds__(BW_THREADS, BIDIAG ? 4 : 3)
 k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
           const int32_t *__restrict__ len_sorted, const double *__restrict__ A, const double *__restrict__ Bt, int M,
           const double2 *__restrict__ spill, const double *__restrict__ ll_seq, const int32_t *__restrict__ active,
-          const int32_t *__restrict__ b_has_zero, double *__restrict__ partials, int64_t pstride,
-          uint8_t *__restrict__ flag, int32_t *__restrict__ new_flags) {
+          const int32_t *__restrict__ b_has_zero, const uint8_t *__restrict__ allfull, double *__restrict__ partials,
+          int64_t pstride, uint8_t *__restrict__ flag, int32_t *__restrict__ new_flags) {
     using S16 = Sym<uint16_t>;
     extern __shared__ double smem[];
     double *sB = smem;                              // B^T: [M] double2 (b0,b1) then [M] double2 (b2,b3)
@@ -535,10 +545,12 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     for (int b = cw.blk_begin + warp; b < cw.blk_end; b += BW_WARPS) {
         const Blk bk = blks[b];
         int T = 0;
+        bool apos = false;
         if (lane < bk.nseq) {
             T = len_sorted[bk.first + lane];
             if (!(ll_seq[bk.first + lane] > neg_inf())) T = 0;  // impossible sequence: contributes nothing (:391-394)
             if (flag[bk.first + lane]) T = 0;                   // exact log-space kernel did this one
+            apos = allfull[bk.first + lane] != 0;               // forward pass: every alpha-hat of this sequence > 0
         }
         st.v0 = st.v1 = st.v2 = st.v3 = 0.0;
         st.imprecise = false;
@@ -604,7 +616,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                     const double nv0 = fma(b01.x, h0, tiny), nv1 = fma(b01.y, h1, tiny);                            \
                     const double nv2 = fma(b23.x, h2, tiny), nv3 = fma(b23.y, h3, tiny);                            \
                     const double vs = (nv0 + nv1) + (nv2 + nv3);                                                    \
-                    if ((norm >= LEAN_MIN) & (qs >= LEAN_MIN) & (vs >= LEAN_MIN) & all_pos4(al0, al1, al2, al3)) {  \
+                    if ((norm >= LEAN_MIN) & (qs >= LEAN_MIN) & (vs >= LEAN_MIN) && (apos || all_pos4(al0, al1, al2, al3))) { \
                         const double r = 1.0 / norm;                                                                \
                         g0 = fma(c0, r, tiny); g1 = fma(c1, r, tiny); g2 = fma(c2, r, tiny); g3 = fma(c3, r, tiny); \
                         const double u0 = al0 * r, u1 = al1 * r, u2 = al2 * r, u3 = al3 * r;                        \

@@ -234,11 +234,8 @@ __device__ __forceinline__ double fwdL_run(int T, int tmax, const uint4 *__restr
                     }
                     if (t == T - 1 && !stop) ll = log(tree_sum<NS>(al)) + (double)esum * LN2;
                 }
-                if (stop) {
-#pragma unroll
-                    for (int j = 0; j < NS; ++j) al[j] = 0.0;
-                }
-                if (SPILL) {
+                // a stopped sequence is skipped by the backward pass: nothing more to spill
+                if (SPILL && !stop) {
 #pragma unroll
                     for (int q = 0; q < L::CPR; ++q)
                         __stcs(sp + ((size_t)t * L::CPR + q) * 32, make_double2(al[2 * q], al[2 * q + 1]));

@@ -213,7 +213,7 @@ def bw_fit(obs, offsets, word_of_seq, W: int, N: int, M: int, pi0, A0, B0, epsil
 
 # ------------------------------------------------------------------------------- recognition
 def score(obs, offsets, N: int, M: int, pi, A, B, obs_dev_ptr: Optional[int] = None, idx_bytes: Optional[int] = None,
-          want_ll: bool = True):
+          want_ll: bool = True, out_ll: Optional[np.ndarray] = None):
     """log P(O_u | model_w) for every utterance x model ([U,W]) and test_hmm's argmax
     (HMM/hmm_testing.py:49-104, 139-161).  pi [W,N], A [W,N,N], B [W,N,M] linear space."""
     lib = _lib.load()
@@ -232,7 +232,12 @@ def score(obs, offsets, N: int, M: int, pi, A, B, obs_dev_ptr: Optional[int] = N
         op, on_dev, ib = ptr(obs), 0, obs.dtype.itemsize
     else:
         op, on_dev, ib = ctypes.c_void_p(obs_dev_ptr), 1, int(idx_bytes)
-    ll = np.empty((U, W)) if want_ll else None
+    if out_ll is not None:  # caller-provided [U, W] fp64 buffer (e.g. pinned memory: the D2H copy is then direct)
+        if out_ll.shape != (U, W) or out_ll.dtype != np.float64 or not out_ll.flags.c_contiguous:
+            raise ValueError(f"out_ll must be a C-contiguous float64 array of shape ({U}, {W})")
+        ll = out_ll
+    else:
+        ll = np.empty((U, W)) if want_ll else None
     arg = np.empty(max(U, 1), dtype=np.int32)
     check(lib.hmmb_score(op, ib, on_dev, ptr(offsets), U, W, N, M, ptr(pi), ptr(A), ptr(B), ptr(ll), ptr(arg)))
     return ll, arg[:U]

@@ -589,7 +589,7 @@ int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_d
     h->nacc = (int64_t)N + (int64_t)N * N + (int64_t)M * N;
     // stride multiple of 16 doubles: every word's count rows start on a 128-byte line (TMA bulk reductions)
     h->astride = (h->nacc + 1 + 15) & ~int64_t(15);
-    h->pstride = h->nacc;
+    h->pstride = h->nacc + 2;  // + the CTA's (max, sum exp) pair of the convergence statistic
     h->hist_cap = 0;
 #define TRYF(expr) do { int _r = (expr); if (_r != HMMB_OK) return fail(_r); } while (0)
 #define CUDAF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(cuda_fail(_e, #expr, __FILE__, __LINE__)); } while (0)

@@ -719,6 +719,33 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         const size_t o = (size_t)(j >> 1) * 2 * M + (size_t)sym * 2 + (j & 1);  // split (j=0,1) / (j=2,3) arrays
         part[20 + e] = ((sCnt[o] + sCnt[(size_t)M * 4 + o]) + sCnt[(size_t)M * 8 + o]) + sCnt[(size_t)M * 12 + o];
     }
+    // ---- this CTA's share of the convergence statistic log_sum_exp_r log P_r (:503): (max, sum exp(. - max))
+    // over its own sequences, combined over the word's CTAs in fixed order by k_bw_reduce
+    {
+        const int r0 = blks[cw.blk_begin].first, r1 = blks[cw.blk_end - 1].first + blks[cw.blk_end - 1].nseq;
+        double m = neg_inf();
+        for (int r = r0 + tid; r < r1; r += BW_THREADS) m = fmax(m, ll_seq[r]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        __syncthreads();  // sRed is free again
+        if (lane == 0) sRed[warp][0] = m;
+        __syncthreads();
+        m = fmax(fmax(sRed[0][0], sRed[1][0]), fmax(sRed[2][0], sRed[3][0]));
+        double sum = 0.0;
+        if (m > neg_inf())
+            for (int r = r0 + tid; r < r1; r += BW_THREADS) {
+                const double l = ll_seq[r];
+                if (l > neg_inf()) sum += exp(l - m);
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) sRed[warp][1] = sum;
+        __syncthreads();
+        if (tid == 0) {
+            part[20 + (size_t)M * 4] = m;
+            part[20 + (size_t)M * 4 + 1] = ((sRed[0][1] + sRed[1][1]) + sRed[2][1]) + sRed[3][1];
+        }
+    }
 }
 
 }  // namespace hmmb

@@ -302,9 +302,14 @@ k_bw_reduce(const double *__restrict__ partials, int64_t pstride, const int32_t 
         }
     }
     if (blockIdx.y != 0) return;
+    // items of the log-sum-exp: the word's sequences (log P_r, weight 1), or — N = 4 path — the
+    // (max, sum) pairs its CTAs left behind their partials
     const int64_t r0 = seq_begin[w], r1 = seq_begin[w + 1];
+    const int64_t i0 = partials ? cta_begin[w] : r0, i1 = partials ? cta_begin[w + 1] : r1;
+    auto item_m = [&](int64_t i) { return partials ? partials[(size_t)i * pstride + nacc] : ll_seq[i]; };
+    auto item_s = [&](int64_t i) { return partials ? partials[(size_t)i * pstride + nacc + 1] : 1.0; };
     double m = neg_inf();
-    for (int64_t r = r0 + tid; r < r1; r += RED_THREADS) m = fmax(m, ll_seq[r]);
+    for (int64_t i = i0 + tid; i < i1; i += RED_THREADS) m = fmax(m, item_m(i));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) sM[warp] = m;
@@ -313,9 +318,9 @@ k_bw_reduce(const double *__restrict__ partials, int64_t pstride, const int32_t 
     for (int q = 1; q < RED_THREADS / 32; ++q) m = fmax(m, sM[q]);
     double s = 0.0;
     if (m > neg_inf())
-        for (int64_t r = r0 + tid; r < r1; r += RED_THREADS) {
-            const double l = ll_seq[r];
-            if (l > neg_inf()) s += exp(l - m);
+        for (int64_t i = i0 + tid; i < i1; i += RED_THREADS) {
+            const double l = item_m(i);
+            if (l > neg_inf()) s += item_s(i) * exp(l - m);
         }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);

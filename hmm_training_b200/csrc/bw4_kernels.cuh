@@ -571,21 +571,22 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         uint4 wnext = __ldg(op + (size_t)(nch - 1) * 32);
 
 // One backward step at time T_ (parity C_ = T_ & 1 is a literal; O_ = the other parity).
-#define HMMB_BWD_STEP(T_, C_, O_)                                                                                   \
+#define HMMB_BWD_STEP(T_, C_, O_, SP_)                                                                              \
     {                                                                                                               \
         const int t = (T_);                                                                                         \
+        const double2 *spt = (SP_); /* = sp + t * 64: every address below is an immediate offset from it */         \
         const unsigned packed = S16::pop_back(w);                                                                   \
         if (t < bk.tmax) { /* warp-uniform */                                                                       \
             const unsigned sym = packed & SYM_MASK;                                                                 \
             const bool act = t < T;                                                                                 \
             const double al0 = P##C_##_01.x, al1 = P##C_##_01.y, al2 = P##C_##_23.x, al3 = P##C_##_23.y;            \
             if (t >= 2 && t - 2 < T) {                                                                              \
-                P##C_##_01 = __ldcs(sp + (size_t)(t - 2) * 64);                                                     \
-                P##C_##_23 = __ldcs(sp + (size_t)(t - 2) * 64 + 32);                                                \
+                P##C_##_01 = __ldcs(spt - 2 * 64);                                                                  \
+                P##C_##_23 = __ldcs(spt - 2 * 64 + 32);                                                             \
             }                                                                                                       \
             if (t >= BWD_L2_PREFETCH && t - BWD_L2_PREFETCH < T) { /* pull the spill towards L2 well ahead */      \
-                prefetch_l2(sp + (size_t)(t - BWD_L2_PREFETCH) * 64);                                               \
-                prefetch_l2(sp + (size_t)(t - BWD_L2_PREFETCH) * 64 + 32);                                          \
+                prefetch_l2(spt - BWD_L2_PREFETCH * 64);                                                            \
+                prefetch_l2(spt - BWD_L2_PREFETCH * 64 + 32);                                                       \
             }                                                                                                       \
             double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;                                                          \
             if (act) {                                                                                              \
@@ -658,13 +659,15 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         }                                                                                                           \
     }
 
+        const double2 *spp = sp + (size_t)(nch * SPC4 - 2) * 64;  // alpha-hat row of the even step of the pair
         for (int c = nch - 1; c >= 0; --c) {
             uint4 w = wnext;
             if (c > 0) wnext = __ldg(op + (size_t)(c - 1) * 32);  // prefetch the next 8 codewords
 #pragma unroll 1
             for (int pr = SPC4 / 2 - 1; pr >= 0; --pr) {
-                HMMB_BWD_STEP(c * SPC4 + 2 * pr + 1, 1, 0)
-                HMMB_BWD_STEP(c * SPC4 + 2 * pr, 0, 1)
+                HMMB_BWD_STEP(c * SPC4 + 2 * pr + 1, 1, 0, spp + 64)
+                HMMB_BWD_STEP(c * SPC4 + 2 * pr, 0, 1, spp)
+                spp -= 2 * 64;
             }
         }
 #undef HMMB_BWD_STEP

@@ -491,6 +491,30 @@ def run_extras(torch, lib, _lib, engine, synthetic, hbm_peak, with_cpu):
                                "fp64_tflops": fm * 45.0 / (kernel_ms * 1e-3) / 1e12,
                                "note": "45 flop per frame x model (bidiagonal N=4); issue-bound, no HBM stream to speak of"},
                     "h2d_bytes_per_step": int(obs_p.nbytes + offsets.nbytes), "d2h_bytes_per_step": int(ll_p.nbytes + 4 * U)}
+    # config 5 stress variant: 1000 left-to-right models with 16 states and 1024 codewords (k_scoreL)
+    Us, Ws, Ns, Ms, Ts = 100_000, 1000, 16, 1024, 100
+    obs, offsets, _ = synthetic.fixed_length_codewords(78, 10, Us // 10, Ts, Ns, Ms)
+    pi, A, B = engine.default_init(Ns, Ms)
+    Bs = np.empty((Ws, Ns, Ms))
+    base = rng.dirichlet(np.ones(Ms) * 0.3, size=(8, Ns))
+    for w in range(Ws):
+        Bs[w] = np.roll(base[w % 8], 7 * w, axis=1)
+    pis, As = np.tile(pi, (Ws, 1)), np.tile(A, (Ws, 1, 1))
+    obs_p = torch.empty(obs.shape, dtype=torch.int16, pin_memory=True).numpy().view(np.uint16)
+    obs_p[:] = obs
+    engine.score(obs_p[:Ts * 1000], offsets[:1001], Ns, Ms, pis, As, Bs, want_ll=False)
+    _lib.check(lib.hmmb_set_profiling(1))
+    _lib.check(lib.hmmb_phase_reset())
+    t0 = time.perf_counter()
+    engine.score(obs_p, offsets, Ns, Ms, pis, As, Bs, want_ll=False)
+    dt = time.perf_counter() - t0
+    kms, kn = _lib.phase_ms("score")
+    _lib.check(lib.hmmb_set_profiling(0))
+    fm = Us * Ts * Ws
+    out["score_n16"] = {"metric": "recognition_utterances_per_s", "value": Us / dt, "unit": "utterances/s (host API, argmax only)",
+                        "utterances": Us, "models": Ws, "N": Ns, "M": Ms, "T": Ts, "seconds": dt,
+                        "kernel": {"name": "k_scoreL<16>", "ms": kms / max(kn, 1),
+                                   "frame_models_per_s": fm / (kms / max(kn, 1) * 1e-3)}}
     return out
 
 

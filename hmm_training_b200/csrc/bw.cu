@@ -964,6 +964,17 @@ static int launch_score_special(SeqSet &s, int W, const double *d_pi, const doub
     return HMMB_OK;
 }
 
+template <int NS>
+static int launch_score_ltr(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll) {
+    if (s.ncta == 0) return HMMB_OK;
+    const size_t smem = (size_t)s.M * NS * 8 + (size_t)s.M * 8 + (size_t)s.M * 2;
+    HMMB_CUDA(cudaFuncSetAttribute(k_scoreL<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 g((unsigned)s.ncta, (unsigned)W);
+    HMMB_LAUNCH("score", k_scoreL<NS>, g, LTR_THREADS, smem, s.d_work, s.d_blks, (const uint4 *)s.d_obs, s.d_len, s.d_order,
+                d_pi, d_A, d_Bt, s.M, W, d_ll);
+    return HMMB_OK;
+}
+
 int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets, int64_t U, int W, int N, int M,
                const double *pi, const double *A, const double *B, double *ll_out, int32_t *argmax_out) {
     HMMB_TRY(require_init());
@@ -974,7 +985,13 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
         SeqSet &s; std::vector<void *> ptrs;
         ~Guard() { s.release(); for (void *p : ptrs) dev_free(p); }
     } guard{s, {}};
-    HMMB_TRY(seqset_build(s, obs, idx_bytes, obs_on_device, offsets, nullptr, U, 1, N, M, true));
+    // left-to-right models at N = 8 / 16 are scored one utterance per thread (k_scoreL)
+    bool ltr = ltr_shape_ok(N, M);
+    for (size_t e = 0; e < (size_t)W * N * N && ltr; ++e) {
+        const int ij = (int)(e % (size_t)(N * N)), i = ij / N, j = ij % N;
+        if (j != i && j != i + 1 && A[e] > 0.0) ltr = false;
+    }
+    HMMB_TRY(seqset_build(s, obs, idx_bytes, obs_on_device, offsets, nullptr, U, 1, N, M, ltr ? LAYOUT_LTR : LAYOUT_AUTO));
     if (U == 0) return HMMB_OK;
     const size_t nB = (size_t)W * N * M, nA = (size_t)W * N * N, nP = (size_t)W * N;
     double *tmp = nullptr, *d_pi = nullptr, *d_A = nullptr, *d_Bt = nullptr, *d_ll = nullptr;
@@ -1001,6 +1018,8 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
         }
         rc = bidiag ? launch_score_special<true>(s, W, d_pi, d_A, d_Bt, d_ll)
                     : launch_score_special<false>(s, W, d_pi, d_A, d_Bt, d_ll);
+    } else if (s.ltr_ns) {
+        rc = s.ltr_ns == 16 ? launch_score_ltr<16>(s, W, d_pi, d_A, d_Bt, d_ll) : launch_score_ltr<8>(s, W, d_pi, d_A, d_Bt, d_ll);
     } else {
 #define GEN(NPV)                                                                                         \
     case NPV:                                                                                            \
@@ -1018,7 +1037,7 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
         // precision guard: pairs marked NaN are recomputed in log space
         int64_t warps = std::min<int64_t>((int64_t)c.sm_count * 16, U);
         const int eg = (int)std::max<int64_t>(1, (warps + BW_WARPS - 1) / BW_WARPS);
-        if (s.special4) {
+        if (s.blocked()) {
             HMMB_LAUNCH("score_exact", (k_score_exact<uint16_t, true>), eg, BW_THREADS, 0, s.d_obs, s.d_foff, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);
         } else {
             if (s.sym_bytes == 1)

@@ -279,6 +279,24 @@ __device__ __forceinline__ void load_BtL(const double *__restrict__ Btw, int M, 
     }
 }
 
+// a_ii / a_i,i+1 of one model into registers with the largest row sum and the support masks
+template <int NS>
+__device__ __forceinline__ void load_modelL(const double *__restrict__ Aw, const double *__restrict__ piw, double (&as)[NS],
+                                            double (&an)[NS], double &rmax, unsigned &selfm, unsigned &nextm,
+                                            unsigned &pmask) {
+    rmax = 0.0;
+    selfm = nextm = pmask = 0u;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        as[i] = __ldg(Aw + i * NS + i);
+        an[i] = (i + 1 < NS) ? __ldg(Aw + i * NS + i + 1) : 0.0;
+        rmax = fmax(rmax, as[i] + an[i]);
+        selfm |= (as[i] > 0.0 ? 1u : 0u) << i;
+        nextm |= (an[i] > 0.0 ? 1u : 0u) << i;
+        pmask |= (__ldg(piw + i) > 0.0 ? 1u : 0u) << i;
+    }
+}
+
 template <int NS>
 __global__ void __launch_bounds__(LTR_THREADS, 1)
 k_bw_fwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
@@ -294,19 +312,11 @@ k_bw_fwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     if (!active[cw.word]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     load_BtL<NS, true>(Bt + (size_t)cw.word * M * NS, M, sB, sBmax, sBmask);
-    const double *Aw = A + (size_t)cw.word * NS * NS, *piw = pi + (size_t)cw.word * NS;
+    const double *piw = pi + (size_t)cw.word * NS;
     double as[NS], an[NS];
-    double rmax = 0.0;
-    unsigned selfm = 0u, nextm = 0u, pmask = 0u;
-#pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        as[i] = __ldg(Aw + i * NS + i);
-        an[i] = (i + 1 < NS) ? __ldg(Aw + i * NS + i + 1) : 0.0;
-        rmax = fmax(rmax, as[i] + an[i]);
-        selfm |= (as[i] > 0.0 ? 1u : 0u) << i;
-        nextm |= (an[i] > 0.0 ? 1u : 0u) << i;
-        pmask |= (__ldg(piw + i) > 0.0 ? 1u : 0u) << i;
-    }
+    double rmax;
+    unsigned selfm, nextm, pmask;
+    load_modelL<NS>(A + (size_t)cw.word * NS * NS, piw, as, an, rmax, selfm, nextm, pmask);
     __syncthreads();
     for (int b = cw.blk_begin + warp; b < cw.blk_end; b += LTR_WARPS) {
         const Blk bk = blks[b];
@@ -320,6 +330,39 @@ k_bw_fwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
             allfull[bk.first + lane] = af ? 1 : 0;
             if (ll != ll) flag[bk.first + lane] = 1;  // precision guard: hand over (sticky)
         }
+    }
+}
+
+// Recognition with left-to-right models (replaces calculate_log_likelihood, HMM/hmm_testing.py:49-104):
+// grid = (utterance work items, models); the CTA keeps one model's B^T in shared memory and
+// scores its 32-utterance blocks with the forward recursion above (no spill).
+template <int NS>
+__global__ void __launch_bounds__(LTR_THREADS, 1)
+k_scoreL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
+         const int32_t *__restrict__ len_sorted, const int32_t *__restrict__ order, const double *__restrict__ pi,
+         const double *__restrict__ A, const double *__restrict__ Bt, int M, int W, double *__restrict__ ll_out) {
+    using L = Ltr<NS>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *sB = reinterpret_cast<double2 *>(smem_raw);
+    double *sBmax = reinterpret_cast<double *>(sB + (size_t)M * L::CPR);
+    unsigned short *sBmask = reinterpret_cast<unsigned short *>(sBmax + M);
+    const CtaWork cw = work[blockIdx.x];
+    const int w = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    load_BtL<NS, true>(Bt + (size_t)w * M * NS, M, sB, sBmax, sBmask);
+    const double *piw = pi + (size_t)w * NS;
+    double as[NS], an[NS];
+    double rmax;
+    unsigned selfm, nextm, pmask;
+    load_modelL<NS>(A + (size_t)w * NS * NS, piw, as, an, rmax, selfm, nextm, pmask);
+    __syncthreads();
+    for (int b = cw.blk_begin + warp; b < cw.blk_end; b += LTR_WARPS) {
+        const Blk bk = blks[b];
+        const int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
+        bool af;
+        const double ll = fwdL_run<NS, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, sBmask, as, an, piw, rmax,
+                                              selfm, nextm, pmask, nullptr, af);
+        if (lane < bk.nseq) ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
     }
 }
 

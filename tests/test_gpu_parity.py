@@ -234,6 +234,40 @@ def test_scoring_matches_oracle_with_structural_zeros(N, M):
     assert allbad[1][0] == -1 and np.isneginf(allbad[0]).all()  # "unknown" (hmm_testing.py:161)
 
 
+@pytest.mark.parametrize("N,M,kind", [(16, 1024, "random"), (16, 200, "zeros"), (8, 64, "random"), (8, 300, "zeros")])
+def test_scoring_left_to_right_kernels(N, M, kind, monkeypatch):
+    """Recognition with upper-bidiagonal models at N = 8 / 16 runs k_scoreL (one utterance per
+    thread); checked against the oracle and against the generic lanes-per-state scorer."""
+    rng = np.random.default_rng(3 * N + M)
+    W, U = 5, 150
+    pi, A, B = _ltr_init(rng, W, N, M, kind)
+    seqs = [rng.integers(0, M, size=int(rng.integers(1, 90))) for _ in range(U)]
+    seqs += synthetic.clustered_sequences(rng, 40, N=N, M=M, tmin=20, tmax=60, spread=max(2, M // (2 * N)))
+    if kind == "zeros":
+        seqs[3] = np.zeros(25, np.int64)  # symbol 0 is emitted by every state: finite under every model
+    obs, offsets = np.concatenate(seqs), np.concatenate([[0], np.cumsum([len(q) for q in seqs])])
+    dt = np.uint8 if M <= 256 else np.uint16
+    monkeypatch.delenv("HMMB_NO_LTR", raising=False)
+    ll, arg = engine.score(obs.astype(dt), offsets, N, M, pi, A, B)
+    ref = O.score_batch(seqs, [(A[w], B[w], pi[w]) for w in range(W)])
+    assert_close(ll, ref, "ltr score")
+    assert np.array_equal(np.isneginf(ll), np.isneginf(ref))
+    # the all-zeros utterance scores 25*log(1e-3) under EVERY model (rows of A sum to 1): an exact tie
+    # on paper, decided by the last bit — compare the winner only where the runner-up is clearly behind
+    top = np.sort(ref, axis=1)[:, ::-1]
+    with np.errstate(invalid="ignore"):
+        clear = ~(np.abs(top[:, 0] - top[:, 1]) <= 1e-7 * np.abs(top[:, 0]))
+    assert clear.sum() >= len(seqs) - 8
+    assert np.array_equal(arg[clear], O.argmax_first(ref)[clear])
+    assert np.array_equal(arg, O.argmax_first(ll))  # and always the first maximum of our own scores
+    if kind == "zeros":
+        assert np.isneginf(ref).sum() > U and np.isfinite(ref[3]).all()
+    monkeypatch.setenv("HMMB_NO_LTR", "1")
+    llg, argg = engine.score(obs.astype(dt), offsets, N, M, pi, A, B)
+    assert_close(ll, llg, "ltr vs generic score")
+    assert np.array_equal(arg[clear], argg[clear])
+
+
 def _tiny_models(rng, W, N, M):
     """Left-to-right models whose emission rows hold denormal / 1e-300-range / zero entries:
     what saved reference models look like after safe_exp underflow (hmm_training.py:524-526)."""

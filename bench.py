@@ -206,7 +206,7 @@ def cpu_baum_welch(cfg, seq_per_word: int, iters: int, procs: int):
     return frames * iters / dt, dt, f"{W} words x {seq_per_word} seq x T={T} (N={N}, M={M}), {iters} EM iterations"
 
 
-def run_reference(args, cfg):
+def run_reference(args, cfg, real_stdout):
     """--impl reference: the reference's algorithm on the host cores.  The reference itself is
     pure Python and only exists in the build container, so this arm times oracle/ (the
     validated numpy port, kind="port") with every host core, on the same workload shape."""
@@ -232,11 +232,27 @@ def run_reference(args, cfg):
         "cpu_baseline": {"value": value, "unit": "frames/s/iter", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "frames/s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(real_stdout, line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    line to stdout on this image), so file descriptor 1 is pointed at stderr for the whole run and
+    the JSON line goes to the saved original descriptor."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_fd: int, line: dict) -> None:
+    sys.stdout.flush()
+    os.write(real_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -249,7 +265,7 @@ def main():
     cfg = dict(WORKLOADS[args.workload])
     cfg["S"] = max(1, int(round(cfg["S"] * args.scale)))
     if args.impl == "reference":
-        run_reference(args, cfg)
+        run_reference(args, cfg, real_stdout)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -394,7 +410,7 @@ def main():
                                                          "backward_handovers": bwd_handover},
         }
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        _emit(real_stdout, line)
     # orderly teardown: free device memory and the library's events before NCCL goes away
     torch.cuda.synchronize()
     lib.hmmb_set_stream(None)

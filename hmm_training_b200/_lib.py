@@ -44,6 +44,9 @@ SYMBOLS = [
                                 _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     ("hmmb_bw_create", _c.c_int, [_c.POINTER(_c.c_void_p), _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                   _c.c_int64, _c.c_int, _c.c_int, _c.c_int]),
+    ("hmmb_bw_create_ex", _c.c_int, [_c.POINTER(_c.c_void_p), _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                     _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                     _c.c_void_p]),
     ("hmmb_bw_destroy", _c.c_int, [_c.c_void_p]),
     ("hmmb_bw_set_params", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     ("hmmb_bw_set_dist", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),

@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <functional>
+#include <memory>
 #include <numeric>
 
 #include "bw_kernels.cuh"
@@ -146,6 +148,53 @@ k_score_exact(const void *__restrict__ obs, const int64_t *__restrict__ base_sor
     }
 }
 
+// Raw codewords of a pinned host buffer are uploaded on the copy stream in a few chunks, started
+// before the host-side sorting / blocking so that PCIe time hides it; when the input is already in
+// sorted order a chunk's blocks are repacked as soon as the chunk has landed.
+struct EarlyUpload {
+    static constexpr int MAX_CHUNKS = 8;
+    void *d_raw = nullptr;
+    const char *src = nullptr;
+    int nchunk = 0;                 // planned chunks
+    int issued = 0;                 // chunks already queued on the copy stream
+    size_t hi[MAX_CHUNKS] = {};     // end byte of each chunk
+    cudaEvent_t ev[MAX_CHUNKS] = {};
+    cudaEvent_t t0 = nullptr;       // HMMB_TIMING: start of the upload (copy stream)
+    bool active() const { return nchunk > 0; }
+    // queue chunks [issued, upto) on the copy stream.  The first half goes out before the host-side
+    // sorting / blocking (PCIe works while the host does), the second half only after the (small)
+    // per-sequence metadata has been queued: copies of different streams share one DMA queue, and the
+    // metadata must not wait behind the whole codeword stream.
+    int issue(int upto) {
+        Ctx &c = ctx();
+        for (int k = issued; k < upto && k < nchunk; ++k) {
+            const size_t lo = k == 0 ? 0 : hi[k - 1];
+            HMMB_CUDA(cudaMemcpyAsync((char *)d_raw + lo, src + lo, hi[k] - lo, cudaMemcpyHostToDevice, c.copy_stream));
+            HMMB_CUDA(cudaEventRecord(ev[k], c.copy_stream));
+            issued = k + 1;
+        }
+        return HMMB_OK;
+    }
+    ~EarlyUpload() {
+        if (nchunk > 0) cudaStreamSynchronize(ctx().copy_stream);
+        for (int k = 0; k < nchunk; ++k) event_put(ev[k]);
+        dev_free(d_raw);
+    }
+};
+
+// Deferred prepare: the trainer may leave the repack of the uploaded chunks to its first E-step,
+// which then runs stage by stage (repack -> forward -> backward of the CTAs whose codewords have
+// landed) while the later chunks are still crossing PCIe.
+struct PendingPrepare {
+    static constexpr int MAX_STAGES = 2;  // = the two halves of the upload: a stage still fills every SM
+    std::unique_ptr<EarlyUpload> up;
+    int idx_bytes = 1;
+    int nstage = 0;
+    int ev_index[MAX_STAGES] = {};   // upload chunk whose event completes the stage
+    int blk_end[MAX_STAGES] = {};    // blocks [.., blk_end) have all their codewords on the device after the stage
+    int cta_end[MAX_STAGES] = {};    // CTA work items [.., cta_end) only touch those blocks
+};
+
 // ---------------------------------------------------------------- sequence set (shared by BW and scoring)
 struct SeqSet {
     int64_t R = 0, frames = 0;
@@ -166,30 +215,63 @@ struct SeqSet {
     int32_t *d_len = nullptr, *d_word = nullptr, *d_order = nullptr;
     Blk *d_blks = nullptr;
     CtaWork *d_work = nullptr;
+    int *d_bad = nullptr;                  // device flag: a codeword >= M was seen by the repack / convert kernels
+    std::unique_ptr<PendingPrepare> pend;  // non-null while the repack is left to the first E-step
     void release() {
+        pend.reset();  // waits for the copy stream before the raw buffer goes back to the allocator
+        dev_free(d_bad);
+        d_bad = nullptr;
         dev_free(d_obs); dev_free(d_meta); dev_free(d_blks); dev_free(d_work);
         d_obs = d_meta = nullptr; d_off = d_foff = nullptr; d_len = d_word = d_order = nullptr; d_blks = nullptr; d_work = nullptr;
     }
 };
 
+// Small host-to-device copies of a build.  While a codeword upload is in flight on the copy stream they go
+// through that stream as well — one DMA queue, so they keep their place between the two halves of the upload
+// instead of being served after it (copies of different streams are not served in issue order) — and
+// h2d_join() orders the compute stream behind them.
+static int h2d_small(void *dst, const void *src, size_t bytes) {
+    Ctx &c = ctx();
+    HMMB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.h2d_on_copy ? c.copy_stream : c.stream));
+    return HMMB_OK;
+}
+static int h2d_join() {
+    Ctx &c = ctx();
+    if (!c.h2d_on_copy) return HMMB_OK;
+    cudaEvent_t e = event_get();
+    HMMB_CUDA(cudaEventRecord(e, c.copy_stream));
+    HMMB_CUDA(cudaStreamWaitEvent(c.stream, e, 0));
+    event_put(e);
+    return HMMB_OK;
+}
+
 static int pick_np(int N) { return N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : 32)); }
 
-// Raw codewords of a pinned host buffer are uploaded on the copy stream in a few chunks, started
-// before the host-side sorting / blocking so that PCIe time hides it; when the input is already in
-// sorted order a chunk's blocks are repacked as soon as the chunk has landed.
-struct EarlyUpload {
-    static constexpr int MAX_CHUNKS = 8;
-    void *d_raw = nullptr;
-    int nchunk = 0;
-    size_t hi[MAX_CHUNKS] = {};     // end byte of each chunk
-    cudaEvent_t ev[MAX_CHUNKS] = {};
-    bool active() const { return nchunk > 0; }
-    ~EarlyUpload() {
-        if (nchunk > 0) cudaStreamSynchronize(ctx().copy_stream);
-        for (int k = 0; k < nchunk; ++k) event_put(ev[k]);
-        dev_free(d_raw);
+// repack blocks [b0, b1) of the blocked layouts from the raw codewords (any input width)
+static int launch_repack_range(SeqSet &s, const void *d_in, int idx_bytes, int b0, int b1, int *d_bad) {
+    if (b1 <= b0) return HMMB_OK;
+    switch (idx_bytes) {
+        case 1: HMMB_LAUNCH("prepare", k_repack_blocks4<uint8_t>, b1 - b0, REPACK_WARPS * 32, 0, (const uint8_t *)d_in, s.d_off, s.d_len, s.d_blks, b0, s.nblk, (uint4 *)s.d_obs, s.M, d_bad); break;
+        case 2: HMMB_LAUNCH("prepare", k_repack_blocks4<uint16_t>, b1 - b0, REPACK_WARPS * 32, 0, (const uint16_t *)d_in, s.d_off, s.d_len, s.d_blks, b0, s.nblk, (uint4 *)s.d_obs, s.M, d_bad); break;
+        case 4: HMMB_LAUNCH("prepare", k_repack_blocks4<uint32_t>, b1 - b0, REPACK_WARPS * 32, 0, (const uint32_t *)d_in, s.d_off, s.d_len, s.d_blks, b0, s.nblk, (uint4 *)s.d_obs, s.M, d_bad); break;
+        default: HMMB_LAUNCH("prepare", k_repack_blocks4<unsigned long long>, b1 - b0, REPACK_WARPS * 32, 0, (const unsigned long long *)d_in, s.d_off, s.d_len, s.d_blks, b0, s.nblk, (uint4 *)s.d_obs, s.M, d_bad); break;
     }
-};
+    return HMMB_OK;
+}
+
+// first block whose codewords are not completely inside the first `hi_bytes` bytes of the raw stream
+// (input already in sorted order: block order = raw order)
+static int blocks_within(const std::vector<Blk> &blks, int from, const int64_t *off_s, const int32_t *len_s, int idx_bytes,
+                         size_t hi_bytes) {
+    int end = from;
+    while (end < (int)blks.size()) {
+        const Blk &b = blks[end];
+        const int64_t last = (int64_t)b.first + b.nseq - 1;
+        if ((size_t)(off_s[last] + len_s[last]) * (size_t)idx_bytes > hi_bytes) break;
+        ++end;
+    }
+    return end;
+}
 
 template <typename InT>
 static int launch_prepare(SeqSet &s, const InT *d_in, int64_t nsym, int *d_bad, const std::vector<Blk> &blks,
@@ -199,17 +281,7 @@ static int launch_prepare(SeqSet &s, const InT *d_in, int64_t nsym, int *d_bad, 
         int done = 0;
         if (up.active() && in_sorted_order) {
             for (int k = 0; k < up.nchunk; ++k) {
-                int end = done;
-                if (k == up.nchunk - 1) {
-                    end = s.nblk;
-                } else {
-                    while (end < s.nblk) {
-                        const Blk &b = blks[end];
-                        const int64_t last = (int64_t)b.first + b.nseq - 1;
-                        if ((size_t)(off_s[last] + len_s[last]) * sizeof(InT) > up.hi[k]) break;
-                        ++end;
-                    }
-                }
+                const int end = k == up.nchunk - 1 ? s.nblk : blocks_within(blks, done, off_s, len_s, (int)sizeof(InT), up.hi[k]);
                 HMMB_CUDA(cudaStreamWaitEvent(c.stream, up.ev[k], 0));
                 if (end > done)
                     HMMB_LAUNCH("prepare", k_repack_blocks4<InT>, end - done, 256, 0, d_in, s.d_off, s.d_len, s.d_blks, done,
@@ -252,7 +324,8 @@ static bool ltr_shape_ok(int N, int M) {
 }
 
 static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets,
-                        const int32_t *word_of_seq, int64_t R, int W, int N, int M, int layout) {
+                        const int32_t *word_of_seq, int64_t R, int W, int N, int M, int layout, bool defer = false,
+                        const std::function<int()> *mid_hook = nullptr) {
     Ctx &c = ctx();
     const bool timing = getenv("HMMB_TIMING") != nullptr;
     const double t0 = now_ms();
@@ -265,7 +338,9 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     s.special4 = layout == LAYOUT_AUTO && N == 4 && M <= BW4_MAX_M && !getenv("HMMB_FORCE_GENERIC");
     s.ltr_ns = (layout == LAYOUT_LTR) ? N : 0;
 
-    EarlyUpload up;
+    std::unique_ptr<EarlyUpload> up_owner(new EarlyUpload());
+    EarlyUpload &up = *up_owner;
+    struct H2dGuard { ~H2dGuard() { ctx().h2d_on_copy = false; } } h2d_guard;
     if (!obs_on_device && R > 0 && offsets[R] > offsets[0] && offsets[R] - offsets[0] < (int64_t(1) << 40)) {
         const char *src = (const char *)obs + (size_t)offsets[0] * idx_bytes;
         const size_t in_bytes = (size_t)(offsets[R] - offsets[0]) * idx_bytes;
@@ -280,15 +355,18 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
             HMMB_CUDA(cudaStreamWaitEvent(c.copy_stream, fence, 0));
             event_put(fence);
             const int nchunk = (int)std::min<size_t>(EarlyUpload::MAX_CHUNKS, std::max<size_t>(1, in_bytes >> 24));
-            for (int k = 0; k < nchunk; ++k) {
-                const size_t lo = k == 0 ? 0 : up.hi[k - 1];
-                const size_t hi = k == nchunk - 1 ? in_bytes : ((in_bytes / nchunk) * (k + 1)) & ~size_t(255);
-                HMMB_CUDA(cudaMemcpyAsync((char *)up.d_raw + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, c.copy_stream));
-                up.ev[k] = event_get();
-                up.hi[k] = hi;
-                up.nchunk = k + 1;
-                HMMB_CUDA(cudaEventRecord(up.ev[k], c.copy_stream));
+            up.src = src;
+            if (timing) {
+                cudaEventCreate(&up.t0);
+                cudaEventRecord(up.t0, c.copy_stream);
             }
+            for (int k = 0; k < nchunk; ++k) {
+                up.hi[k] = k == nchunk - 1 ? in_bytes : ((in_bytes / nchunk) * (k + 1)) & ~size_t(255);
+                up.ev[k] = event_get();
+                up.nchunk = k + 1;
+            }
+            HMMB_TRY(up.issue((nchunk + 1) / 2));
+            c.h2d_on_copy = true;
         }
     }
 
@@ -296,6 +374,11 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     // to the device with a single copy: [off int64 | foff int64 | len int32 | word int32 | order int32].
     const size_t nR = (size_t)std::max<int64_t>(R, 1);
     const size_t meta_bytes = nR * (2 * sizeof(int64_t) + 3 * sizeof(int32_t));
+    if (c.stage_busy) {  // the previous build's metadata copy (possibly still queued behind a codeword upload)
+        cudaEventSynchronize(c.stage_busy);
+        event_put(c.stage_busy);
+        c.stage_busy = nullptr;
+    }
     if (c.stage_bytes < meta_bytes) {
         if (c.stage) cudaFreeHost(c.stage);
         c.stage = nullptr;
@@ -438,18 +521,28 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     s.d_len = reinterpret_cast<int32_t *>(s.d_foff + nR);
     s.d_word = s.d_len + nR;
     s.d_order = s.d_word + nR;
-    if (R > 0) HMMB_CUDA(cudaMemcpyAsync(s.d_meta, c.stage, meta_bytes, cudaMemcpyHostToDevice, c.stream));
+    if (R > 0) {
+        HMMB_TRY(h2d_small(s.d_meta, c.stage, meta_bytes));
+        c.stage_busy = event_get();
+        HMMB_CUDA(cudaEventRecord(c.stage_busy, c.h2d_on_copy ? c.copy_stream : c.stream));
+    }
     if (s.blocked()) {
         HMMB_TRY(dev_alloc_t(&s.d_blks, std::max<size_t>(blks.size(), 1)));
         HMMB_TRY(dev_alloc_t(&s.d_work, std::max<size_t>(work.size(), 1)));
         if (!blks.empty()) {
-            HMMB_CUDA(cudaMemcpyAsync(s.d_blks, blks.data(), blks.size() * sizeof(Blk), cudaMemcpyHostToDevice, c.stream));
-            HMMB_CUDA(cudaMemcpyAsync(s.d_work, work.data(), work.size() * sizeof(CtaWork), cudaMemcpyHostToDevice, c.stream));
+            HMMB_TRY(h2d_small(s.d_blks, blks.data(), blks.size() * sizeof(Blk)));
+            HMMB_TRY(h2d_small(s.d_work, work.data(), work.size() * sizeof(CtaWork)));
         }
         HMMB_TRY(dev_alloc(&s.d_obs, (size_t)std::max<int64_t>(obs_rows, 1) * sizeof(uint4)));
     } else {
         HMMB_TRY(dev_alloc(&s.d_obs, (size_t)std::max<int64_t>(s.frames, 1) * s.sym_bytes));
     }
+    // the caller's own small uploads (accumulator layout, initial parameters) also go ahead of the
+    // second half of the codewords in the DMA queue
+    if (mid_hook) HMMB_TRY((*mid_hook)());
+    HMMB_TRY(h2d_join());
+    c.h2d_on_copy = false;
+    if (up.active()) HMMB_TRY(up.issue(up.nchunk));  // second half of the codewords, behind the metadata
     // raw codewords -> device (if needed) -> canonical layout
     const void *d_in = obs;
     void *d_tmp = nullptr;
@@ -466,9 +559,30 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
             d_in = src;
         }
     }
-    int *d_bad = nullptr;
-    HMMB_TRY(dev_alloc_t(&d_bad, 1));
+    HMMB_TRY(dev_alloc_t(&s.d_bad, 1));
+    int *d_bad = s.d_bad;
     HMMB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), c.stream));
+    if (defer && s.special4 && up.active() && !unsorted && s.nblk > 0) {
+        // leave the repack to the first E-step (bw_estep): record which blocks / CTA work items each stage completes
+        std::unique_ptr<PendingPrepare> p(new PendingPrepare());
+        p->idx_bytes = idx_bytes;
+        p->nstage = std::min<int>(PendingPrepare::MAX_STAGES, up.nchunk);
+        int bdone = 0, cdone = 0;
+        for (int j = 0; j < p->nstage; ++j) {
+            const int k = (p->nstage == 2 && j == 0) ? (up.nchunk + 1) / 2 - 1 : up.nchunk - 1;
+            p->ev_index[j] = k;
+            bdone = (j == p->nstage - 1) ? s.nblk : blocks_within(blks, bdone, off_s, len_s, idx_bytes, up.hi[k]);
+            while (cdone < s.ncta && work[cdone].blk_end <= bdone) ++cdone;
+            p->blk_end[j] = bdone;
+            p->cta_end[j] = (j == p->nstage - 1) ? s.ncta : cdone;
+        }
+        p->up = std::move(up_owner);
+        s.pend = std::move(p);
+        if (timing)
+            fprintf(stderr, "[hmmb] seqset_build: host sort/blocking %.2f ms, deferred prepare in %d stages (R=%lld, frames=%lld)\n",
+                    t1 - t0, s.pend->nstage, (long long)R, (long long)s.frames);
+        return HMMB_OK;
+    }
     int rc = HMMB_OK;
     if (R > 0) {
         switch (idx_bytes) {
@@ -485,7 +599,6 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         if (e != cudaSuccess) rc = cuda_fail(e, "prepare sync", __FILE__, __LINE__);
     }
     dev_free(d_tmp);
-    dev_free(d_bad);
     if (timing)
         fprintf(stderr, "[hmmb] seqset_build: host sort/blocking %.2f ms, upload + repack %.2f ms (R=%lld, frames=%lld)\n",
                 t1 - t0, now_ms() - t1, (long long)R, (long long)s.frames);
@@ -507,7 +620,9 @@ struct hmmb_bw {
     SeqSet sl;                    // N = 8 / 16: additional blocked layout for the left-to-right kernels
     bool has_ltr = false;         // sl was built
     bool use_ltr = false;         // every word's A is upper-bidiagonal (checked in set_params): run the sl kernels
-    uint8_t *d_allfull = nullptr; // per sequence: every spilled alpha-hat > 0 (written by k_bw_fwdL)
+    uint8_t *d_allfull = nullptr; // per sequence: every spilled alpha-hat > 0 (written by the forward kernels)
+    bool check_bad = false;       // pipelined prepare: the codeword-range flag has not been read back yet
+    std::unique_ptr<PendingPrepare> pend_release;  // consumed by the E-step; freed after the next stream sync
     void *d_raw = nullptr;        // raw codewords uploaded once when both layouts are built
     SeqSet &cur() { return use_ltr ? sl : s; }
     int W = 0, N = 0, M = 0;
@@ -535,6 +650,7 @@ struct hmmb_bw {
 };
 
 static void bw_release(hmmb_bw *h) {
+    h->pend_release.reset();
     h->s.release();
     h->sl.release();
     dev_free(h->d_allfull);
@@ -552,47 +668,20 @@ static int bw_alloc_accum(hmmb_bw *h) {
     return dev_alloc_t(&h->d_accum, (size_t)h->accum_n);
 }
 
-// (C linkage comes from the declarations in include/hmmb200.h)
+static int bw_set_params_impl(hmmb_bw *h, const double *pi0, const double *A0, const double *B0, bool sync);
 
-int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets,
-                   const int32_t *word_of_seq, int64_t R, int W, int N, int M) {
-    HMMB_TRY(require_init());
-    if (!out || !word_of_seq) { set_error("hmmb_bw_create: null argument"); return HMMB_ERR_ARG; }
-    *out = nullptr;
+// Buffers sized by the sequence set, accumulator layout, the small per-word uploads (second half of hmmb_bw_create).
+static int bw_finish_create(hmmb_bw *h, int64_t R) {
     Ctx &c = ctx();
-    hmmb_bw *h = new hmmb_bw();
-    h->W = W; h->N = N; h->M = M;
-    auto fail = [&](int code) { bw_release(h); delete h; return code; };
-    int rc;
-    h->has_ltr = ltr_shape_ok(N, M);
-    if (h->has_ltr && !obs_on_device && R > 0 && offsets && obs && offsets[R] > offsets[0]) {
-        // both layouts are built from the codewords: upload them once
-        const size_t in_bytes = (size_t)(offsets[R] - offsets[0]) * idx_bytes;
-        rc = dev_alloc(&h->d_raw, in_bytes);
-        if (rc != HMMB_OK) return fail(rc);
-        cudaError_t e = cudaMemcpyAsync(h->d_raw, (const char *)obs + (size_t)offsets[0] * idx_bytes, in_bytes,
-                                        cudaMemcpyHostToDevice, c.stream);
-        if (e != cudaSuccess) return fail(cuda_fail(e, "codeword upload", __FILE__, __LINE__));
-        // seqset_build indexes a device stream from offsets[0]
-        obs = (const char *)h->d_raw - (size_t)offsets[0] * idx_bytes;
-        obs_on_device = 1;
-    }
-    rc = seqset_build(h->s, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_AUTO);
-    if (rc != HMMB_OK) return fail(rc);
-    if (h->has_ltr) {
-        rc = seqset_build(h->sl, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_LTR);
-        if (rc != HMMB_OK) return fail(rc);
-        dev_free(h->d_raw);
-        h->d_raw = nullptr;
-    }
     SeqSet &s = h->s;
+    const int W = h->W, N = h->N, M = h->M;
     h->nacc = (int64_t)N + (int64_t)N * N + (int64_t)M * N;
     // stride multiple of 16 doubles: every word's count rows start on a 128-byte line (TMA bulk reductions)
     h->astride = (h->nacc + 1 + 15) & ~int64_t(15);
     h->pstride = h->nacc + 2;  // + the CTA's (max, sum exp) pair of the convergence statistic
     h->hist_cap = 0;
-#define TRYF(expr) do { int _r = (expr); if (_r != HMMB_OK) return fail(_r); } while (0)
-#define CUDAF(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(cuda_fail(_e, #expr, __FILE__, __LINE__)); } while (0)
+#define TRYF(expr) HMMB_TRY(expr)
+#define CUDAF(expr) HMMB_CUDA(expr)
     TRYF(dev_alloc_t(&h->d_pi, (size_t)W * N));
     TRYF(dev_alloc_t(&h->d_A, (size_t)W * N * N));
     TRYF(dev_alloc_t(&h->d_Bt, (size_t)W * M * N));
@@ -615,14 +704,14 @@ int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_d
         TRYF(dev_alloc_t(&h->d_exact_scratch, (size_t)h->exact_grid * BW_WARPS * h->exact_stride));
     }
     TRYF(dev_alloc_t(&h->d_seq_begin, (size_t)W + 1));
-    CUDAF(cudaMemcpyAsync(h->d_seq_begin, s.seq_begin.data(), (W + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream));
+    TRYF(h2d_small(h->d_seq_begin, s.seq_begin.data(), (W + 1) * sizeof(int64_t)));
     size_t spill_bytes;
     if (s.special4) {
         spill_bytes = (size_t)std::max<int64_t>(s.spill_steps, 1) * 64 * sizeof(double2);
         TRYF(dev_alloc_t(&h->d_partials, (size_t)std::max(s.ncta, 1) * h->pstride));
         TRYF(dev_alloc_t(&h->d_cta_begin, (size_t)W + 1));
         TRYF(dev_alloc_t(&h->d_allfull, (size_t)std::max<int64_t>(R, 1)));
-        CUDAF(cudaMemcpyAsync(h->d_cta_begin, s.cta_begin.data(), (W + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c.stream));
+        TRYF(h2d_small(h->d_cta_begin, s.cta_begin.data(), (W + 1) * sizeof(int32_t)));
     } else {
         spill_bytes = (size_t)std::max<int64_t>(s.frames, 1) * N * sizeof(double);
         if (h->has_ltr) {
@@ -630,15 +719,80 @@ int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_d
             TRYF(dev_alloc_t(&h->d_allfull, (size_t)std::max<int64_t>(R, 1)));
         }
     }
-    rc = dev_alloc((void **)&h->d_spill, spill_bytes);
+    int rc = dev_alloc((void **)&h->d_spill, spill_bytes);
     if (rc != HMMB_OK) {
         set_error("alpha spill of %.2f GB does not fit in device memory; shard the sequences over more GPUs",
                   spill_bytes / 1e9);
-        return fail(HMMB_ERR_OOM);
+        return HMMB_ERR_OOM;
     }
-    CUDAF(cudaStreamSynchronize(c.stream));  // host staging vectors in seqset_build are gone after this point
 #undef TRYF
 #undef CUDAF
+    return HMMB_OK;
+}
+
+
+// (C linkage comes from the declarations in include/hmmb200.h)
+
+int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets,
+                   const int32_t *word_of_seq, int64_t R, int W, int N, int M) {
+    return hmmb_bw_create_ex(out, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, 0, nullptr, nullptr,
+                             nullptr);
+}
+
+int hmmb_bw_create_ex(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets,
+                      const int32_t *word_of_seq, int64_t R, int W, int N, int M, int flags, const double *pi0,
+                      const double *A0, const double *B0) {
+    HMMB_TRY(require_init());
+    if (!out || !word_of_seq) { set_error("hmmb_bw_create: null argument"); return HMMB_ERR_ARG; }
+    *out = nullptr;
+    Ctx &c = ctx();
+    hmmb_bw *h = new hmmb_bw();
+    h->W = W; h->N = N; h->M = M;
+    auto fail = [&](int code) { bw_release(h); delete h; return code; };
+    int rc;
+    h->has_ltr = ltr_shape_ok(N, M);
+    if (h->has_ltr && !obs_on_device && R > 0 && offsets && obs && offsets[R] > offsets[0]) {
+        // both layouts are built from the codewords: upload them once
+        const size_t in_bytes = (size_t)(offsets[R] - offsets[0]) * idx_bytes;
+        rc = dev_alloc(&h->d_raw, in_bytes);
+        if (rc != HMMB_OK) return fail(rc);
+        cudaError_t e = cudaMemcpyAsync(h->d_raw, (const char *)obs + (size_t)offsets[0] * idx_bytes, in_bytes,
+                                        cudaMemcpyHostToDevice, c.stream);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "codeword upload", __FILE__, __LINE__));
+        // seqset_build indexes a device stream from offsets[0]
+        obs = (const char *)h->d_raw - (size_t)offsets[0] * idx_bytes;
+        obs_on_device = 1;
+    }
+    const bool have_params = pi0 && A0 && B0;
+    // everything that follows the sequence set (buffers sized by it, the small uploads, optionally the
+    // initial parameters).  In a pipelined create it runs INSIDE seqset_build, between the metadata and the
+    // second half of the codeword upload, so that none of it waits behind that upload.
+    bool finished = false;
+    std::function<int()> finish = [&]() -> int {
+        finished = true;
+        HMMB_TRY(bw_finish_create(h, R));
+        if (have_params) HMMB_TRY(bw_set_params_impl(h, pi0, A0, B0, false));
+        return HMMB_OK;
+    };
+    const bool pipeline = (flags & HMMB_BW_PIPELINE_UPLOAD) != 0 && !h->has_ltr;
+    rc = seqset_build(h->s, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_AUTO, pipeline,
+                      pipeline ? &finish : nullptr);
+    if (rc != HMMB_OK) return fail(rc);
+    if (h->has_ltr) {
+        rc = seqset_build(h->sl, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_LTR);
+        if (rc != HMMB_OK) return fail(rc);
+        dev_free(h->d_raw);
+        h->d_raw = nullptr;
+    }
+    if (!finished) {
+        rc = finish();
+        if (rc != HMMB_OK) return fail(rc);
+    }
+    if (!h->s.pend) {
+        // (a pipelined create returns with its uploads in flight; otherwise everything is on the device now)
+        cudaError_t e = cudaStreamSynchronize(c.stream);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "create sync", __FILE__, __LINE__));
+    }
     *out = h;
     return HMMB_OK;
 }
@@ -660,17 +814,46 @@ const char *hmmb_bw_kernel_family(hmmb_bw_t *h) {
     return "generic";
 }
 
-int hmmb_bw_set_params(hmmb_bw_t *h, const double *pi0, const double *A0, const double *B0) {
-    HMMB_TRY(require_init());
-    if (!h || !pi0 || !A0 || !B0) { set_error("hmmb_bw_set_params: null argument"); return HMMB_ERR_ARG; }
+// sync == false (pipelined create): the parameters go through a pinned staging buffer so that the call
+// neither blocks nor waits behind the codeword upload; everything stays ordered on the compute stream.
+static int bw_set_params_impl(hmmb_bw *h, const double *pi0, const double *A0, const double *B0, bool sync) {
     Ctx &c = ctx();
     const int W = h->W, N = h->N, M = h->M;
     double *tmp = nullptr;
     const size_t nB = (size_t)W * N * M, nA = (size_t)W * N * N, nP = (size_t)W * N;
     HMMB_TRY(dev_alloc_t(&tmp, nB + nA + nP));
-    HMMB_CUDA(cudaMemcpyAsync(tmp, B0, nB * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    HMMB_CUDA(cudaMemcpyAsync(tmp + nB, A0, nA * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    HMMB_CUDA(cudaMemcpyAsync(tmp + nB + nA, pi0, nP * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    if (sync) {
+        HMMB_CUDA(cudaMemcpyAsync(tmp, B0, nB * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        HMMB_CUDA(cudaMemcpyAsync(tmp + nB, A0, nA * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        HMMB_CUDA(cudaMemcpyAsync(tmp + nB + nA, pi0, nP * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    } else {
+        const size_t bytes = (nB + nA + nP) * sizeof(double);
+        if (c.pstage_busy) {
+            cudaEventSynchronize(c.pstage_busy);
+            event_put(c.pstage_busy);
+            c.pstage_busy = nullptr;
+        }
+        if (c.pstage_bytes < bytes) {
+            if (c.pstage) cudaFreeHost(c.pstage);
+            c.pstage = nullptr;
+            c.pstage_bytes = 0;
+            if (cudaHostAlloc(&c.pstage, bytes, cudaHostAllocDefault) != cudaSuccess) {
+                (void)cudaGetLastError();
+                set_error("pinned staging allocation of %zu bytes failed", bytes);
+                dev_free(tmp);
+                return HMMB_ERR_OOM;
+            }
+            c.pstage_bytes = bytes;
+        }
+        double *ps = static_cast<double *>(c.pstage);
+        memcpy(ps, B0, nB * sizeof(double));
+        memcpy(ps + nB, A0, nA * sizeof(double));
+        memcpy(ps + nB + nA, pi0, nP * sizeof(double));
+        HMMB_TRY(h2d_small(tmp, ps, bytes));
+        c.pstage_busy = event_get();
+        HMMB_CUDA(cudaEventRecord(c.pstage_busy, c.h2d_on_copy ? c.copy_stream : c.stream));
+        HMMB_TRY(h2d_join());  // the kernels below read tmp
+    }
     dim3 gb((unsigned)std::min((N * M + 255) / 256, 64), (unsigned)W);
     HMMB_CUDA(cudaMemsetAsync(h->d_bzero, 0, (size_t)W * sizeof(int32_t), c.stream));
     HMMB_LAUNCH("bw_load", k_load_B, gb, 256, 0, tmp, N, M, h->d_Bt, h->d_bzero);
@@ -700,11 +883,17 @@ int hmmb_bw_set_params(hmmb_bw_t *h, const double *pi0, const double *A0, const 
     HMMB_CUDA(cudaMemsetAsync(h->d_newflags, 0, sizeof(int32_t), c.stream));
     HMMB_CUDA(cudaMemsetAsync(h->d_nexact, 0, sizeof(int64_t), c.stream));
     h->n_backward_handover = 0;
-    HMMB_CUDA(cudaStreamSynchronize(c.stream));
-    dev_free(tmp);
+    if (sync) HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    dev_free(tmp);  // stream-ordered reuse: later users of the block are queued behind the kernels above
     h->params_set = true;
     h->any_active = true;
     return HMMB_OK;
+}
+
+int hmmb_bw_set_params(hmmb_bw_t *h, const double *pi0, const double *A0, const double *B0) {
+    HMMB_TRY(require_init());
+    if (!h || !pi0 || !A0 || !B0) { set_error("hmmb_bw_set_params: null argument"); return HMMB_ERR_ARG; }
+    return bw_set_params_impl(h, pi0, A0, B0, true);
 }
 
 int hmmb_bw_set_dist(hmmb_bw_t *h, int rank, int world, hmmb_allreduce_fn allreduce, void *user) {
@@ -764,11 +953,62 @@ static int launch_generic_estep(hmmb_bw *h) {
 
 template <bool BIDIAG>
 static int launch_special_estep(hmmb_bw *h) {
+    Ctx &c = ctx();
     SeqSet &s = h->s;
-    if (s.ncta == 0) return HMMB_OK;
+    if (s.ncta == 0) { s.pend.reset(); return HMMB_OK; }
     const size_t smem_f = (size_t)h->M * 5 * sizeof(double) + (size_t)((h->M + 15) & ~15);
     const size_t smem_b = (size_t)h->M * 4 * sizeof(double) * (1 + BW_WARPS) + (size_t)BW_THREADS * 4 * sizeof(double);
     HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwd4<BIDIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    // forward + backward of the CTA work items [c0, c1)
+    auto launch_range = [&](int c0, int c1) -> int {
+        if (c1 <= c0) return HMMB_OK;
+        HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, c1 - c0, BW_THREADS, smem_f, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
+                    s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag,
+                    h->d_allfull);
+        HMMB_LAUNCH("bw_backward", k_bw_bwd4<BIDIAG>, c1 - c0, BW_THREADS, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
+                    s.d_len, h->d_A, h->d_Bt, h->M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero,
+                    h->d_allfull, h->d_partials + (size_t)c0 * h->pstride, h->pstride, h->d_flag, h->d_newflags);
+        return HMMB_OK;
+    };
+    if (s.pend) {
+        // first E-step of a pipelined fit: stage j = the blocks whose codewords have landed (copy-stream event),
+        // repacked and pushed through forward + backward while the next chunks are still on PCIe
+        PendingPrepare &p = *s.pend;
+        int bdone = 0, cdone = 0;
+        cudaEvent_t tdone[PendingPrepare::MAX_STAGES] = {}, tbeg[PendingPrepare::MAX_STAGES] = {};
+        for (int j = 0; j < p.nstage; ++j) {
+            HMMB_CUDA(cudaStreamWaitEvent(c.stream, p.up->ev[p.ev_index[j]], 0));
+            if (p.up->t0) { cudaEventCreate(&tbeg[j]); cudaEventRecord(tbeg[j], c.stream); }
+            HMMB_TRY(launch_repack_range(s, p.up->d_raw, p.idx_bytes, bdone, p.blk_end[j], s.d_bad));
+            HMMB_TRY(launch_range(cdone, p.cta_end[j]));
+            if (p.up->t0) { cudaEventCreate(&tdone[j]); cudaEventRecord(tdone[j], c.stream); }
+            bdone = p.blk_end[j];
+            cdone = p.cta_end[j];
+        }
+        if (p.up->t0) {  // HMMB_TIMING: where the upload chunks and the stages sit on one time line
+            cudaStreamSynchronize(c.stream);
+            for (int k = 0; k < p.up->nchunk; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, p.up->t0, p.up->ev[k]);
+                fprintf(stderr, "[hmmb] upload chunk %d landed at %.2f ms\n", k, ms);
+            }
+            for (int j = 0; j < p.nstage; ++j) {
+                float a = 0.f, b = 0.f;
+                cudaEventElapsedTime(&a, p.up->t0, tbeg[j]);
+                cudaEventElapsedTime(&b, p.up->t0, tdone[j]);
+                fprintf(stderr, "[hmmb] stage %d (blocks < %d, CTAs < %d): %.2f -> %.2f ms\n", j, p.blk_end[j], p.cta_end[j], a, b);
+                cudaEventDestroy(tbeg[j]);
+                cudaEventDestroy(tdone[j]);
+            }
+            cudaEventDestroy(p.up->t0);
+            p.up->t0 = nullptr;
+        }
+        h->check_bad = true;
+        h->pend_release = std::move(s.pend);  // raw buffer + events: released after the next stream sync
+        // flagged sequences only exist from the second iteration on (flags are set by this forward pass):
+        // the exact kernel runs after the stages; it and the backward pass are independent
+        return launch_exact<uint16_t, true>(h);
+    }
     HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
                 s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag,
                 h->d_allfull);
@@ -812,6 +1052,23 @@ static int bw_estep(hmmb_bw *h) {
     return HMMB_ERR_UNSUPPORTED;
 }
 
+// Called right after a cudaStreamSynchronize of the compute stream: the pipelined prepare's upload
+// state can go, and its codeword-range flag is read back (the check hmmb_bw_create makes itself when
+// it does the repack).
+static int bw_after_sync(hmmb_bw *h) {
+    h->pend_release.reset();
+    if (h->check_bad) {
+        h->check_bad = false;
+        int bad = 0;
+        HMMB_CUDA(cudaMemcpy(&bad, h->s.d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bad) {
+            set_error("codeword out of range: some observation is >= M=%d (reference: IndexError)", h->M);
+            return HMMB_ERR_RANGE;
+        }
+    }
+    return HMMB_OK;
+}
+
 int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync_each) {
     HMMB_TRY(require_init());
     if (!h || !h->params_set) { set_error("hmmb_bw_iterate: parameters not set"); return HMMB_ERR_ARG; }
@@ -828,6 +1085,7 @@ int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync
             int32_t nf = 0;
             HMMB_CUDA(cudaMemcpyAsync(&nf, h->d_newflags, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
             HMMB_CUDA(cudaStreamSynchronize(c.stream));
+            HMMB_TRY(bw_after_sync(h));
             if (nf == 0) break;
             h->n_backward_handover += nf;
             HMMB_CUDA(cudaMemsetAsync(h->d_newflags, 0, sizeof(int32_t), c.stream));
@@ -855,6 +1113,7 @@ int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync
         int32_t any = 0;
         HMMB_CUDA(cudaMemcpyAsync(&any, h->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
         HMMB_CUDA(cudaStreamSynchronize(c.stream));
+        HMMB_TRY(bw_after_sync(h));
         h->any_active = any != 0;
     }
     return HMMB_OK;
@@ -925,8 +1184,9 @@ int hmmb_bw_fit(const void *obs, int idx_bytes, const int64_t *offsets, const in
                 int N, int M, const double *pi0, const double *A0, const double *B0, double eps, int max_iter,
                 double *pi, double *A, double *B, double *ll_hist, int32_t *iters) {
     hmmb_bw_t *h = nullptr;
-    HMMB_TRY(hmmb_bw_create(&h, obs, idx_bytes, 0, offsets, word_of_seq, R, W, N, M));
-    int rc = hmmb_bw_set_params(h, pi0, A0, B0);
+    if (!pi0 || !A0 || !B0) { set_error("hmmb_bw_fit: null parameters"); return HMMB_ERR_ARG; }
+    HMMB_TRY(hmmb_bw_create_ex(&h, obs, idx_bytes, 0, offsets, word_of_seq, R, W, N, M, HMMB_BW_PIPELINE_UPLOAD, pi0, A0, B0));
+    int rc = HMMB_OK;
     if (rc == HMMB_OK) rc = hmmb_bw_iterate(h, max_iter, eps, max_iter, 1);
     if (rc == HMMB_OK) rc = hmmb_bw_get_params(h, 1, pi, A, B);
     if (rc == HMMB_OK && (ll_hist || iters)) rc = hmmb_bw_get_history(h, ll_hist, std::max(max_iter, 1), iters);

@@ -33,48 +33,51 @@ constexpr int SYM_BITS = 11;
 constexpr int BW4_MAX_M = 512;   // warp-private count copies must fit in shared memory
 
 // ---------------------------------------------------------------- repack
+// One warp per (block, chunk of 8 steps), lane = sequence.  The conflict rank of a lane at a step
+// (number of lower lanes of the block with the same codeword) comes from SYM_BITS ballots: the
+// lanes that agree with me on every bit are my peers.  No shared memory, no barriers; the output
+// row of the chunk is one coalesced 512-byte store.
+constexpr int REPACK_WARPS = 8;
 template <typename InT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(REPACK_WARPS * 32)
 k_repack_blocks4(const InT *__restrict__ obs, const int64_t *__restrict__ off_sorted,
                  const int32_t *__restrict__ len_sorted, const Blk *__restrict__ blks, int blk_base, int nblk,
                  uint4 *__restrict__ obs_blk, int M, int *__restrict__ bad) {
-    __shared__ unsigned short sSym[SPC4][32];
     const int b = blk_base + blockIdx.x;
     if (b >= nblk) return;
     const Blk bk = blks[b];
     const int nch = (bk.tmax + SPC4 - 1) / SPC4;
-    const int tid = threadIdx.x;  // 256 threads = 8 steps x 32 lanes
-    const int s = tid >> 5, lane = tid & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int T = 0;
     const InT *src = obs;
     if (lane < bk.nseq) {
         T = len_sorted[bk.first + lane];
         src = obs + off_sorted[bk.first + lane];
     }
-    for (int c = 0; c < nch; ++c) {
-        const int t = c * SPC4 + s;
-        unsigned sym = 0xffffu;  // marks "no frame"
-        if (t < T) {
-            unsigned long long v = (unsigned long long)src[t];
-            if (v >= (unsigned long long)M) { atomicOr(bad, 1); v = 0; }
-            sym = (unsigned)v;
-        }
-        __syncthreads();
-        sSym[s][lane] = (unsigned short)sym;
-        __syncthreads();
-        unsigned rank = 0;
-        if (sym != 0xffffu)
-            for (int l = 0; l < lane; ++l) rank += (sSym[s][l] == sym) ? 1u : 0u;
-        const unsigned packed = (sym == 0xffffu) ? 0u : (sym | (rank << SYM_BITS));
-        __syncthreads();
-        sSym[s][lane] = (unsigned short)packed;
-        __syncthreads();
-        if (s == 0) {
-            unsigned r[4];
+    const unsigned lt = (1u << lane) - 1u;
+    for (int c = warp; c < nch; c += REPACK_WARPS) {
+        unsigned r[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) r[q] = (unsigned)sSym[2 * q][lane] | ((unsigned)sSym[2 * q + 1][lane] << 16);
-            obs_blk[bk.obs_base + (size_t)c * 32 + lane] = make_uint4(r[0], r[1], r[2], r[3]);
+        for (int s = 0; s < SPC4; ++s) {
+            const int t = c * SPC4 + s;
+            const bool have = t < T;
+            unsigned sym = 0u;
+            if (have) {
+                unsigned long long v = (unsigned long long)src[t];
+                if (v >= (unsigned long long)M) { atomicOr(bad, 1); v = 0; }
+                sym = (unsigned)v;
+            }
+            unsigned peers = __ballot_sync(0xffffffffu, have);  // lanes without a frame are nobody's peer
+#pragma unroll
+            for (int bit = 0; bit < SYM_BITS; ++bit) {
+                const unsigned set = __ballot_sync(0xffffffffu, (sym >> bit) & 1u);
+                peers &= ((sym >> bit) & 1u) ? set : ~set;
+            }
+            const unsigned rank = __popc(peers & lt);
+            const unsigned packed = have ? (sym | (rank << SYM_BITS)) : 0u;
+            r[s >> 1] |= packed << ((s & 1) * 16);
         }
+        obs_blk[bk.obs_base + (size_t)c * 32 + lane] = make_uint4(r[0], r[1], r[2], r[3]);
     }
 }
 

@@ -49,6 +49,7 @@ struct Ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of raw codewords, overlapped with host prep and repack
+    bool h2d_on_copy = false;            // small H2D copies of the running build go through copy_stream too
     int64_t launches = 0;
     bool profiling = false;
     std::vector<std::string> phase_names;
@@ -62,6 +63,11 @@ struct Ctx {
     // pinned host staging buffer (per-sequence metadata of the last build)
     void *stage = nullptr;
     size_t stage_bytes = 0;
+    cudaEvent_t stage_busy = nullptr;   // recorded after the last copy out of `stage`
+    // pinned staging of the initial parameters of a pipelined create
+    void *pstage = nullptr;
+    size_t pstage_bytes = 0;
+    cudaEvent_t pstage_busy = nullptr;
 };
 
 Ctx &ctx();

@@ -180,6 +180,11 @@ int hmmb_shutdown(void) {
     if (c.stage) cudaFreeHost(c.stage);
     c.stage = nullptr;
     c.stage_bytes = 0;
+    if (c.pstage) cudaFreeHost(c.pstage);
+    c.pstage = nullptr;
+    c.pstage_bytes = 0;
+    if (c.stage_busy) { cudaEventDestroy(c.stage_busy); c.stage_busy = nullptr; }
+    if (c.pstage_busy) { cudaEventDestroy(c.pstage_busy); c.pstage_busy = nullptr; }
     for (auto ev : c.event_pool) cudaEventDestroy(ev);
     c.event_pool.clear();
     if (c.own_stream) cudaStreamDestroy(c.own_stream);

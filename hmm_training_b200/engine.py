@@ -111,7 +111,7 @@ class BaumWelch:
     word_of_seq int32 [R] in [0, W).  ``obs_dev_ptr`` passes codewords already in HBM."""
 
     def __init__(self, obs, offsets, word_of_seq, W: int, N: int, M: int, obs_dev_ptr: Optional[int] = None,
-                 idx_bytes: Optional[int] = None):
+                 idx_bytes: Optional[int] = None, pipeline_upload: bool = False, init=None):
         lib = _lib.load()
         self._lib = lib
         self.W, self.N, self.M = int(W), int(N), int(M)
@@ -130,10 +130,19 @@ class BaumWelch:
         else:
             op, on_dev, ib = ctypes.c_void_p(obs_dev_ptr), 1, int(idx_bytes)
         h = ctypes.c_void_p()
-        check(lib.hmmb_bw_create(ctypes.byref(h), op, ib, on_dev, ptr(offsets), ptr(word_of_seq), self.R, self.W,
-                                 self.N, self.M))
+        # pipeline_upload: hmmb_bw_create_ex may return while pinned codewords are still crossing PCIe;
+        # the first iterate() runs behind the upload, so the buffer is kept alive until close()
+        # init = (pi0, A0, B0): uploaded by the create ahead of the bulk of the codewords (= set_params)
+        p0 = a0 = b0 = None
+        if init is not None:
+            p0, a0, b0 = (c_f64(x) for x in init)
+            if p0.shape != (self.W, self.N) or a0.shape != (self.W, self.N, self.N) or b0.shape != (self.W, self.N, self.M):
+                raise ValueError(f"parameter shapes must be ({W},{N}), ({W},{N},{N}), ({W},{N},{M})")
+        check(lib.hmmb_bw_create_ex(ctypes.byref(h), op, ib, on_dev, ptr(offsets), ptr(word_of_seq), self.R, self.W,
+                                    self.N, self.M, 1 if pipeline_upload else 0, ptr(p0), ptr(a0), ptr(b0)))
         self._h = h
         self._keep = None
+        self._obs_keepalive = obs if pipeline_upload else None
         self.frames = int(lib.hmmb_bw_total_frames(h))
 
     def set_params(self, pi0, A0, B0) -> None:
@@ -201,8 +210,7 @@ def bw_fit(obs, offsets, word_of_seq, W: int, N: int, M: int, pi0, A0, B0, epsil
            max_iterations: int = 100, allreduce=None, rank: int = 0, world: int = 1):
     """Batched hmm_training (HMM/hmm_training.py:265-541) for W words at once.
     Returns (pi [W,N], A [W,N,N], B [W,N,M], ll_hist [W,max_iterations], iters [W])."""
-    with BaumWelch(obs, offsets, word_of_seq, W, N, M) as bw:
-        bw.set_params(pi0, A0, B0)
+    with BaumWelch(obs, offsets, word_of_seq, W, N, M, pipeline_upload=True, init=(pi0, A0, B0)) as bw:
         if world > 1:
             bw.set_dist(rank, world, allreduce)
         bw.iterate(max_iterations, epsilon, max_iterations, sync_each=True)

@@ -104,6 +104,20 @@ typedef struct hmmb_bw hmmb_bw_t;
 int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_device,
                    const int64_t *offsets, const int32_t *word_of_seq, int64_t R, int W, int N,
                    int M);
+/* flags for hmmb_bw_create_ex.  HMMB_BW_PIPELINE_UPLOAD: when the codewords come from PINNED host
+ * memory in (word, length-descending) order and N = 4, the call returns while they are still
+ * being uploaded (copy stream, a few chunks) and the first hmmb_bw_iterate runs its E-step stage
+ * by stage behind the upload (repack -> forward -> backward of the blocks that have landed).
+ * The caller must keep `obs` valid and unchanged until that first hmmb_bw_iterate has returned;
+ * a codeword >= M is then reported by that call (HMMB_ERR_RANGE) instead of by the create.
+ * Results are those of the unpipelined path (the CTA partition is finer, so sums may differ in
+ * the last bits).                                                                            */
+#define HMMB_BW_PIPELINE_UPLOAD 1
+/* pi0 / A0 / B0 (all three or none): initial parameters as for hmmb_bw_set_params, uploaded by the
+ * create itself ahead of the bulk of the codewords (a later hmmb_bw_set_params is still allowed). */
+int hmmb_bw_create_ex(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_device,
+                      const int64_t *offsets, const int32_t *word_of_seq, int64_t R, int W, int N,
+                      int M, int flags, const double *pi0, const double *A0, const double *B0);
 int hmmb_bw_destroy(hmmb_bw_t *h);
 /* pi0 [W,N], A0 [W,N,N], B0 [W,N,M] linear-space initial parameters; resets iteration state */
 int hmmb_bw_set_params(hmmb_bw_t *h, const double *pi0, const double *A0, const double *B0);

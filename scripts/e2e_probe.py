@@ -8,8 +8,18 @@ obs, off, wos = synthetic.fixed_length_codewords(1000, W,S,T,N,M)
 obs_p = torch.empty(obs.shape, dtype=torch.uint8, pin_memory=True); obs_h = obs_p.numpy(); obs_h[:] = obs
 pi0,A0,B0 = engine.default_init(N,M); pi0,A0,B0 = np.tile(pi0,(W,1)),np.tile(A0,(W,1,1)),np.tile(B0,(W,1,1))
 for rep in range(3):
-    t=time.perf_counter(); bw = engine.BaumWelch(obs_h, off, wos, W,N,M); t1=time.perf_counter()
-    bw.set_params(pi0,A0,B0); t2=time.perf_counter()
+    PIPE = os.environ.get("PIPE","1")=="1"
+    t=time.perf_counter(); bw = engine.BaumWelch(obs_h, off, wos, W,N,M, pipeline_upload=PIPE, init=(pi0,A0,B0) if PIPE else None); t1=time.perf_counter()
+    if not PIPE: bw.set_params(pi0,A0,B0)
+    t2=time.perf_counter()
     bw.iterate(1,-1.0,1,True); t3=time.perf_counter()
     out=bw.params(True); h=bw.history(1); t4=time.perf_counter(); bw.close(); t5=time.perf_counter()
     print('create %.2f set %.2f iterate %.2f get %.2f close %.2f total %.2f ms'%tuple(1e3*x for x in (t1-t,t2-t1,t3-t2,t4-t3,t5-t4,t5-t)))
+# phase timing of the pipelined first iteration (CUDA events around every launch)
+lib = _lib.load()
+_lib.check(lib.hmmb_set_profiling(1)); _lib.check(lib.hmmb_phase_reset())
+bw = engine.BaumWelch(obs_h, off, wos, W, N, M, pipeline_upload=PIPE, init=(pi0, A0, B0) if PIPE else None)
+if not PIPE: bw.set_params(pi0, A0, B0)
+bw.iterate(1, -1.0, 1, True); bw.close()
+print({k: (round(_lib.phase_ms(k)[0], 3), _lib.phase_ms(k)[1]) for k in ("prepare", "bw_forward", "bw_backward", "bw_exact", "bw_reduce", "bw_mstep")})
+_lib.check(lib.hmmb_set_profiling(0))

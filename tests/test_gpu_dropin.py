@@ -196,3 +196,53 @@ def test_train_and_test_callers_match_reference_pipeline(batched, fast, tmp_path
     assert [pred[i] for i in order] == [str(x) for x in g["pred"][gorder]]
     out = capsys.readouterr().out
     assert "Overall Accuracy: 100.00%" in out and os.path.exists(tmp_path / "Data" / "Plots" / "confusion_matrix.csv")
+
+
+def _pinned_copy(a):
+    """numpy view of pinned host memory (hmmb_host_alloc) holding a copy of `a`."""
+    import ctypes
+    from hmm_training_b200 import _lib
+    lib = _lib.load()
+    p = lib.hmmb_host_alloc(a.nbytes)
+    assert p
+    buf = np.ctypeslib.as_array((ctypes.c_uint8 * a.nbytes).from_address(p)).view(a.dtype).reshape(a.shape)
+    buf[...] = a
+    return buf, p
+
+
+def test_pipelined_upload_matches_plain_create():
+    """engine.bw_fit on a large PINNED codeword buffer takes the pipelined path (chunked upload on the
+    copy stream, first E-step in stages behind it, parameters uploaded by the create); results must be
+    bit-identical to create + set_params + iterate on the same data, and a codeword >= M must still
+    surface as IndexError."""
+    from hmm_training_b200 import _lib, engine
+    N, M, W, S, T = 4, 256, 6, 40000, 150  # 36 MB of codewords: two upload chunks -> two pipeline stages
+    obs, offsets, wos = synthetic.fixed_length_codewords(3, W, S, T, N, M)
+    pi0, A0, B0 = engine.default_init(N, M)
+    pi0, A0, B0 = np.tile(pi0, (W, 1)), np.tile(A0, (W, 1, 1)), np.tile(B0, (W, 1, 1))
+    pinned, handle = _pinned_copy(obs)
+    try:
+        a = engine.bw_fit(pinned, offsets, wos, W, N, M, pi0, A0, B0, max_iterations=3)
+        with engine.BaumWelch(obs, offsets, wos, W, N, M) as bw:  # pageable input: plain path
+            bw.set_params(pi0, A0, B0)
+            bw.iterate(3, 1e-6, 3)
+            b = bw.params() + bw.history(3)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y, equal_nan=True)
+        with engine.BaumWelch(pinned, offsets, wos, W, N, M, pipeline_upload=True, init=(pi0, A0, B0)) as bw:
+            assert bw.kernel_family() == "n4_left_to_right"
+            bw.iterate(1, 1e-6, 3)
+            bw.set_params(pi0, A0, B0)  # restart on the resident data
+            bw.iterate(3, 1e-6, 3)
+            c = bw.params() + bw.history(3)
+        for x, y in zip(a, c):
+            assert np.array_equal(x, y, equal_nan=True)
+        pinned16, h16 = _pinned_copy(obs.astype(np.uint16))
+        try:
+            pinned16[len(pinned16) // 2 + 7] = 300  # >= M, in the second half of the upload
+            with pytest.raises(IndexError):
+                engine.bw_fit(pinned16, offsets, wos, W, N, M, pi0, A0, B0, max_iterations=2)
+        finally:
+            _lib.load().hmmb_host_free(h16)
+    finally:
+        _lib.load().hmmb_host_free(handle)

@@ -396,7 +396,9 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     int32_t *word_s = len_s + nR;
     int32_t *order_s = word_s + nR;
 
-    std::vector<int32_t> len(R);
+    // (a context-owned scratch vector: a fresh 4 MB vector per build costs more in page faults than the loop)
+    std::vector<int32_t> &len = c.len_scratch;
+    if ((int64_t)len.size() < R) len.resize((size_t)R);
     int bad_kind = 0;
     int64_t bad_at = -1;
 #pragma omp parallel for schedule(static) if (R > 65536)
@@ -458,7 +460,8 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     // sequences of a word are contiguous in the sorted order: word boundaries by binary search
     for (int w = 0; w < nwords; ++w)
         s.seq_begin[w + 1] = std::upper_bound(word_s, word_s + R, (int32_t)w) - word_s;
-    s.order.assign(order_s, order_s + R);
+    if (unsorted) s.order.assign(order_s, order_s + R);  // empty = identity (input already in sorted order)
+    else s.order.clear();
     if (!s.blocked()) {
         int64_t facc = 0;  // frame prefix (generic path only; the N = 4 path stores block rows here)
         for (int64_t i = 0; i < R; ++i) {
@@ -469,6 +472,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
 
     std::vector<Blk> blks;
     std::vector<CtaWork> work;
+    blks.reserve((size_t)(R / 32 + nwords + 1));
     int64_t obs_rows = 0;
     if (s.blocked()) {
         const int SPC = SPC4;  // packed u16 entries (codeword | conflict rank) per uint4
@@ -484,7 +488,6 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
                 b.tmax = len_s[i];  // sorted by length descending within the word
                 b.obs_base = obs_rows;
                 b.spill_base = s.spill_steps;
-                for (int l = 0; l < b.nseq; ++l) foff_s[i + l] = obs_rows + l;  // used by the exact kernels
                 obs_rows += (int64_t)((b.tmax + SPC - 1) / SPC) * 32;
                 s.spill_steps += b.tmax;
                 blks.push_back(b);
@@ -492,6 +495,10 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         }
         word_blk_begin[nwords] = (int)blks.size();
         s.nblk = (int)blks.size();
+        // uint4 row of every sequence's lane in the blocked layout (used by the exact kernels)
+#pragma omp parallel for schedule(static) if (s.nblk > 2048)
+        for (int b = 0; b < s.nblk; ++b)
+            for (int l = 0; l < blks[b].nseq; ++l) foff_s[blks[b].first + l] = blks[b].obs_base + l;
         // CTA work items: ~8 CTAs per SM in total (N = 4; the left-to-right kernels run one
         // 8-warp CTA per SM: ~4 per SM), at least one warp-round each
         const int target = s.special4 ? c.sm_count * 8 : c.sm_count * 4;
@@ -1176,7 +1183,8 @@ int hmmb_bw_get_seq_ll(hmmb_bw_t *h, double *ll_seq) {
         HMMB_CUDA(cudaMemcpyAsync(tmp.data(), h->d_llseq, h->s.R * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         HMMB_CUDA(cudaStreamSynchronize(c.stream));
     }
-    for (int64_t i = 0; i < h->s.R; ++i) ll_seq[h->cur().order[i]] = tmp[i];
+    const std::vector<int32_t> &order = h->cur().order;  // empty = identity
+    for (int64_t i = 0; i < h->s.R; ++i) ll_seq[order.empty() ? i : order[i]] = tmp[i];
     return HMMB_OK;
 }
 

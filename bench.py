@@ -507,6 +507,17 @@ def run_extras(torch, lib, _lib, engine, synthetic, hbm_peak, with_cpu):
                                "fp64_tflops": fm * 45.0 / (kernel_ms * 1e-3) / 1e12,
                                "note": "45 flop per frame x model (bidiagonal N=4); issue-bound, no HBM stream to speak of"},
                     "h2d_bytes_per_step": int(obs_p.nbytes + offsets.nbytes), "d2h_bytes_per_step": int(ll_p.nbytes + 4 * U)}
+    if with_cpu:
+        from oracle import hmm_oracle as O
+        nu = 400
+        seqs = [obs[u * 100:(u + 1) * 100].astype(np.int64) for u in range(nu)]
+        models = [(Am[w], Bm[w], pim[w]) for w in range(Wm)]
+        O.score_batch(seqs[:20], models)
+        t0 = time.perf_counter()
+        O.score_batch(seqs, models)
+        dtc = time.perf_counter() - t0
+        out["score"]["cpu_baseline"] = {"value": nu / dtc, "unit": "utterances/s", "cores": 1, "kind": "port",
+                                        "sample": f"{nu} utterances x {Wm} models, T=100 (numpy oracle, 1 core)"}
     # config 5 stress variant: 1000 left-to-right models with 16 states and 1024 codewords (k_scoreL)
     Us, Ws, Ns, Ms, Ts = 100_000, 1000, 16, 1024, 100
     obs, offsets, _ = synthetic.fixed_length_codewords(78, 10, Us // 10, Ts, Ns, Ms)

@@ -51,7 +51,8 @@ template <bool BIDIAG>
 __global__ void __launch_bounds__(BW_THREADS)
 k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4 *__restrict__ obs_blk,
          const int32_t *__restrict__ len_sorted, const int32_t *__restrict__ order, const double *__restrict__ pi,
-         const double *__restrict__ A, const double *__restrict__ Bt, int M, int W, double *__restrict__ ll_out) {
+         const double *__restrict__ A, const double *__restrict__ Bt, int M, int W, double *__restrict__ ll_out,
+         int32_t *__restrict__ any_nan) {
     extern __shared__ double sB[];
     double *sBmax = sB + (size_t)M * 4;
     unsigned char *sBmask = reinterpret_cast<unsigned char *>(sBmax + M);
@@ -69,7 +70,10 @@ k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4
         bool af;
         const double ll = fwd4_run<BIDIAG, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, reinterpret_cast<const double2 *>(sB),
                                                   reinterpret_cast<const double2 *>(sB) + M, sBmax, sBmask, a, p, rmax, mk, nullptr, af);
-        if (lane < bk.nseq) ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
+        if (lane < bk.nseq) {
+            ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
+            if (ll != ll) *any_nan = 1;  // precision guard marked this pair: k_score_exact has work to do
+        }
     }
 }
 
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(BW_THREADS)
 k_scoreG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, const int32_t *__restrict__ len_sorted,
          const int32_t *__restrict__ order, int64_t U, int64_t per_group, int N, int M, int W,
          const double *__restrict__ pi, const double *__restrict__ A, const double *__restrict__ Bt,
-         double *__restrict__ ll_out) {
+         double *__restrict__ ll_out, int32_t *__restrict__ any_nan) {
     __shared__ double sStage[BW_WARPS][128];
     const int w = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -97,7 +101,10 @@ k_scoreG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, c
         const SymT *o = obs + (T > 0 ? off_sorted[r] : 0);
         const double ll = fwdG_run<NP, SymT, false>(T, Tw, N, j, gbase, lane, o, Bt + (size_t)w * M * N, acol, pj,
                                                     nullptr, sStage[warp]);
-        if (T > 0 && j == 0) ll_out[(size_t)order[r] * W + w] = ll;
+        if (T > 0 && j == 0) {
+            ll_out[(size_t)order[r] * W + w] = ll;
+            if (ll != ll) *any_nan = 1;
+        }
     }
 }
 
@@ -119,7 +126,9 @@ template <typename SymT, bool BLOCKED>
 __global__ void __launch_bounds__(BW_THREADS)
 k_score_exact(const void *__restrict__ obs, const int64_t *__restrict__ base_sorted, const int32_t *__restrict__ len_sorted,
               const int32_t *__restrict__ order, int64_t U, int N, int M, int W, const double *__restrict__ pi,
-              const double *__restrict__ A, const double *__restrict__ Bt, double *__restrict__ ll_out) {
+              const double *__restrict__ A, const double *__restrict__ Bt, double *__restrict__ ll_out,
+              const int32_t *__restrict__ any_nan) {
+    if (*any_nan == 0) return;  // the scorers marked nothing: no scan of the [U, W] matrix
     const int lane = threadIdx.x & 31;
     const int64_t gw = (int64_t)blockIdx.x * BW_WARPS + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * BW_WARPS;
@@ -1204,7 +1213,7 @@ int hmmb_bw_fit(const void *obs, int idx_bytes, const int64_t *offsets, const in
 
 // ---------------------------------------------------------------- recognition
 template <int NP, typename SymT>
-static int launch_score_generic(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll) {
+static int launch_score_generic(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll, int32_t *d_nan) {
     Ctx &c = ctx();
     constexpr int GPW = 32 / NP;
     int64_t grid = (std::max<int64_t>(s.R, 1) + BW_WARPS * GPW - 1) / (BW_WARPS * GPW);
@@ -1213,12 +1222,12 @@ static int launch_score_generic(SeqSet &s, int W, const double *d_pi, const doub
     const int64_t per_group = (s.R + total_groups - 1) / total_groups;
     dim3 g((unsigned)grid, (unsigned)W);
     HMMB_LAUNCH("score", (k_scoreG<NP, SymT>), g, BW_THREADS, 0, (const SymT *)s.d_obs, s.d_off, s.d_len, s.d_order, s.R,
-                per_group, s.N, s.M, W, d_pi, d_A, d_Bt, d_ll);
+                per_group, s.N, s.M, W, d_pi, d_A, d_Bt, d_ll, d_nan);
     return HMMB_OK;
 }
 
 template <bool BIDIAG>
-static int launch_score_special(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll) {
+static int launch_score_special(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll, int32_t *d_nan) {
     Ctx &c = ctx();
     if (s.nblk == 0) return HMMB_OK;
     // each CTA re-uses one model's B for several 32-utterance blocks
@@ -1228,18 +1237,18 @@ static int launch_score_special(SeqSet &s, int W, const double *d_pi, const doub
     dim3 g((unsigned)((s.nblk + bpc - 1) / bpc), (unsigned)W);
     const size_t smem = (size_t)s.M * 5 * sizeof(double) + (size_t)((s.M + 15) & ~15);
     HMMB_LAUNCH("score", k_score4<BIDIAG>, g, BW_THREADS, smem, s.d_blks, s.nblk, bpc, (const uint4 *)s.d_obs, s.d_len,
-                s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll);
+                s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll, d_nan);
     return HMMB_OK;
 }
 
 template <int NS>
-static int launch_score_ltr(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll) {
+static int launch_score_ltr(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll, int32_t *d_nan) {
     if (s.ncta == 0) return HMMB_OK;
     const size_t smem = (size_t)s.M * NS * 8 + (size_t)s.M * 8 + (size_t)s.M * 2;
     HMMB_CUDA(cudaFuncSetAttribute(k_scoreL<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 g((unsigned)s.ncta, (unsigned)W);
     HMMB_LAUNCH("score", k_scoreL<NS>, g, LTR_THREADS, smem, s.d_work, s.d_blks, (const uint4 *)s.d_obs, s.d_len, s.d_order,
-                d_pi, d_A, d_Bt, s.M, W, d_ll);
+                d_pi, d_A, d_Bt, s.M, W, d_ll, d_nan);
     return HMMB_OK;
 }
 
@@ -1270,6 +1279,9 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
     HMMB_TRY(dev_alloc_t(&d_Bt, nB)); guard.ptrs.push_back(d_Bt);
     HMMB_TRY(dev_alloc_t(&d_ll, (size_t)U * W)); guard.ptrs.push_back(d_ll);
     HMMB_TRY(dev_alloc_t(&d_arg, (size_t)U)); guard.ptrs.push_back(d_arg);
+    int32_t *d_nan = nullptr;  // set by the scorers when the precision guard marked a pair
+    HMMB_TRY(dev_alloc_t(&d_nan, 1)); guard.ptrs.push_back(d_nan);
+    HMMB_CUDA(cudaMemsetAsync(d_nan, 0, sizeof(int32_t), c.stream));
     HMMB_CUDA(cudaMemcpyAsync(tmp, B, nB * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     HMMB_CUDA(cudaMemcpyAsync(tmp + nB, A, nA * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     HMMB_CUDA(cudaMemcpyAsync(tmp + nB + nA, pi, nP * sizeof(double), cudaMemcpyHostToDevice, c.stream));
@@ -1284,15 +1296,15 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
             const int ij = (int)(e % 16), i = ij / 4, j = ij % 4;
             if (j != i && j != i + 1 && A[e] > 0.0) bidiag = false;
         }
-        rc = bidiag ? launch_score_special<true>(s, W, d_pi, d_A, d_Bt, d_ll)
-                    : launch_score_special<false>(s, W, d_pi, d_A, d_Bt, d_ll);
+        rc = bidiag ? launch_score_special<true>(s, W, d_pi, d_A, d_Bt, d_ll, d_nan)
+                    : launch_score_special<false>(s, W, d_pi, d_A, d_Bt, d_ll, d_nan);
     } else if (s.ltr_ns) {
-        rc = s.ltr_ns == 16 ? launch_score_ltr<16>(s, W, d_pi, d_A, d_Bt, d_ll) : launch_score_ltr<8>(s, W, d_pi, d_A, d_Bt, d_ll);
+        rc = s.ltr_ns == 16 ? launch_score_ltr<16>(s, W, d_pi, d_A, d_Bt, d_ll, d_nan) : launch_score_ltr<8>(s, W, d_pi, d_A, d_Bt, d_ll, d_nan);
     } else {
 #define GEN(NPV)                                                                                         \
     case NPV:                                                                                            \
-        rc = s.sym_bytes == 1 ? launch_score_generic<NPV, uint8_t>(s, W, d_pi, d_A, d_Bt, d_ll)         \
-                              : launch_score_generic<NPV, uint16_t>(s, W, d_pi, d_A, d_Bt, d_ll);       \
+        rc = s.sym_bytes == 1 ? launch_score_generic<NPV, uint8_t>(s, W, d_pi, d_A, d_Bt, d_ll, d_nan)         \
+                              : launch_score_generic<NPV, uint16_t>(s, W, d_pi, d_A, d_Bt, d_ll, d_nan);       \
         break;
         switch (s.NP) {
             GEN(4) GEN(8) GEN(16) GEN(32)
@@ -1306,12 +1318,12 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
         int64_t warps = std::min<int64_t>((int64_t)c.sm_count * 16, U);
         const int eg = (int)std::max<int64_t>(1, (warps + BW_WARPS - 1) / BW_WARPS);
         if (s.blocked()) {
-            HMMB_LAUNCH("score_exact", (k_score_exact<uint16_t, true>), eg, BW_THREADS, 0, s.d_obs, s.d_foff, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);
+            HMMB_LAUNCH("score_exact", (k_score_exact<uint16_t, true>), eg, BW_THREADS, 0, s.d_obs, s.d_foff, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll, d_nan);
         } else {
             if (s.sym_bytes == 1)
-                HMMB_LAUNCH("score_exact", (k_score_exact<uint8_t, false>), eg, BW_THREADS, 0, s.d_obs, s.d_off, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);
+                HMMB_LAUNCH("score_exact", (k_score_exact<uint8_t, false>), eg, BW_THREADS, 0, s.d_obs, s.d_off, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll, d_nan);
             else
-                HMMB_LAUNCH("score_exact", (k_score_exact<uint16_t, false>), eg, BW_THREADS, 0, s.d_obs, s.d_off, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll);
+                HMMB_LAUNCH("score_exact", (k_score_exact<uint16_t, false>), eg, BW_THREADS, 0, s.d_obs, s.d_off, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll, d_nan);
         }
     }
     HMMB_LAUNCH("score_argmax", k_argmax_first, (unsigned)((U + 255) / 256), 256, 0, d_ll, U, W, d_arg);

@@ -340,7 +340,8 @@ template <int NS>
 __global__ void __launch_bounds__(LTR_THREADS, 1)
 k_scoreL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
          const int32_t *__restrict__ len_sorted, const int32_t *__restrict__ order, const double *__restrict__ pi,
-         const double *__restrict__ A, const double *__restrict__ Bt, int M, int W, double *__restrict__ ll_out) {
+         const double *__restrict__ A, const double *__restrict__ Bt, int M, int W, double *__restrict__ ll_out,
+         int32_t *__restrict__ any_nan) {
     using L = Ltr<NS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *sB = reinterpret_cast<double2 *>(smem_raw);
@@ -362,7 +363,10 @@ k_scoreL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const u
         bool af;
         const double ll = fwdL_run<NS, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, sBmask, as, an, piw, rmax,
                                               selfm, nextm, pmask, nullptr, af);
-        if (lane < bk.nseq) ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
+        if (lane < bk.nseq) {
+            ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
+            if (ll != ll) *any_nan = 1;  // precision guard marked this pair: k_score_exact has work to do
+        }
     }
 }
 

@@ -168,7 +168,9 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
  * [cap_frames,13] in file order.  Returns the number of frames found (frames beyond
  * cap_frames are counted but not stored; mfcc_out may be NULL to count only) or a negative
  * error (HMMB_ERR_RANGE: a vector that does not have 13 entries — the reference raises
- * ValueError("Vectors must be of size 13."), codevector_functions.py:83-84).  No CUDA needed. */
+ * ValueError("Vectors must be of size 13."), codevector_functions.py:83-84).  No CUDA needed.
+ * text[len] must be readable and not part of a number (a NUL terminator, as in a C string or a
+ * Python bytes object): numbers are parsed with strtod.                                      */
 int64_t hmmb_frames_json_scan(const char *text, int64_t len, double *mfcc_out, int64_t cap_frames);
 
 #ifdef __cplusplus

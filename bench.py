@@ -38,6 +38,7 @@ WORKLOADS = {
     # name: (W, S per word per GPU, T, N, M)
     "bw_c3": dict(W=10, S=100_000, T=200, N=4, M=256, desc="config 3: 10 words x 100k seq x T=200, N=4, M=256"),
     "bw_c4": dict(W=1000, S=500, T=200, N=16, M=1024, desc="config 4: 1000 words x 500 seq x T=200, N=16, M=1024"),
+    "bw_n8": dict(W=1000, S=500, T=200, N=8, M=1024, desc="1000 words x 500 seq x T=200, N=8, M=1024 (left-to-right kernels at 8 states)"),
     "bw_c1": dict(W=10, S=20, T=100, N=4, M=256, desc="config 1: 10 words x 20 seq x T~100 (latency-bound parity config)"),
 }
 

@@ -298,7 +298,7 @@ __device__ __forceinline__ void load_modelL(const double *__restrict__ Aw, const
 }
 
 template <int NS>
-__global__ void __launch_bounds__(LTR_THREADS, 1)
+__global__ void __launch_bounds__(LTR_THREADS, NS == 8 ? 2 : 1)
 k_bw_fwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
           const int32_t *__restrict__ len_sorted, const double *__restrict__ pi, const double *__restrict__ A,
           const double *__restrict__ Bt, int M, double2 *__restrict__ spill, double *__restrict__ ll_seq,
@@ -337,7 +337,7 @@ k_bw_fwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
 // grid = (utterance work items, models); the CTA keeps one model's B^T in shared memory and
 // scores its 32-utterance blocks with the forward recursion above (no spill).
 template <int NS>
-__global__ void __launch_bounds__(LTR_THREADS, 1)
+__global__ void __launch_bounds__(LTR_THREADS, NS == 8 ? 2 : 1)
 k_scoreL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
          const int32_t *__restrict__ len_sorted, const int32_t *__restrict__ order, const double *__restrict__ pi,
          const double *__restrict__ A, const double *__restrict__ Bt, int M, int W, double *__restrict__ ll_out,
@@ -470,7 +470,7 @@ __device__ __forceinline__ void bulk_reduce_add_f64(double *dst_global, unsigned
 
 // Accumulator layout per word: [pi N][xi N*N][cnt M*N] (fp64, L2 atomics), N == NS.
 template <int NS>
-__global__ void __launch_bounds__(LTR_THREADS, 1)
+__global__ void __launch_bounds__(LTR_THREADS, NS == 8 ? 2 : 1)
 k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
           const int32_t *__restrict__ len_sorted, const double *__restrict__ A, const double *__restrict__ Bt, int M,
           const double2 *__restrict__ spill, const double *__restrict__ ll_seq, const int32_t *__restrict__ active,

@@ -183,6 +183,38 @@ def test_baum_welch_left_to_right_kernels(N, M, kind, monkeypatch):
     assert_close(ll_seq, llg, "ltr vs generic per-sequence LL")
 
 
+def test_left_to_right_kernels_at_config4_shape(monkeypatch):
+    """BASELINE config 4's shape at a size the generic kernels still finish quickly (12 words x 300
+    sequences x T = 200, N = 16, M = 1024, 6 iterations — trained B rows then hold values down to the
+    1e-20 floor and far below): the left-to-right kernels must agree with the lanes-per-state kernels
+    to 1e-9, keep rows stochastic, and not decrease the convergence statistic."""
+    N, M, W, S, T = 16, 1024, 12, 300, 200
+    obs, offsets, wos = synthetic.fixed_length_codewords(11, W, S, T, N, M)
+    pi0, A0, B0 = engine.default_init(N, M)
+    init = (np.tile(pi0, (W, 1)), np.tile(A0, (W, 1, 1)), np.tile(B0, (W, 1, 1)))
+    res = {}
+    for fam, env in (("left_to_right", None), ("generic", "1")):
+        if env:
+            monkeypatch.setenv("HMMB_NO_LTR", env)
+        else:
+            monkeypatch.delenv("HMMB_NO_LTR", raising=False)
+        with engine.BaumWelch(obs, offsets, wos, W, N, M) as bw:
+            bw.set_params(*init)
+            assert bw.kernel_family() == fam
+            bw.iterate(6, -1.0, 6)
+            res[fam] = bw.params() + bw.history(6) + (bw.seq_ll(), bw.diagnostics())
+    a, b = res["left_to_right"], res["generic"]
+    for x, y, what in zip(a[:4], b[:4], ("pi", "A", "B", "ll history")):
+        assert_close(x, y, f"left_to_right vs generic {what}")
+    assert_close(a[5], b[5], "per-sequence LL of the last E-step")
+    assert np.array_equal(a[4], b[4]) and np.all(a[4] == 6)
+    pi, A, B, hist = a[:4]
+    assert np.allclose(pi.sum(axis=1), 1) and np.allclose(A.sum(axis=2), 1) and np.allclose(B.sum(axis=2), 1)
+    assert np.all(np.diff(hist, axis=1) > -1e-6)
+    assert np.array_equal(A == 0, np.tile(A0 == 0, (W, 1, 1)))  # the left-to-right support is preserved
+    assert a[6] == b[6] == (0, 0)  # neither family needed the exact log-space path on this data
+
+
 def test_baum_welch_is_deterministic():
     g = load_golden("bw_clustered_s2_it1")
     N, M, W = 4, 256, 3

@@ -519,6 +519,21 @@ def run_extras(torch, lib, _lib, engine, synthetic, hbm_peak, with_cpu):
         dtc = time.perf_counter() - t0
         out["score"]["cpu_baseline"] = {"value": nu / dtc, "unit": "utterances/s", "cores": 1, "kind": "port",
                                         "sample": f"{nu} utterances x {Wm} models, T=100 (numpy oracle, 1 core)"}
+    # MFCC front-end (parity unpinned): 100k frames of 320 samples
+    Ym = np.random.default_rng(9).normal(size=(100_000, 320)) * 1000.0
+    Ymp = torch.from_numpy(Ym).pin_memory().numpy()
+    engine.mfcc_frames(Ymp[:2000])
+    _lib.check(lib.hmmb_set_profiling(1))
+    _lib.check(lib.hmmb_phase_reset())
+    t0 = time.perf_counter()
+    engine.mfcc_frames(Ymp)
+    dtm = time.perf_counter() - t0
+    mms, _ = _lib.phase_ms("mfcc")
+    _lib.check(lib.hmmb_set_profiling(0))
+    out["mfcc"] = {"metric": "mfcc_frames_per_s", "value": len(Ym) / dtm, "unit": "frames/s (host API end to end)",
+                   "frames": len(Ym), "frame_len": 320, "kernel_ms": mms, "kernel_frames_per_s": len(Ym) / (mms * 1e-3),
+                   "h2d_bytes_per_step": int(Ym.nbytes), "d2h_bytes_per_step": len(Ym) * 13 * 8,
+                   "note": "parity with librosa unpinned (oracle/mfcc_oracle.py)"}
     # config 5 stress variant: 1000 left-to-right models with 16 states and 1024 codewords (k_scoreL)
     Us, Ws, Ns, Ms, Ts = 100_000, 1000, 16, 1024, 100
     obs, offsets, _ = synthetic.fixed_length_codewords(78, 10, Us // 10, Ts, Ns, Ms)

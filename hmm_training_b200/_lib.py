@@ -60,6 +60,7 @@ SYMBOLS = [
     ("hmmb_bw_fit", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int,
                                _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_double, _c.c_int, _c.c_void_p,
                                _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    ("hmmb_mfcc_frames", _c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_double, _c.c_void_p]),
     ("hmmb_frames_json_scan", _c.c_int64, [_c.c_char_p, _c.c_int64, _c.c_void_p, _c.c_int64]),
     ("hmmb_score", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int,
                               _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),

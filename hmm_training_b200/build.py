@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhmmb200.so")
-SOURCES = ["context.cu", "vq.cu", "bw.cu", "loader.cu"]
+SOURCES = ["context.cu", "vq.cu", "bw.cu", "loader.cu", "mfcc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp", "-shared", "--use_fast_math=false"]
 

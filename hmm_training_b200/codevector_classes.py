@@ -125,6 +125,56 @@ class DataStorage:
         return data
 
 
+class AudioProcessor:
+    """Recording -> overlapping 20 ms frames -> RawDataMFCC, as the reference's AudioProcessor
+    (CodeVector/codevector_classes.py:346-431): frame_size 320, hop 160 at 16 kHz, the remaining tail kept as
+    a shorter last frame if it has more than 12 samples (:413-431).  The reference computes the 13 MFCCs of
+    each frame with one librosa call inside RawDataMFCC.__post_init__ (:217-250); here all frames of a
+    recording go through hmmb_mfcc_frames in one batch per frame length (SURVEY.md §8f row 3 — parity with
+    librosa itself is unpinned, see oracle/mfcc_oracle.py)."""
+
+    def __init__(self, sample_rate=16000, frame_duration_ms=20, overlap_ms=10):
+        self.sample_rate = sample_rate
+        self.frame_duration_ms = frame_duration_ms
+        self.overlap_ms = overlap_ms
+        self.frame_size = int(sample_rate * frame_duration_ms / 1000)
+        self.overlap_size = int(sample_rate * overlap_ms / 1000)
+        self.hop_size = self.frame_size - self.overlap_size
+
+    def _split_into_frames_with_overlap(self, audio_data: np.ndarray) -> List[np.ndarray]:
+        frames = [audio_data[i:i + self.frame_size]
+                  for i in range(0, len(audio_data) - self.frame_size + 1, self.hop_size)]
+        last_start = len(frames) * self.hop_size
+        if last_start < len(audio_data):
+            last_frame = audio_data[last_start:]
+            if len(last_frame) > 12:
+                frames.append(last_frame)
+        return frames
+
+    def mfcc_matrix(self, audio_data: np.ndarray) -> np.ndarray:
+        """[F, 13] MFCCs of the recording's frames (the packed form every consumer of this package accepts)."""
+        from . import engine
+        frames = self._split_into_frames_with_overlap(np.asarray(audio_data))
+        out = np.zeros((len(frames), 13))
+        by_len = {}
+        for i, fr in enumerate(frames):
+            by_len.setdefault(len(fr), []).append(i)
+        for L, idx in by_len.items():
+            Y = np.stack([np.asarray(frames[i], dtype=np.float64).reshape(-1) for i in idx])
+            out[idx] = engine.mfcc_frames(Y, self.sample_rate)
+        return out
+
+    def process_recording(self, audio_path: str, purpose: str):
+        """List of RawDataMFCC frames of a .npy recording (same objects for 'train', 'hmm' and 'test', :375-402)."""
+        import os
+        audio_data = np.load(audio_path)
+        frames = self._split_into_frames_with_overlap(audio_data)
+        mfcc = self.mfcc_matrix(audio_data)
+        recording_name = os.path.splitext(os.path.basename(audio_path))[0]
+        return [RawDataMFCC(raw_samples=frame, sample_rate=self.sample_rate, mfcc=mfcc[i], frame_number=i,
+                            recording=recording_name) for i, frame in enumerate(frames)]
+
+
 def load_mfcc_matrix(filepath: str) -> np.ndarray:
     """[F, 13] fp64 matrix of the "mfcc_vector" fields of a frame file written by
     DataStorage.save_raw_data (reference :438-444), in file order, WITHOUT building F

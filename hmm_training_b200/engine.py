@@ -47,6 +47,18 @@ def vq_encode(X: np.ndarray, C: np.ndarray) -> np.ndarray:
     return idx
 
 
+def mfcc_frames(Y: np.ndarray, sr: float = 16000.0) -> np.ndarray:
+    """[F, 13] MFCCs of F equal-length frames Y [F, L] — what RawDataMFCC.calculate_mfcc computes per frame
+    with librosa (CodeVector/codevector_classes.py:226-250), batched on the GPU (hmmb_mfcc_frames)."""
+    Y = c_f64(Y)
+    if Y.ndim != 2:
+        raise ValueError("frames must be [F, L]")
+    out = np.empty((Y.shape[0], 13))
+    if Y.shape[0]:
+        check(_lib.load().hmmb_mfcc_frames(ptr(Y), Y.shape[0], Y.shape[1], 0, float(sr), ptr(out)))
+    return out
+
+
 def _wrap_allreduce(fn: Optional[Callable[[int, int], None]]):
     """fn(dev_ptr, n_doubles) -> None, wrapped as the C hook; returns (cfunc, keepalive)."""
     if fn is None:

@@ -160,6 +160,15 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
                int W, int N, int M, const double *pi, const double *A, const double *B,
                double *ll_out, int32_t *argmax_out);
 
+/* ------------------------------------------------------------------ MFCC front-end
+ * Replaces RawDataMFCC.calculate_mfcc, CodeVector/codevector_classes.py:226-250, batched: F frames
+ * of L samples each (Y [F,L] fp64, host or device) -> mfcc_out [F,13] (host), the coefficients of
+ * librosa.feature.mfcc(y=frame, sr, n_mfcc=13, n_fft=L, hop_length=None, center=False, n_mels=26).
+ * 2 <= L <= 1024 (the reference's frames have 320 samples, the tail frame of a recording 13..319).
+ * librosa is not available where this was built: the kernel follows its published algorithm as
+ * restated in oracle/mfcc_oracle.py; parity with librosa itself is unpinned.          */
+int hmmb_mfcc_frames(const double *Y, int64_t F, int L, int y_on_device, double sr, double *mfcc_out);
+
 /* ------------------------------------------------------------------ frame-file loader (host only)
  * Replaces the json.load + RawDataMFCC.from_dict loop of DataStorage.load_raw_data_mfcc,
  * CodeVector/codevector_classes.py:478-495, for the one field the hot path reads: scans the

@@ -522,7 +522,7 @@ def run_extras(torch, lib, _lib, engine, synthetic, hbm_peak, with_cpu):
     # MFCC front-end (parity unpinned): 100k frames of 320 samples
     Ym = np.random.default_rng(9).normal(size=(100_000, 320)) * 1000.0
     Ymp = torch.from_numpy(Ym).pin_memory().numpy()
-    engine.mfcc_frames(Ymp[:2000])
+    engine.mfcc_frames(Ymp)  # warm: device blocks of this size enter the library's caching allocator
     _lib.check(lib.hmmb_set_profiling(1))
     _lib.check(lib.hmmb_phase_reset())
     t0 = time.perf_counter()

@@ -3,9 +3,9 @@ sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 from hmm_training_b200 import _lib, engine, synthetic
 _lib.init(0)
-W,S,T,N,M=10,100000,200,4,256
+W,S,T,N,M=(1000,500,200,16,1024) if os.environ.get('C4') else (10,100000,200,4,256)
 obs, off, wos = synthetic.fixed_length_codewords(1000, W,S,T,N,M)
-obs_p = torch.empty(obs.shape, dtype=torch.uint8, pin_memory=True); obs_h = obs_p.numpy(); obs_h[:] = obs
+obs_p = torch.empty(obs.shape, dtype=torch.uint8 if obs.dtype==np.uint8 else torch.int16, pin_memory=True); obs_h = obs_p.numpy().view(obs.dtype); obs_h[:] = obs
 pi0,A0,B0 = engine.default_init(N,M); pi0,A0,B0 = np.tile(pi0,(W,1)),np.tile(A0,(W,1,1)),np.tile(B0,(W,1,1))
 for rep in range(3):
     PIPE = os.environ.get("PIPE","1")=="1"

@@ -30,6 +30,7 @@ constexpr int VQ_D = 12;      // dims 1..12 take part in the distance
                               // the kernel sits at ~78 % of the fp64 issue rate counting the 25 DP instructions per pair)
 #endif
 constexpr int ACC_W = 14;     // per-centroid accumulator row: 13 sums + count
+constexpr int VQ_PRIV_K = 32; // up to this many centroids every warp keeps a private accumulator table
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -45,13 +46,22 @@ k_vq_assign(const double *__restrict__ X, int64_t F, const double *__restrict__ 
             int32_t *__restrict__ idx_out, double *__restrict__ dist_out, double *__restrict__ accum,
             int smem_accum) {
     extern __shared__ double smem[];
-    double *sC = smem;                              // [tile][12]
-    double *sAcc = smem + (size_t)VQ_TILE * VQ_D;   // [K][14] (MODE 1, if smem_accum)
+    double *sC = smem;                                          // [tile][12]
+    double *sAcc = smem + (size_t)min(K, VQ_TILE) * VQ_D;       // [K][14] (MODE 1, if smem_accum)
     __shared__ double sRed[VQ_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31;
+    // Few centroids (Lloyd passes of the first LBG generations): all lanes hit the same handful of rows, so
+    // shared atomics serialise.  Every warp then owns a private [K][14] table: the lanes park their frame and
+    // its key in shared memory and lanes 0..13 (one per accumulator column) walk the 32 frames, adding column
+    // d of frame l to row key[l] — no atomics, no shuffles, cost independent of K.
+    const bool priv = MODE == 1 && smem_accum == 2;
+    double *wAcc = sAcc + (size_t)(tid >> 5) * K * ACC_W;                                       // [K][14] per warp
+    double *wX = sAcc + (size_t)(VQ_THREADS / 32) * K * ACC_W + (size_t)(tid >> 5) * 32 * 13;   // [32][13] per warp
+    int *wKey = reinterpret_cast<int *>(sAcc + (size_t)(VQ_THREADS / 32) * (K * ACC_W + 32 * 13)) + (tid >> 5) * 32;
     if (MODE == 1 && smem_accum) {
-        for (int e = tid; e < K * ACC_W; e += VQ_THREADS) sAcc[e] = 0.0;
+        const int n = priv ? (VQ_THREADS / 32) * K * ACC_W : K * ACC_W;
+        for (int e = tid; e < n; e += VQ_THREADS) sAcc[e] = 0.0;
     }
     double dist_local = 0.0;
     const int ntiles = (K + VQ_TILE - 1) / VQ_TILE;
@@ -117,7 +127,19 @@ k_vq_assign(const double *__restrict__ X, int64_t F, const double *__restrict__ 
         if (MODE == 1) {
             if (valid) dist_local += best_s;
             double *acc = smem_accum ? sAcc : accum;
-            if (K <= 16) {
+            if (priv) {
+#pragma unroll
+                for (int d = 0; d < 13; ++d) wX[lane * 13 + d] = x[d];
+                wKey[lane] = valid ? best : -1;
+                __syncwarp();
+                if (lane < ACC_W) {
+                    for (int l = 0; l < 32; ++l) {
+                        const int k = wKey[l];
+                        if (k >= 0) wAcc[k * ACC_W + lane] += (lane < 13) ? wX[l * 13 + lane] : 1.0;
+                    }
+                }
+                __syncwarp();
+            } else if (K <= 16) {
                 // few centroids: every lane hits the same handful of rows, so reduce per
                 // key across the warp with shuffles and issue one atomic per (key, dim).
                 unsigned remaining = __ballot_sync(0xffffffffu, valid);
@@ -150,7 +172,15 @@ k_vq_assign(const double *__restrict__ X, int64_t F, const double *__restrict__ 
             for (int w = 0; w < VQ_THREADS / 32; ++w) s += sRed[w];
             atomicAdd(accum + (size_t)K * ACC_W, s);
         }
-        if (smem_accum) {
+        if (priv) {
+            __syncthreads();
+            for (int e = tid; e < K * ACC_W; e += VQ_THREADS) {
+                double a = 0.0;
+#pragma unroll
+                for (int w = 0; w < VQ_THREADS / 32; ++w) a += sAcc[(size_t)w * K * ACC_W + e];
+                if (a != 0.0) atomicAdd(accum + e, a);
+            }
+        } else if (smem_accum) {
             for (int e = tid; e < K * ACC_W; e += VQ_THREADS) {
                 double a = sAcc[e];
                 if (a != 0.0) atomicAdd(accum + e, a);
@@ -178,10 +208,17 @@ __global__ void k_lbg_split(const double *__restrict__ C, int K, double *__restr
     C2[(size_t)(2 * k + 1) * 13 + d] = v * 0.999;
 }
 
+// smem_accum: 0 = accumulate straight into global memory, 1 = one shared [K][14] table per CTA,
+// 2 = one private table per warp (K <= VQ_PRIV_K)
 static size_t vq_smem_bytes(int K, int mode, int *smem_accum) {
-    size_t tile = (size_t)VQ_TILE * VQ_D * sizeof(double);
+    size_t tile = (size_t)std::min(K, VQ_TILE) * VQ_D * sizeof(double);
     size_t acc = (size_t)K * ACC_W * sizeof(double);
     *smem_accum = 0;
+    if (mode == 1 && K <= VQ_PRIV_K && !getenv("HMMB_LBG_NO_PRIVATE")) {
+        *smem_accum = 2;
+        const size_t warps = VQ_THREADS / 32;
+        return tile + warps * (acc + 32 * 13 * sizeof(double)) + warps * 32 * sizeof(int);
+    }
     if (mode == 1 && tile + acc <= 200 * 1024) {
         *smem_accum = 1;
         return tile + acc;

@@ -44,7 +44,9 @@ template <int MODE>
 __global__ void __launch_bounds__(VQ_THREADS)
 k_vq_assign(const double *__restrict__ X, int64_t F, const double *__restrict__ C, int K,
             int32_t *__restrict__ idx_out, double *__restrict__ dist_out, double *__restrict__ accum,
-            int smem_accum) {
+            int smem_accum, const int *__restrict__ skip) {
+    // a Lloyd pass queued speculatively after the generation has converged (k_lbg_check) is a no-op
+    if (skip && *skip) return;
     extern __shared__ double smem[];
     double *sC = smem;                                          // [tile][12]
     double *sAcc = smem + (size_t)min(K, VQ_TILE) * VQ_D;       // [K][14] (MODE 1, if smem_accum)
@@ -190,7 +192,32 @@ k_vq_assign(const double *__restrict__ X, int64_t F, const double *__restrict__ 
 }
 
 // new_adjust_centroids: mean of the assigned frames (all 13 dims), zeros(13) if empty.
-__global__ void k_lbg_update(const double *__restrict__ accum, int K, double *__restrict__ C) {
+// Convergence state of one LBG generation, kept on the device so that Lloyd passes can be queued
+// several at a time without a host round trip per pass (codevector_functions.py:475-476, :485, :509-510).
+struct LbgState {
+    double prev, gd;
+    int it, done;
+};
+__global__ void k_lbg_reset(LbgState *st) {
+    st->prev = 0.0;
+    st->gd = 0.0;
+    st->it = 0;
+    st->done = 0;
+}
+// after the centroid update of a pass: count it, compare the summed distance with the previous pass
+__global__ void k_lbg_check(const double *__restrict__ gdp, LbgState *st, double eps) {
+    if (st->done) return;
+    const double gd = *gdp;
+    const double diff = fabs(st->prev - gd);
+    st->it += 1;
+    st->prev = gd;
+    st->gd = gd;
+    if (!(diff > eps)) st->done = 1;  // loop condition `while diff > eps` (:485)
+}
+
+__global__ void k_lbg_update(const double *__restrict__ accum, int K, double *__restrict__ C,
+                             const LbgState *__restrict__ st) {
+    if (st && st->done) return;  // (the flag only changes in k_lbg_check, a separate launch)
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= K * 13) return;
     int k = e / 13, d = e - k * 13;
@@ -227,7 +254,7 @@ static size_t vq_smem_bytes(int K, int mode, int *smem_accum) {
 }
 
 static int vq_launch(int mode, const double *dX, int64_t F, const double *dC, int K, int32_t *d_idx,
-                     double *d_dist, double *d_accum) {
+                     double *d_dist, double *d_accum, const int *d_skip = nullptr) {
     Ctx &c = ctx();
     int smem_accum = 0;
     size_t smem = vq_smem_bytes(K, mode, &smem_accum);
@@ -240,11 +267,11 @@ static int vq_launch(int mode, const double *dX, int64_t F, const double *dC, in
     if (mode == 0) {
         HMMB_CUDA(cudaFuncSetAttribute(k_vq_assign<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HMMB_LAUNCH("vq_encode", k_vq_assign<0>, (unsigned)grid, VQ_THREADS, smem, dX, F, dC, K, d_idx, d_dist,
-                    d_accum, smem_accum);
+                    d_accum, smem_accum, d_skip);
     } else {
         HMMB_CUDA(cudaFuncSetAttribute(k_vq_assign<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HMMB_LAUNCH("lbg_assign", k_vq_assign<1>, (unsigned)grid, VQ_THREADS, smem, dX, F, dC, K, d_idx, d_dist,
-                    d_accum, smem_accum);
+                    d_accum, smem_accum, d_skip);
     }
     return HMMB_OK;
 }
@@ -354,7 +381,7 @@ int hmmb_lbg_fit(const double *X, int64_t F, int x_on_device, int K, int max_ite
         int rc = allreduce(acc, ACC_W + 1, user);
         if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
     }
-    HMMB_LAUNCH("lbg_update", k_lbg_update, 1, 32, 0, acc, 1, cur);
+    HMMB_LAUNCH("lbg_update", k_lbg_update, 1, 32, 0, acc, 1, cur, (const LbgState *)nullptr);
     size_t gpos = 0;
     HMMB_CUDA(cudaMemcpyAsync(gens_out, cur, 13 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     gpos += 13;
@@ -363,24 +390,39 @@ int hmmb_lbg_fit(const double *X, int64_t F, int x_on_device, int K, int max_ite
     int Kg = 2;
     HMMB_CUDA(cudaMemsetAsync(d_idx, 0, (size_t)(F > 0 ? F : 1) * sizeof(int32_t), c.stream));
 
+    DevBuf dState;
+    HMMB_TRY(dev_alloc(&dState.p, sizeof(LbgState)));
+    LbgState *st = dState.as<LbgState>();
+    constexpr int LBG_QUEUE = 8;  // Lloyd passes queued per host round trip
     for (int g = 1; g <= n_gen; ++g) {
-        double prev = 0.0, diff = eps + 100.0, gd = 0.0;  // :475-476
-        int it = 0;
-        while (diff > eps && it < max_iter) {  // :485
-            ++it;
-            HMMB_CUDA(cudaMemsetAsync(acc, 0, ((size_t)Kg * ACC_W + 1) * sizeof(double), c.stream));
-            HMMB_TRY(vq_launch(1, dX, F, cur, Kg, d_idx, nullptr, acc));
-            if (allreduce) {
-                int rc = allreduce(acc, (int64_t)Kg * ACC_W + 1, user);
-                if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+        // Lloyd loop of the generation (:475-514).  The convergence test runs on the device (k_lbg_check); passes
+        // are queued LBG_QUEUE at a time and the ones behind the converged pass return at once, so the host
+        // synchronises once per LBG_QUEUE passes instead of once per pass.
+        HMMB_LAUNCH("lbg_update", k_lbg_reset, 1, 1, 0, st);
+        double *buf[2] = {cur, nxt};
+        LbgState hs{0.0, 0.0, 0, 0};
+        int enq = 0;
+        while (!hs.done && enq < max_iter) {
+            const int n = std::min(LBG_QUEUE, max_iter - enq);
+            for (int i = 0; i < n; ++i) {
+                const int p = enq + i;
+                HMMB_CUDA(cudaMemsetAsync(acc, 0, ((size_t)Kg * ACC_W + 1) * sizeof(double), c.stream));
+                HMMB_TRY(vq_launch(1, dX, F, buf[p & 1], Kg, d_idx, nullptr, acc, &st->done));
+                if (allreduce) {
+                    int rc = allreduce(acc, (int64_t)Kg * ACC_W + 1, user);
+                    if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+                }
+                HMMB_LAUNCH("lbg_update", k_lbg_update, (Kg * 13 + 127) / 128, 128, 0, acc, Kg, buf[(p + 1) & 1], st);
+                HMMB_LAUNCH("lbg_update", k_lbg_check, 1, 1, 0, acc + (size_t)Kg * ACC_W, st, eps);
             }
-            HMMB_LAUNCH("lbg_update", k_lbg_update, (Kg * 13 + 127) / 128, 128, 0, acc, Kg, nxt);
-            HMMB_CUDA(cudaMemcpyAsync(&gd, acc + (size_t)Kg * ACC_W, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+            enq += n;
+            HMMB_CUDA(cudaMemcpyAsync(&hs, st, sizeof(LbgState), cudaMemcpyDeviceToHost, c.stream));
             HMMB_CUDA(cudaStreamSynchronize(c.stream));
-            { double *t = cur; cur = nxt; nxt = t; }
-            diff = fabs(prev - gd);  // :509-510
-            prev = gd;
         }
+        const int it = hs.it;
+        const double gd = hs.gd;
+        cur = buf[it & 1];  // written by the last pass that ran
+        nxt = buf[(it + 1) & 1];
         if (iters_per_gen) iters_per_gen[g - 1] = it;
         if (gdist_out) gdist_out[g - 1] = gd;
         HMMB_CUDA(cudaMemcpyAsync(gens_out + gpos, cur, (size_t)Kg * 13 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));

@@ -147,3 +147,24 @@ def test_allreduce_hook_and_llstats_gather_over_gloo():
         assert abs(comb[0] - want0) < 1e-12 and comb[1] == float("-inf")
         assert abs(comb[2] - O.log_sum_exp(np.array([-7.0 + np.log(1.5), -6.0 + np.log(1.5)]))) < 1e-12
     assert np.array_equal(res[0][1], res[1][1])
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU: exactly one JSON
+    line on stdout with the contract's keys, everything else on stderr."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HMMB_CPU_SEQ_PER_WORD="8")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "baum_welch_frames_per_s_per_iter" and d["value"] > 0
+    for key in ("unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config"):
+        assert key in d
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

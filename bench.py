@@ -273,6 +273,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # torchrun exports OMP_NUM_THREADS=1; give every rank its share of the host cores for the library's
+        # host-side blocking (hmmb_init reads HMMB_HOST_THREADS)
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        os.environ.setdefault("HMMB_HOST_THREADS", str(max(1, min(8, (os.cpu_count() or 1) // max(local_world, 1)))))
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():

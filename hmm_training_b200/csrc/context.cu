@@ -1,4 +1,9 @@
 // Context, error reporting, caching allocator and phase timers of libhmmb200.
+#include <cstdlib>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #include "common.cuh"
 
 namespace hmmb {
@@ -165,6 +170,14 @@ int hmmb_init(int device) {
     HMMB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
     HMMB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+#ifdef _OPENMP
+    // launchers such as torchrun export OMP_NUM_THREADS=1; the host-side blocking of a build is a handful of
+    // memory-bound loops that still gain from a few threads per rank
+    if (const char *t = getenv("HMMB_HOST_THREADS")) {
+        const int n = atoi(t);
+        if (n > 0) omp_set_num_threads(n);
+    }
+#endif
     c.inited = true;
     return HMMB_OK;
 }

@@ -336,6 +336,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from hmm_training_b200 import _lib, engine, synthetic
     from hmm_training_b200 import dist as hdist
+    bound_cpus = hdist.bind_to_gpu_cpus(local_rank) if world > 1 else 0  # NUMA-local pinned buffers and host threads
     lib = _lib.load()
     _lib.init(local_rank)
     hdist.bind_torch_stream()
@@ -466,7 +467,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["desc"], "frames_per_gpu_per_iter": frames_rank, "W": W, "seq_per_word_per_gpu": S,
                        "T": T, "N": N, "M": M, "parallelism": f"sequences sharded over {world} GPU(s), 1 allreduce/iter",
-                       "l2": "inputs larger than L2 (codewords + alpha spill >> 126 MB)"},
+                       "l2": "inputs larger than L2 (codewords + alpha spill >> 126 MB)",
+                       "cpus_bound_per_rank": bound_cpus},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
             "clocks": clk.summary(), "precision_guard": {"exact_sequence_passes": exact_passes,
                                                          "backward_handovers": bwd_handover},

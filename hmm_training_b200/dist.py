@@ -88,3 +88,33 @@ def combine_llstats(stats: Sequence[Tuple[float, float]]) -> float:
         return float("-inf")
     s = sum(sv * np.exp(m - mx) for m, sv in stats if m != float("-inf"))
     return float(mx + np.log(s))
+
+
+def bind_to_gpu_cpus(device_index: int) -> int:
+    """Pin the calling process to the CPUs NVML reports as local to GPU `device_index` (its NUMA node), so
+    that the pinned host buffers it allocates afterwards (first touch) and the library's host threads sit
+    next to that GPU's PCIe root.  With eight ranks uploading at once this is what decides the aggregate
+    host-to-device bandwidth.  Returns the number of CPUs bound to (0 = left unchanged: NVML or the
+    affinity call unavailable, or the container's CPU set does not meet the GPU's)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        phys = device_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(ncpu, 1024) + 63) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = local & allowed
+        if not target or target == allowed:
+            return 0
+        os.sched_setaffinity(0, target)
+        return len(target)
+    except Exception:
+        return 0

@@ -356,8 +356,16 @@ def main():
     launches0 = lib.hmmb_launch_count()
     bw = engine.BaumWelch(obs, offsets, wos, W, N, M)
     bw.set_params(pi0, A0, B0)
+    # default 1 = off: measured on config 4 at 2 GPUs, 4 / 8 groups cost more (7.77 / 7.80 ms per iteration) than the
+    # plain all-reduce after the E-step (7.26 ms): per-group launches serialise the tails of the backward pass
+    overlap_groups = int(os.environ.get("HMMB_OVERLAP_GROUPS", "1"))
+    overlap = world > 1 and bw.kernel_family() == "left_to_right" and overlap_groups > 1
     if world > 1:
-        bw.set_dist(rank, world, hdist.make_allreduce())
+        # left-to-right path (config 4: 133 MB of accumulators): all-reduce per word group on a side stream,
+        # overlapped with the next group's backward pass
+        bw.set_dist(rank, world, hdist.make_allreduce(overlap=overlap))
+        if overlap:
+            bw.set_overlap(overlap_groups)
     cap = args.warmup + args.steps + 8
     smi = SmiLoopSampler(local_rank).start() if (world > 1 and rank == 0) else None
     if smi:
@@ -466,7 +474,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["desc"], "frames_per_gpu_per_iter": frames_rank, "W": W, "seq_per_word_per_gpu": S,
-                       "T": T, "N": N, "M": M, "parallelism": f"sequences sharded over {world} GPU(s), 1 allreduce/iter",
+                       "T": T, "N": N, "M": M, "parallelism": f"sequences sharded over {world} GPU(s), 1 allreduce/iter" +
+                       (f" in {overlap_groups} word groups overlapped with the backward pass" if overlap else ""),
                        "l2": "inputs larger than L2 (codewords + alpha spill >> 126 MB)",
                        "cpus_bound_per_rank": bound_cpus},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,

@@ -50,6 +50,7 @@ SYMBOLS = [
     ("hmmb_bw_destroy", _c.c_int, [_c.c_void_p]),
     ("hmmb_bw_set_params", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     ("hmmb_bw_set_dist", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    ("hmmb_bw_set_overlap", _c.c_int, [_c.c_void_p, _c.c_int]),
     ("hmmb_bw_iterate", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_double, _c.c_int, _c.c_int]),
     ("hmmb_bw_get_params", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     ("hmmb_bw_get_history", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p]),

@@ -662,6 +662,9 @@ struct hmmb_bw {
     int rank = 0, world = 1;
     hmmb_allreduce_fn allreduce = nullptr;
     void *user = nullptr;
+    int overlap_groups = 1;        // > 1: left-to-right E-step in word groups, each group's accumulators all-reduced
+                                   // while the next group's backward pass runs (hmmb_bw_set_overlap)
+    bool estep_reduced = false;    // the E-step just launched did the reduce + all-reduce itself
     bool params_set = false, any_active = true;
 };
 
@@ -922,6 +925,13 @@ int hmmb_bw_set_dist(hmmb_bw_t *h, int rank, int world, hmmb_allreduce_fn allred
     return bw_alloc_accum(h);
 }
 
+int hmmb_bw_set_overlap(hmmb_bw_t *h, int groups) {
+    HMMB_TRY(require_init());
+    if (!h || groups < 1 || groups > 64) { set_error("hmmb_bw_set_overlap: groups must be 1..64"); return HMMB_ERR_ARG; }
+    h->overlap_groups = groups;
+    return HMMB_OK;
+}
+
 static int bw_ensure_hist(hmmb_bw *h, int cap) {
     if (cap <= h->hist_cap) return HMMB_OK;
     Ctx &c = ctx();
@@ -1048,9 +1058,35 @@ static int launch_ltr_estep(hmmb_bw *h) {
     HMMB_LAUNCH("bw_forward", k_bw_fwdL<NS>, s.ncta, LTR_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs, s.d_len,
                 h->d_pi, h->d_A, h->d_Bt, M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag, h->d_allfull);
     HMMB_TRY((launch_exact<uint16_t, true>(h)));
-    HMMB_LAUNCH("bw_backward", k_bw_bwdL<NS>, s.ncta, LTR_THREADS, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs, s.d_len,
-                h->d_A, h->d_Bt, M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero, h->d_allfull,
-                h->d_accum, h->astride, h->d_flag, h->d_newflags);
+    const int groups = (h->allreduce && h->world > 1) ? std::min(h->overlap_groups, h->W) : 1;
+    if (groups <= 1) {
+        HMMB_LAUNCH("bw_backward", k_bw_bwdL<NS>, s.ncta, LTR_THREADS, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs, s.d_len,
+                    h->d_A, h->d_Bt, M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero, h->d_allfull,
+                    h->d_accum, h->astride, h->d_flag, h->d_newflags);
+        return HMMB_OK;
+    }
+    // Communication / compute overlap (config 4: 133 MB of accumulators per iteration).  The convergence
+    // statistic and the sequence counts only need the forward pass, so k_bw_reduce runs first; the backward
+    // pass then goes word group by word group, and each group's slice of the accumulator buffer is handed to the
+    // all-reduce hook as soon as its kernels are queued — the hook runs it on a side stream while the next
+    // group's backward pass computes.  hook(NULL, 0) at the end joins the side stream.
+    HMMB_LAUNCH("bw_reduce", k_bw_reduce, dim3((unsigned)h->W, 1u), RED_THREADS, 0, (const double *)nullptr, h->pstride,
+                h->d_cta_begin, h->d_llseq, h->d_seq_begin, h->d_accum, h->astride, h->nacc,
+                h->d_accum + (size_t)h->W * h->astride, h->rank, h->W, h->d_active);
+    for (int g = 0; g < groups; ++g) {
+        const int w0 = (int)((int64_t)h->W * g / groups), w1 = (int)((int64_t)h->W * (g + 1) / groups);
+        const int c0 = s.cta_begin[w0], c1 = s.cta_begin[w1];
+        if (c1 > c0)
+            HMMB_LAUNCH("bw_backward", k_bw_bwdL<NS>, c1 - c0, LTR_THREADS, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
+                        s.d_len, h->d_A, h->d_Bt, M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero,
+                        h->d_allfull, h->d_accum, h->astride, h->d_flag, h->d_newflags);
+        int rc = h->allreduce(h->d_accum + (size_t)w0 * h->astride, (int64_t)(w1 - w0) * h->astride, h->user);
+        if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+    }
+    int rc = h->allreduce(h->d_accum + (size_t)h->W * h->astride, (int64_t)h->world * h->W * 2, h->user);  // LL statistics
+    if (rc == 0) rc = h->allreduce(nullptr, 0, h->user);                                                     // join
+    if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+    h->estep_reduced = true;
     return HMMB_OK;
 }
 
@@ -1094,8 +1130,11 @@ int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync
         if (!h->any_active) break;
         for (int attempt = 0; attempt < 2; ++attempt) {
             HMMB_CUDA(cudaMemsetAsync(h->d_accum, 0, (size_t)h->accum_n * sizeof(double), c.stream));
+            h->estep_reduced = false;
             HMMB_TRY(bw_estep(h));
-            if (!sync_each) break;
+            // (an E-step that already ran its collectives cannot be redone by one rank alone: backward-pass
+            // hand-overs then only take effect from the next iteration, as with sync_each == 0)
+            if (!sync_each || h->estep_reduced) break;
             // backward-pass hand-overs are discovered after their sequence already contributed:
             // redo this E-step once with them routed to the exact kernel (flags are sticky)
             int32_t nf = 0;
@@ -1106,13 +1145,15 @@ int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync
             h->n_backward_handover += nf;
             HMMB_CUDA(cudaMemsetAsync(h->d_newflags, 0, sizeof(int32_t), c.stream));
         }
-        const dim3 rgrid((unsigned)h->W, h->s.special4 ? (unsigned)((h->nacc + RED_EX - 1) / RED_EX) : 1u);
-        HMMB_LAUNCH("bw_reduce", k_bw_reduce, rgrid, RED_THREADS, 0, h->s.special4 ? h->d_partials : nullptr, h->pstride,
-                    h->d_cta_begin, h->d_llseq, h->d_seq_begin, h->d_accum, h->astride, h->nacc,
-                    h->d_accum + (size_t)h->W * h->astride, h->rank, h->W, h->d_active);
-        if (h->allreduce && h->world > 1) {
-            int rc = h->allreduce(h->d_accum, h->accum_n, h->user);
-            if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+        if (!h->estep_reduced) {
+            const dim3 rgrid((unsigned)h->W, h->s.special4 ? (unsigned)((h->nacc + RED_EX - 1) / RED_EX) : 1u);
+            HMMB_LAUNCH("bw_reduce", k_bw_reduce, rgrid, RED_THREADS, 0, h->s.special4 ? h->d_partials : nullptr, h->pstride,
+                        h->d_cta_begin, h->d_llseq, h->d_seq_begin, h->d_accum, h->astride, h->nacc,
+                        h->d_accum + (size_t)h->W * h->astride, h->rank, h->W, h->d_active);
+            if (h->allreduce && h->world > 1) {
+                int rc = h->allreduce(h->d_accum, h->accum_n, h->user);
+                if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+            }
         }
         HMMB_CUDA(cudaMemsetAsync(h->d_any, 0, sizeof(int32_t), c.stream));
         HMMB_LAUNCH("bw_mstep", k_bw_mstep, h->W, RED_THREADS, 0, h->d_accum, h->astride,

@@ -45,13 +45,27 @@ def bind_torch_stream():
     return s
 
 
-def make_allreduce(group=None, device: str = "cuda"):
+def make_allreduce(group=None, device: str = "cuda", overlap: bool = False):
     """Returns fn(ptr, n_doubles) that sums the buffer in place over the process group.
-    device='cpu' treats ptr as host memory (gloo; used by the CPU tests of the plumbing)."""
+    device='cpu' treats ptr as host memory (gloo; used by the CPU tests of the plumbing).
+    overlap=True (with BaumWelch.set_overlap): every collective runs on a side stream, ordered behind what is
+    queued on the library's stream at the time of the call, so that it overlaps the kernels queued afterwards;
+    the library's closing fn(0, 0) call makes its stream wait for the side stream."""
     import torch
     import torch.distributed as dist
+    comm_stream = torch.cuda.Stream() if (overlap and device != "cpu") else None
 
     def fn(ptr: int, n: int) -> None:
+        if n == 0:  # join
+            if comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(comm_stream)
+            return
+        if comm_stream is not None:
+            comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm_stream):
+                t = torch.as_tensor(_DeviceBuffer(ptr, n), device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return
         if device == "cpu":
             buf = (ctypes.c_double * n).from_address(ptr)
             t = torch.from_numpy(np.frombuffer(buf, dtype=np.float64))

@@ -66,7 +66,7 @@ def _wrap_allreduce(fn: Optional[Callable[[int, int], None]]):
 
     def hook(dev_ptr, n, _user):
         try:
-            fn(dev_ptr, n)
+            fn(dev_ptr or 0, n)  # (NULL, 0) = "join" of an overlapping hook (hmmb_bw_set_overlap)
             return 0
         except Exception as exc:  # pragma: no cover - surfaced through the C error path
             import traceback
@@ -169,6 +169,11 @@ class BaumWelch:
         self._keep = (cfn, keep)
         check(self._lib.hmmb_bw_set_dist(self._h, rank, world, ctypes.cast(cfn, ctypes.c_void_p) if cfn else None,
                                          None))
+
+    def set_overlap(self, groups: int) -> None:
+        """Left-to-right kernels only: run the backward pass in `groups` word groups and hand each group's
+        accumulators to the all-reduce hook as soon as its kernels are queued (use dist.make_allreduce(overlap=True))."""
+        check(self._lib.hmmb_bw_set_overlap(self._h, int(groups)))
 
     def iterate(self, n_iter: int, epsilon: float = 1e-6, max_iterations: int = 100, sync_each: bool = True) -> None:
         check(self._lib.hmmb_bw_iterate(self._h, int(n_iter), float(epsilon), int(max_iterations), int(sync_each)))

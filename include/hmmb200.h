@@ -122,6 +122,15 @@ int hmmb_bw_destroy(hmmb_bw_t *h);
 /* pi0 [W,N], A0 [W,N,N], B0 [W,N,M] linear-space initial parameters; resets iteration state */
 int hmmb_bw_set_params(hmmb_bw_t *h, const double *pi0, const double *A0, const double *B0);
 int hmmb_bw_set_dist(hmmb_bw_t *h, int rank, int world, hmmb_allreduce_fn allreduce, void *user);
+/* Communication / compute overlap for the left-to-right kernels (N = 8 / 16), whose accumulator buffer is large
+ * (133 MB at 1000 words x 16 states x 1024 codewords).  groups > 1: the backward pass runs word group by word
+ * group and the hook is called once per group with that group's slice of the buffer, then once for the
+ * log-likelihood statistics, then once as hook(NULL, 0, user) = "join".  A hook that runs each collective on a
+ * side stream (ordered behind the work queued on hmmb_get_stream() at the time of the call) and makes
+ * hmmb_get_stream() wait for that side stream in the join call overlaps the transfer of group g with the
+ * backward pass of group g+1; a plain synchronous hook must simply ignore the n == 0 call.  With groups > 1 a
+ * backward-pass hand-over takes effect from the next iteration (as with sync_each == 0).  Default 1.      */
+int hmmb_bw_set_overlap(hmmb_bw_t *h, int groups);
 /* run up to n_iter EM iterations (stops early when every word has converged: diff < eps or
  * max_iter reached, :346).  sync_each != 0 checks the device-side "any word active" flag
  * after each iteration; 0 queues all n_iter iterations without a host sync.             */

@@ -35,8 +35,27 @@ out = engine.bw_fit(sobs, soff, wos[mine], W, N, M, np.tile(pi0, (W, 1)), np.til
 X = synthetic.mfcc_mixture(3, 600, K=16)
 lo, hi = hdist.shard_range(600, rank, world)
 C, gens, assign, iters, gd = engine.lbg_fit(X[lo:hi], 32, 100, 0.001, allreduce=hdist.make_allreduce())
+# left-to-right N = 16 models: plain all-reduce vs word groups overlapped with the backward pass
+rng = np.random.default_rng(5)
+N16, M16, W16 = 16, 1024, 6
+corpus = [synthetic.clustered_sequences(rng, 40, N=N16, M=M16, tmin=20, tmax=60, shift=11 * w, spread=32) for w in range(W16)]
+o16, off16, wos16 = synthetic.pack_corpus(corpus, M16)
+mine16 = hdist.shard_sequences_round_robin(wos16, rank, world)
+seqs16 = [o16[off16[r]:off16[r + 1]] for r in mine16]
+so16 = np.concatenate(seqs16); soff16 = np.concatenate([[0], np.cumsum([len(q) for q in seqs16])]).astype(np.int64)
+p16, a16, b16 = engine.default_init(N16, M16)
+init16 = (np.tile(p16, (W16, 1)), np.tile(a16, (W16, 1, 1)), np.tile(b16, (W16, 1, 1)))
+ltr = {}
+for name, groups in (("plain", 1), ("overlap", 3)):
+    with engine.BaumWelch(so16, soff16, wos16[mine16], W16, N16, M16) as bw:
+        bw.set_params(*init16)
+        assert bw.kernel_family() == "left_to_right"
+        bw.set_dist(rank, world, hdist.make_allreduce(overlap=groups > 1))
+        bw.set_overlap(groups)
+        bw.iterate(3, 1e-6, 3)
+        ltr[name] = bw.params() + bw.history(3)
 np.savez(os.environ["HMMB_OUT"] + f".{rank}.npz", pi=out[0], A=out[1], B=out[2], hist=out[3], iters=out[4], C=C,
-         lbg_iters=iters, assign=assign)
+         lbg_iters=iters, assign=assign, **{f"ltr_{k}_{i}": v for k, r in ltr.items() for i, v in enumerate(r)})
 torch.cuda.synchronize()
 _lib.load().hmmb_set_stream(None); _lib.load().hmmb_shutdown()
 dist.barrier()
@@ -63,6 +82,20 @@ def test_two_rank_training_matches_reference_golden(tmp_path):
     assert np.array_equal(r0["iters"], g["iters"])
     assert_close(r0["hist"][:, :10], g["ll_hist"], "ll")
     assert_close(r0["A"], g["A"], "A"); assert_close(r0["B"], g["B"], "B"); assert_close(r0["pi"], g["pi"], "pi")
+    # left-to-right path: ranks agree, overlapped == plain bit for bit, and both match a single-process fit
+    from hmm_training_b200 import engine, synthetic
+    rng = np.random.default_rng(5)
+    N16, M16, W16 = 16, 1024, 6
+    corpus = [synthetic.clustered_sequences(rng, 40, N=N16, M=M16, tmin=20, tmax=60, shift=11 * w, spread=32) for w in range(W16)]
+    o16, off16, wos16 = synthetic.pack_corpus(corpus, M16)
+    p16, a16, b16 = engine.default_init(N16, M16)
+    single = engine.bw_fit(o16, off16, wos16, W16, N16, M16, np.tile(p16, (W16, 1)), np.tile(a16, (W16, 1, 1)),
+                           np.tile(b16, (W16, 1, 1)), max_iterations=3)
+    for i in range(5):
+        assert np.array_equal(r0[f"ltr_plain_{i}"], r1[f"ltr_plain_{i}"], equal_nan=True)
+        assert np.array_equal(r0[f"ltr_plain_{i}"], r0[f"ltr_overlap_{i}"], equal_nan=True)
+        assert np.array_equal(r0[f"ltr_overlap_{i}"], r1[f"ltr_overlap_{i}"], equal_nan=True)
+        assert_close(r0[f"ltr_overlap_{i}"], single[i], f"2-rank left-to-right vs single process [{i}]", rtol=1e-10)
     gl = load_golden("lbg_600_k32")
     assert np.array_equal(r0["lbg_iters"], gl["iters"])
     assert_close(r0["C"], gl["C"], "centroids", atol=1e-12)

@@ -1268,16 +1268,19 @@ static int launch_score_generic(SeqSet &s, int W, const double *d_pi, const doub
 }
 
 template <bool BIDIAG>
-static int launch_score_special(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll, int32_t *d_nan) {
+static int launch_score_special(SeqSet &s, int W, const double *d_pi, const double *d_A, const double *d_Bt, double *d_ll, int32_t *d_nan,
+                                int b0 = 0, int b1 = -1) {
     Ctx &c = ctx();
-    if (s.nblk == 0) return HMMB_OK;
+    if (b1 < 0) b1 = s.nblk;
+    const int nb = b1 - b0;  // blocks [b0, b1) (a stage of the pipelined scorer, or all of them)
+    if (nb <= 0) return HMMB_OK;
     // each CTA re-uses one model's B for several 32-utterance blocks
     int bpc = std::max(BW_WARPS, (s.nblk * W + c.sm_count * 16 - 1) / (c.sm_count * 16));
     bpc = (bpc + BW_WARPS - 1) / BW_WARPS * BW_WARPS;
     bpc = std::min(bpc, 64);
-    dim3 g((unsigned)((s.nblk + bpc - 1) / bpc), (unsigned)W);
+    dim3 g((unsigned)((nb + bpc - 1) / bpc), (unsigned)W);
     const size_t smem = (size_t)s.M * 5 * sizeof(double) + (size_t)((s.M + 15) & ~15);
-    HMMB_LAUNCH("score", k_score4<BIDIAG>, g, BW_THREADS, smem, s.d_blks, s.nblk, bpc, (const uint4 *)s.d_obs, s.d_len,
+    HMMB_LAUNCH("score", k_score4<BIDIAG>, g, BW_THREADS, smem, s.d_blks + b0, nb, bpc, (const uint4 *)s.d_obs, s.d_len,
                 s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll, d_nan);
     return HMMB_OK;
 }
@@ -1309,27 +1312,91 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
         const int ij = (int)(e % (size_t)(N * N)), i = ij / N, j = ij % N;
         if (j != i && j != i + 1 && A[e] > 0.0) ltr = false;
     }
-    HMMB_TRY(seqset_build(s, obs, idx_bytes, obs_on_device, offsets, nullptr, U, 1, N, M, ltr ? LAYOUT_LTR : LAYOUT_AUTO));
-    if (U == 0) return HMMB_OK;
     const size_t nB = (size_t)W * N * M, nA = (size_t)W * N * N, nP = (size_t)W * N;
     double *tmp = nullptr, *d_pi = nullptr, *d_A = nullptr, *d_Bt = nullptr, *d_ll = nullptr;
     int32_t *d_arg = nullptr;
-    HMMB_TRY(dev_alloc_t(&tmp, nB + nA + nP)); guard.ptrs.push_back(tmp);
-    HMMB_TRY(dev_alloc_t(&d_pi, nP)); guard.ptrs.push_back(d_pi);
-    HMMB_TRY(dev_alloc_t(&d_A, nA)); guard.ptrs.push_back(d_A);
-    HMMB_TRY(dev_alloc_t(&d_Bt, nB)); guard.ptrs.push_back(d_Bt);
-    HMMB_TRY(dev_alloc_t(&d_ll, (size_t)U * W)); guard.ptrs.push_back(d_ll);
-    HMMB_TRY(dev_alloc_t(&d_arg, (size_t)U)); guard.ptrs.push_back(d_arg);
     int32_t *d_nan = nullptr;  // set by the scorers when the precision guard marked a pair
-    HMMB_TRY(dev_alloc_t(&d_nan, 1)); guard.ptrs.push_back(d_nan);
-    HMMB_CUDA(cudaMemsetAsync(d_nan, 0, sizeof(int32_t), c.stream));
-    HMMB_CUDA(cudaMemcpyAsync(tmp, B, nB * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    HMMB_CUDA(cudaMemcpyAsync(tmp + nB, A, nA * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    HMMB_CUDA(cudaMemcpyAsync(tmp + nB + nA, pi, nP * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    dim3 gb((unsigned)std::min((N * M + 255) / 256, 64), (unsigned)W);
-    HMMB_LAUNCH("score_load", k_load_B, gb, 256, 0, tmp, N, M, d_Bt, (int32_t *)nullptr);
-    HMMB_LAUNCH("score_load", k_load_clamped, (unsigned)std::min<size_t>((nA + 255) / 256, 1024), 256, 0, tmp + nB, (int64_t)nA, d_A);
-    HMMB_LAUNCH("score_load", k_load_clamped, (unsigned)std::min<size_t>((nP + 255) / 256, 1024), 256, 0, tmp + nB + nA, (int64_t)nP, d_pi);
+    bool models_up = false;
+    // model parameters -> device.  In the pipelined scorer this runs inside seqset_build, between the two halves
+    // of the codeword upload and on the same DMA queue (see hmmb_bw_create_ex).
+    std::function<int()> upload_models = [&]() -> int {
+        models_up = true;
+        if (U == 0) return HMMB_OK;
+        HMMB_TRY(dev_alloc_t(&tmp, nB + nA + nP)); guard.ptrs.push_back(tmp);
+        HMMB_TRY(dev_alloc_t(&d_pi, nP)); guard.ptrs.push_back(d_pi);
+        HMMB_TRY(dev_alloc_t(&d_A, nA)); guard.ptrs.push_back(d_A);
+        HMMB_TRY(dev_alloc_t(&d_Bt, nB)); guard.ptrs.push_back(d_Bt);
+        HMMB_TRY(dev_alloc_t(&d_ll, (size_t)U * W)); guard.ptrs.push_back(d_ll);
+        HMMB_TRY(dev_alloc_t(&d_arg, (size_t)U)); guard.ptrs.push_back(d_arg);
+        HMMB_TRY(dev_alloc_t(&d_nan, 1)); guard.ptrs.push_back(d_nan);
+        HMMB_CUDA(cudaMemsetAsync(d_nan, 0, sizeof(int32_t), c.stream));
+        HMMB_TRY(h2d_small(tmp, B, nB * sizeof(double)));
+        HMMB_TRY(h2d_small(tmp + nB, A, nA * sizeof(double)));
+        HMMB_TRY(h2d_small(tmp + nB + nA, pi, nP * sizeof(double)));
+        HMMB_TRY(h2d_join());
+        dim3 gb((unsigned)std::min((N * M + 255) / 256, 64), (unsigned)W);
+        HMMB_LAUNCH("score_load", k_load_B, gb, 256, 0, tmp, N, M, d_Bt, (int32_t *)nullptr);
+        HMMB_LAUNCH("score_load", k_load_clamped, (unsigned)std::min<size_t>((nA + 255) / 256, 1024), 256, 0, tmp + nB, (int64_t)nA, d_A);
+        HMMB_LAUNCH("score_load", k_load_clamped, (unsigned)std::min<size_t>((nP + 255) / 256, 1024), 256, 0, tmp + nB + nA, (int64_t)nP, d_pi);
+        return HMMB_OK;
+    };
+    // Pipelined scorer (N = 4, pinned codewords in length-descending order, small models): the two halves of the
+    // upload are repacked and scored as they land, and each half's rows of the [U, W] matrix start their way back
+    // to the host while the other half is still being scored.
+    const bool pipeline = !ltr && nB * sizeof(double) <= (size_t(4) << 20) && !getenv("HMMB_SCORE_NO_PIPELINE");
+    HMMB_TRY(seqset_build(s, obs, idx_bytes, obs_on_device, offsets, nullptr, U, 1, N, M, ltr ? LAYOUT_LTR : LAYOUT_AUTO,
+                          pipeline, pipeline ? &upload_models : nullptr));
+    if (U == 0) return HMMB_OK;
+    if (!models_up) HMMB_TRY(upload_models());
+    if (s.pend) {
+        bool bidiag = true;
+        for (size_t e = 0; e < nA && bidiag; ++e) {
+            const int ij = (int)(e % 16), i = ij / 4, j = ij % 4;
+            if (j != i && j != i + 1 && A[e] > 0.0) bidiag = false;
+        }
+        PendingPrepare &p = *s.pend;
+        int bdone = 0;
+        cudaEvent_t scored = event_get();
+        for (int j = 0; j < p.nstage; ++j) {
+            HMMB_CUDA(cudaStreamWaitEvent(c.stream, p.up->ev[p.ev_index[j]], 0));
+            HMMB_TRY(launch_repack_range(s, p.up->d_raw, p.idx_bytes, bdone, p.blk_end[j], s.d_bad));
+            HMMB_TRY(bidiag ? launch_score_special<true>(s, W, d_pi, d_A, d_Bt, d_ll, d_nan, bdone, p.blk_end[j])
+                            : launch_score_special<false>(s, W, d_pi, d_A, d_Bt, d_ll, d_nan, bdone, p.blk_end[j]));
+            if (ll_out) {
+                // scoring has a single "word", so block b holds utterances [32 b, 32 b + 32) of the (identity) order
+                const int64_t u0 = (int64_t)bdone * 32, u1 = std::min<int64_t>(U, (int64_t)p.blk_end[j] * 32);
+                HMMB_CUDA(cudaEventRecord(scored, c.stream));
+                HMMB_CUDA(cudaStreamWaitEvent(c.d2h_stream, scored, 0));
+                HMMB_CUDA(cudaMemcpyAsync(ll_out + u0 * W, d_ll + u0 * W, (size_t)(u1 - u0) * W * sizeof(double),
+                                          cudaMemcpyDeviceToHost, c.d2h_stream));
+            }
+            bdone = p.blk_end[j];
+        }
+        event_put(scored);
+        HMMB_LAUNCH("score_argmax", k_argmax_first, (unsigned)((U + 255) / 256), 256, 0, d_ll, U, W, d_arg);
+        int32_t flags[2] = {0, 0};
+        HMMB_CUDA(cudaMemcpyAsync(&flags[0], d_nan, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        HMMB_CUDA(cudaMemcpyAsync(&flags[1], s.d_bad, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        if (argmax_out) HMMB_CUDA(cudaMemcpyAsync(argmax_out, d_arg, (size_t)U * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        HMMB_CUDA(cudaStreamSynchronize(c.stream));
+        HMMB_CUDA(cudaStreamSynchronize(c.d2h_stream));
+        s.pend.reset();
+        if (flags[1]) {
+            set_error("codeword out of range: some observation is >= M=%d (reference: IndexError)", M);
+            return HMMB_ERR_RANGE;
+        }
+        if (flags[0]) {
+            // rare: the precision guard marked pairs; recompute them in log space and send everything again
+            const int64_t warps = std::min<int64_t>((int64_t)c.sm_count * 16, U);
+            const int eg = (int)std::max<int64_t>(1, (warps + BW_WARPS - 1) / BW_WARPS);
+            HMMB_LAUNCH("score_exact", (k_score_exact<uint16_t, true>), eg, BW_THREADS, 0, s.d_obs, s.d_foff, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll, d_nan);
+            HMMB_LAUNCH("score_argmax", k_argmax_first, (unsigned)((U + 255) / 256), 256, 0, d_ll, U, W, d_arg);
+            if (ll_out) HMMB_CUDA(cudaMemcpyAsync(ll_out, d_ll, (size_t)U * W * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+            if (argmax_out) HMMB_CUDA(cudaMemcpyAsync(argmax_out, d_arg, (size_t)U * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+            HMMB_CUDA(cudaStreamSynchronize(c.stream));
+        }
+        return HMMB_OK;
+    }
     int rc;
     if (s.special4) {
         bool bidiag = true;

@@ -170,6 +170,7 @@ int hmmb_init(int device) {
     HMMB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
     HMMB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    HMMB_CUDA(cudaStreamCreateWithFlags(&c.d2h_stream, cudaStreamNonBlocking));
 #ifdef _OPENMP
     // launchers such as torchrun export OMP_NUM_THREADS=1; the host-side blocking of a build is a handful of
     // memory-bound loops that still gain from a few threads per rank
@@ -202,7 +203,8 @@ int hmmb_shutdown(void) {
     c.event_pool.clear();
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
-    c.own_stream = c.stream = c.copy_stream = nullptr;
+    if (c.d2h_stream) cudaStreamDestroy(c.d2h_stream);
+    c.own_stream = c.stream = c.copy_stream = c.d2h_stream = nullptr;
     c.inited = false;
     return HMMB_OK;
 }

@@ -246,3 +246,52 @@ def test_pipelined_upload_matches_plain_create():
             _lib.load().hmmb_host_free(h16)
     finally:
         _lib.load().hmmb_host_free(handle)
+
+
+@pytest.mark.parametrize("tiny", [False, True])
+def test_pipelined_scorer_matches_plain(tiny, monkeypatch):
+    """Recognition on a large PINNED codeword buffer runs in two stages behind the upload, with each half's
+    rows of the [U, W] matrix copied back while the other half is scored; results must equal the unpipelined
+    path bit for bit — also when the precision guard marks pairs (denormal emissions) and everything is sent
+    again after the exact log-space recomputation."""
+    from hmm_training_b200 import _lib, engine
+    rng = np.random.default_rng(17)
+    N, M, W, U, T = 4, 16 if tiny else 256, 6, 400_000, 90  # 36 MB of codewords -> two upload chunks / stages
+    if tiny:
+        pi = np.zeros((W, N)); pi[:, 0] = 1.0
+        A = np.zeros((W, N, N))
+        for i in range(N):
+            A[:, i, i] = 0.7
+            A[:, i, min(i + 1, N - 1)] += 0.3
+        B = rng.dirichlet(np.ones(M), size=(W, N))
+        tiny_vals = np.array([1e-300, 3e-310, 1e-320, 4.9e-324, 0.0, 1e-250])
+        for w in range(W):
+            for k in range(M):
+                if k % 3 == w % 3:
+                    keep = rng.integers(0, N)
+                    for j in range(N):
+                        if j != keep:
+                            B[w, j, k] = tiny_vals[rng.integers(0, len(tiny_vals))]
+        obs = rng.integers(0, M, size=U * T).astype(np.uint8)
+    else:
+        pi0, A0, B0 = engine.default_init(N, M)
+        pi, A = np.tile(pi0, (W, 1)), np.tile(A0, (W, 1, 1))
+        B = rng.dirichlet(np.ones(M) * 0.3, size=(W, N))
+        obs, _, _ = synthetic.fixed_length_codewords(5, 4, U // 4, T, N, M)
+    offsets = np.arange(U + 1, dtype=np.int64) * T
+    pinned, handle = _pinned_copy(obs)
+    try:
+        monkeypatch.delenv("HMMB_SCORE_NO_PIPELINE", raising=False)
+        ll, arg = engine.score(pinned, offsets, N, M, pi, A, B)
+        monkeypatch.setenv("HMMB_SCORE_NO_PIPELINE", "1")
+        ll0, arg0 = engine.score(pinned, offsets, N, M, pi, A, B)
+        assert np.array_equal(ll, ll0, equal_nan=True) and np.array_equal(arg, arg0)
+        assert not np.isnan(ll).any()
+        if tiny:
+            fin = np.isfinite(ll)
+            assert fin.any() and (ll[fin] < -700).any()  # the denormal / exact paths were exercised
+        sub = slice(0, 300)
+        ref = O.score_batch([obs[u * T:(u + 1) * T].astype(np.int64) for u in range(300)], [(A[w], B[w], pi[w]) for w in range(W)])
+        assert_close(ll[sub], ref, "pipelined scorer vs oracle")
+    finally:
+        _lib.load().hmmb_host_free(handle)

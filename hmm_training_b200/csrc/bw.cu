@@ -34,6 +34,21 @@ __global__ void k_load_clamped(const double *__restrict__ src, int64_t n, double
 __global__ void k_fill(double *p, int64_t n, double v) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) p[e] = v;
 }
+// Per-sequence metadata that follows from the block table of the blocked layouts (uint4 row of the lane, word,
+// identity order): filled on the device instead of crossing PCIe (16 of the 28 bytes per sequence).
+__global__ void k_meta_blocked(const Blk *__restrict__ blks, int nblk, int64_t *__restrict__ foff, int32_t *__restrict__ word,
+                               int32_t *__restrict__ order) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < nblk; b += gridDim.x * wpb) {
+        const Blk k = blks[b];
+        if (lane < k.nseq) {
+            const int64_t i = (int64_t)k.first + lane;
+            foff[i] = k.obs_base + lane;
+            word[i] = k.word;
+            if (order) order[i] = (int32_t)i;
+        }
+    }
+}
 __global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) p[e] = v;
 }
@@ -195,7 +210,7 @@ struct EarlyUpload {
 // which then runs stage by stage (repack -> forward -> backward of the CTAs whose codewords have
 // landed) while the later chunks are still crossing PCIe.
 struct PendingPrepare {
-    static constexpr int MAX_STAGES = 2;  // = the two halves of the upload: a stage still fills every SM
+    static constexpr int MAX_STAGES = EarlyUpload::MAX_CHUNKS;  // the trainer runs one stage per chunk on alternating streams
     std::unique_ptr<EarlyUpload> up;
     int idx_bytes = 1;
     int nstage = 0;
@@ -203,6 +218,19 @@ struct PendingPrepare {
     int blk_end[MAX_STAGES] = {};    // blocks [.., blk_end) have all their codewords on the device after the stage
     int cta_end[MAX_STAGES] = {};    // CTA work items [.., cta_end) only touch those blocks
 };
+
+// stages of the pipelined first E-step (HMMB_PIPE_STAGES overrides).  Measured on config 3 (8 upload chunks, 1120
+// CTAs): 2 stages 6.8 ms per fit call, 4 stages on two streams 6.1 ms, 8 stages 7.9 ms — a CTA's own duration
+// (~1.6 ms for repack + forward + backward of its 28 blocks) bounds the tail behind the last chunk, and eight
+// stages leave only 280 of the 592 CTA slots busy.
+static int pipeline_stages() {
+    const char *e = getenv("HMMB_PIPE_STAGES");
+    return e ? std::max(1, std::min(atoi(e), (int)PendingPrepare::MAX_STAGES)) : 4;
+}
+static int score_stages() {
+    const char *e = getenv("HMMB_SCORE_STAGES");
+    return e ? std::max(1, std::min(atoi(e), (int)PendingPrepare::MAX_STAGES)) : 3;  // 1M utterances: 6.8 / 6.5 / 6.9 ms at 2 / 3 / 4
+}
 
 // ---------------------------------------------------------------- sequence set (shared by BW and scoring)
 struct SeqSet {
@@ -334,7 +362,7 @@ static bool ltr_shape_ok(int N, int M) {
 
 static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_device, const int64_t *offsets,
                         const int32_t *word_of_seq, int64_t R, int W, int N, int M, int layout, bool defer = false,
-                        const std::function<int()> *mid_hook = nullptr) {
+                        const std::function<int()> *mid_hook = nullptr, int max_stages = 2) {
     Ctx &c = ctx();
     const bool timing = getenv("HMMB_TIMING") != nullptr;
     const double t0 = now_ms();
@@ -374,13 +402,18 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
                 up.ev[k] = event_get();
                 up.nchunk = k + 1;
             }
-            HMMB_TRY(up.issue((nchunk + 1) / 2));
+            // as many chunks as the host-side pass below takes (~1 ms per million sequences); the metadata goes
+            // next in the DMA queue, the rest of the codewords behind it
+            const char *fe = getenv("HMMB_UPLOAD_FIRST");
+            HMMB_TRY(up.issue(fe ? std::max(1, atoi(fe)) : std::max(1, nchunk / 4)));
             c.h2d_on_copy = true;
         }
     }
 
-    // Per-sequence metadata is staged in ONE pinned host buffer (cached in the context) and goes
-    // to the device with a single copy: [off int64 | foff int64 | len int32 | word int32 | order int32].
+    // Per-sequence metadata is staged in ONE pinned host buffer (cached in the context) and goes to the device
+    // with a single copy: [off int64 | len int32 | order int32 | foff int64 | word int32].  The blocked layouts
+    // only send the first 12 (input in sorted order) or 16 bytes per sequence: the rest follows from the block
+    // table (k_meta_blocked).
     const size_t nR = (size_t)std::max<int64_t>(R, 1);
     const size_t meta_bytes = nR * (2 * sizeof(int64_t) + 3 * sizeof(int32_t));
     if (c.stage_busy) {  // the previous build's metadata copy (possibly still queued behind a codeword upload)
@@ -400,29 +433,45 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         c.stage_bytes = meta_bytes + (meta_bytes >> 2);
     }
     int64_t *off_s = reinterpret_cast<int64_t *>(c.stage);
-    int64_t *foff_s = off_s + nR;
-    int32_t *len_s = reinterpret_cast<int32_t *>(foff_s + nR);
-    int32_t *word_s = len_s + nR;
-    int32_t *order_s = word_s + nR;
+    int32_t *len_s = reinterpret_cast<int32_t *>(off_s + nR);
+    int32_t *order_s = len_s + nR;
+    int64_t *foff_s = reinterpret_cast<int64_t *>(order_s + nR);
+    int32_t *word_s = reinterpret_cast<int32_t *>(foff_s + nR);
 
-    // (a context-owned scratch vector: a fresh 4 MB vector per build costs more in page faults than the loop)
+    // One pass: validate, lengths, "already in (word, length descending) order?", and the staging arrays filled
+    // for that (usual) case; only an unsorted input pays for the sort and a second fill.
+    // (len: a context-owned scratch vector — a fresh 4 MB vector per build costs more in page faults than the loop)
     std::vector<int32_t> &len = c.len_scratch;
     if ((int64_t)len.size() < R) len.resize((size_t)R);
     int bad_kind = 0;
     int64_t bad_at = -1;
-#pragma omp parallel for schedule(static) if (R > 65536)
+    int unsorted = 0;
+    int tmax_all = 0;
+    auto clamp_len = [](int64_t T) { return (int32_t)(T > 0 && T <= (1 << 30) ? T : 0); };
+#pragma omp parallel for schedule(static) reduction(| : unsorted) reduction(max : tmax_all) if (R > 65536)
     for (int64_t r = 0; r < R; ++r) {
         const int64_t T = offsets[r + 1] - offsets[r];
+        const int32_t wb = word_of_seq ? word_of_seq[r] : 0;
         int kind = 0;
         if (T == 0) kind = 1;
         else if (T < 0) kind = 2;
         else if (T > (1 << 30)) kind = 3;
-        else if (word_of_seq && (word_of_seq[r] < 0 || word_of_seq[r] >= W)) kind = 4;
+        else if (wb < 0 || wb >= W) kind = 4;
         if (kind) {
 #pragma omp critical
             if (bad_at < 0 || r < bad_at) { bad_at = r; bad_kind = kind; }
         }
-        len[r] = (int32_t)(T > 0 && T <= (1 << 30) ? T : 0);
+        const int32_t l = clamp_len(T);
+        len[r] = l;
+        if (r > 0) {
+            const int32_t wa = word_of_seq ? word_of_seq[r - 1] : 0;
+            if (wa > wb || (wa == wb && clamp_len(offsets[r] - offsets[r - 1]) < l)) unsorted |= 1;
+        }
+        order_s[r] = (int32_t)r;
+        off_s[r] = offsets[r] - offsets[0];
+        len_s[r] = l;
+        word_s[r] = wb;
+        tmax_all = std::max(tmax_all, (int)l);
     }
     if (bad_kind == 1) {
         // reference: IndexError at hmm_training.py:376 / hmm_testing.py:75 for an empty recording
@@ -439,32 +488,22 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         return HMMB_ERR_ARG;
     }
     s.frames = R > 0 ? offsets[R] - offsets[0] : 0;
-    int unsorted = 0;
-#pragma omp parallel for schedule(static) reduction(| : unsorted) if (R > 65536)
-    for (int64_t r = 1; r < R; ++r) {
-        const int wa = word_of_seq ? word_of_seq[r - 1] : 0, wb = word_of_seq ? word_of_seq[r] : 0;
-        if (wa > wb || (wa == wb && len[r - 1] < len[r])) unsorted |= 1;
-    }
     if (unsorted) {
-        std::iota(order_s, order_s + R, 0);
         std::stable_sort(order_s, order_s + R, [&](int32_t x, int32_t y) {
             const int wx = word_of_seq ? word_of_seq[x] : 0, wy = word_of_seq ? word_of_seq[y] : 0;
             if (wx != wy) return wx < wy;
             return len[x] > len[y];
         });
+#pragma omp parallel for schedule(static) if (R > 65536)
+        for (int64_t i = 0; i < R; ++i) {
+            const int32_t r = order_s[i];
+            off_s[i] = offsets[r] - offsets[0];
+            len_s[i] = len[r];
+            word_s[i] = word_of_seq ? word_of_seq[r] : 0;
+        }
     }
     const int nwords = word_of_seq ? W : 1;
     s.seq_begin.assign(nwords + 1, 0);
-    int tmax_all = 0;
-#pragma omp parallel for schedule(static) reduction(max : tmax_all) if (R > 65536)
-    for (int64_t i = 0; i < R; ++i) {
-        const int32_t r = unsorted ? order_s[i] : (int32_t)i;
-        order_s[i] = r;
-        off_s[i] = offsets[r] - offsets[0];
-        len_s[i] = len[r];
-        word_s[i] = word_of_seq ? word_of_seq[r] : 0;
-        tmax_all = std::max(tmax_all, (int)len[r]);
-    }
     s.tmax_all = tmax_all;
     // sequences of a word are contiguous in the sorted order: word boundaries by binary search
     for (int w = 0; w < nwords; ++w)
@@ -504,10 +543,6 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         }
         word_blk_begin[nwords] = (int)blks.size();
         s.nblk = (int)blks.size();
-        // uint4 row of every sequence's lane in the blocked layout (used by the exact kernels)
-#pragma omp parallel for schedule(static) if (s.nblk > 2048)
-        for (int b = 0; b < s.nblk; ++b)
-            for (int l = 0; l < blks[b].nseq; ++l) foff_s[blks[b].first + l] = blks[b].obs_base + l;
         // CTA work items: ~8 CTAs per SM in total (N = 4; the left-to-right kernels run one
         // 8-warp CTA per SM: ~4 per SM), at least one warp-round each
         const int target = s.special4 ? c.sm_count * 8 : c.sm_count * 4;
@@ -533,12 +568,13 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     // ---- device buffers
     HMMB_TRY(dev_alloc(&s.d_meta, meta_bytes));
     s.d_off = reinterpret_cast<int64_t *>(s.d_meta);
-    s.d_foff = s.d_off + nR;
-    s.d_len = reinterpret_cast<int32_t *>(s.d_foff + nR);
-    s.d_word = s.d_len + nR;
-    s.d_order = s.d_word + nR;
+    s.d_len = reinterpret_cast<int32_t *>(s.d_off + nR);
+    s.d_order = s.d_len + nR;
+    s.d_foff = reinterpret_cast<int64_t *>(s.d_order + nR);
+    s.d_word = reinterpret_cast<int32_t *>(s.d_foff + nR);
     if (R > 0) {
-        HMMB_TRY(h2d_small(s.d_meta, c.stage, meta_bytes));
+        const size_t sent = !s.blocked() ? meta_bytes : nR * (unsorted ? 16 : 12);
+        HMMB_TRY(h2d_small(s.d_meta, c.stage, sent));
         c.stage_busy = event_get();
         HMMB_CUDA(cudaEventRecord(c.stage_busy, c.h2d_on_copy ? c.copy_stream : c.stream));
     }
@@ -558,7 +594,10 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     if (mid_hook) HMMB_TRY((*mid_hook)());
     HMMB_TRY(h2d_join());
     c.h2d_on_copy = false;
-    if (up.active()) HMMB_TRY(up.issue(up.nchunk));  // second half of the codewords, behind the metadata
+    if (up.active()) HMMB_TRY(up.issue(up.nchunk));  // the rest of the codewords, behind the metadata
+    if (s.blocked() && s.nblk > 0)
+        HMMB_LAUNCH("prepare", k_meta_blocked, std::min((s.nblk + 7) / 8, c.sm_count * 8), 256, 0, s.d_blks, s.nblk, s.d_foff,
+                    s.d_word, unsorted ? (int32_t *)nullptr : s.d_order);
     // raw codewords -> device (if needed) -> canonical layout
     const void *d_in = obs;
     void *d_tmp = nullptr;
@@ -582,10 +621,10 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         // leave the repack to the first E-step (bw_estep): record which blocks / CTA work items each stage completes
         std::unique_ptr<PendingPrepare> p(new PendingPrepare());
         p->idx_bytes = idx_bytes;
-        p->nstage = std::min<int>(PendingPrepare::MAX_STAGES, up.nchunk);
+        p->nstage = std::max(1, std::min<int>(std::min<int>(PendingPrepare::MAX_STAGES, max_stages), up.nchunk));
         int bdone = 0, cdone = 0;
         for (int j = 0; j < p->nstage; ++j) {
-            const int k = (p->nstage == 2 && j == 0) ? (up.nchunk + 1) / 2 - 1 : up.nchunk - 1;
+            const int k = (j + 1) * up.nchunk / p->nstage - 1;  // the stage is complete when chunk k has landed
             p->ev_index[j] = k;
             bdone = (j == p->nstage - 1) ? s.nblk : blocks_within(blks, bdone, off_s, len_s, idx_bytes, up.hi[k]);
             while (cdone < s.ncta && work[cdone].blk_end <= bdone) ++cdone;
@@ -795,7 +834,7 @@ int hmmb_bw_create_ex(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_o
     };
     const bool pipeline = (flags & HMMB_BW_PIPELINE_UPLOAD) != 0 && !h->has_ltr;
     rc = seqset_build(h->s, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_AUTO, pipeline,
-                      pipeline ? &finish : nullptr);
+                      pipeline ? &finish : nullptr, pipeline_stages());
     if (rc != HMMB_OK) return fail(rc);
     if (h->has_ltr) {
         rc = seqset_build(h->sl, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_LTR);
@@ -999,10 +1038,24 @@ static int launch_special_estep(hmmb_bw *h) {
     if (s.pend) {
         // first E-step of a pipelined fit: stage j = the blocks whose codewords have landed (copy-stream event),
         // repacked and pushed through forward + backward while the next chunks are still on PCIe
+        // A stage is a fraction of a wave of CTAs, so consecutive stages go to two alternating side streams:
+        // the next stage's repack and forward pass fill the SMs that the tail of this stage's backward pass
+        // leaves idle.  Everything a stage writes (blocked codewords, spill, per-sequence results, per-CTA
+        // partials) is private to its blocks; the compute stream joins both side streams afterwards.
         PendingPrepare &p = *s.pend;
         int bdone = 0, cdone = 0;
         cudaEvent_t tdone[PendingPrepare::MAX_STAGES] = {}, tbeg[PendingPrepare::MAX_STAGES] = {};
+        cudaStream_t main_stream = c.stream;
+        const bool side = p.nstage > 2 && !getenv("HMMB_PIPE_ONE_STREAM");
+        struct Restore { Ctx &c; cudaStream_t s; ~Restore() { c.stream = s; } } restore{c, main_stream};
+        if (side) {
+            cudaEvent_t fork = event_get();
+            HMMB_CUDA(cudaEventRecord(fork, main_stream));
+            for (auto st : c.stage_stream) HMMB_CUDA(cudaStreamWaitEvent(st, fork, 0));
+            event_put(fork);
+        }
         for (int j = 0; j < p.nstage; ++j) {
+            if (side) c.stream = c.stage_stream[j & 1];
             HMMB_CUDA(cudaStreamWaitEvent(c.stream, p.up->ev[p.ev_index[j]], 0));
             if (p.up->t0) { cudaEventCreate(&tbeg[j]); cudaEventRecord(tbeg[j], c.stream); }
             HMMB_TRY(launch_repack_range(s, p.up->d_raw, p.idx_bytes, bdone, p.blk_end[j], s.d_bad));
@@ -1010,6 +1063,15 @@ static int launch_special_estep(hmmb_bw *h) {
             if (p.up->t0) { cudaEventCreate(&tdone[j]); cudaEventRecord(tdone[j], c.stream); }
             bdone = p.blk_end[j];
             cdone = p.cta_end[j];
+        }
+        c.stream = main_stream;
+        if (side) {
+            for (auto st : c.stage_stream) {
+                cudaEvent_t join = event_get();
+                HMMB_CUDA(cudaEventRecord(join, st));
+                HMMB_CUDA(cudaStreamWaitEvent(main_stream, join, 0));
+                event_put(join);
+            }
         }
         if (p.up->t0) {  // HMMB_TIMING: where the upload chunks and the stages sit on one time line
             cudaStreamSynchronize(c.stream);
@@ -1345,7 +1407,7 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
     // to the host while the other half is still being scored.
     const bool pipeline = !ltr && nB * sizeof(double) <= (size_t(4) << 20) && !getenv("HMMB_SCORE_NO_PIPELINE");
     HMMB_TRY(seqset_build(s, obs, idx_bytes, obs_on_device, offsets, nullptr, U, 1, N, M, ltr ? LAYOUT_LTR : LAYOUT_AUTO,
-                          pipeline, pipeline ? &upload_models : nullptr));
+                          pipeline, pipeline ? &upload_models : nullptr, score_stages()));
     if (U == 0) return HMMB_OK;
     if (!models_up) HMMB_TRY(upload_models());
     if (s.pend) {

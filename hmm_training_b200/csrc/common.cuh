@@ -51,6 +51,7 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;  // H2D of raw codewords, overlapped with host prep and repack
     std::vector<int32_t> len_scratch;    // per-sequence lengths of the build in progress (host)
     cudaStream_t d2h_stream = nullptr;   // results leaving while later stages still compute (pipelined scorer)
+    cudaStream_t stage_stream[2] = {nullptr, nullptr};  // pipelined first E-step: stages alternate between these
     bool h2d_on_copy = false;            // small H2D copies of the running build go through copy_stream too
     int64_t launches = 0;
     bool profiling = false;

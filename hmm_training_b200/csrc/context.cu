@@ -171,6 +171,7 @@ int hmmb_init(int device) {
     c.stream = c.own_stream;
     HMMB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     HMMB_CUDA(cudaStreamCreateWithFlags(&c.d2h_stream, cudaStreamNonBlocking));
+    for (auto &st : c.stage_stream) HMMB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
 #ifdef _OPENMP
     // launchers such as torchrun export OMP_NUM_THREADS=1; the host-side blocking of a build is a handful of
     // memory-bound loops that still gain from a few threads per rank
@@ -204,6 +205,10 @@ int hmmb_shutdown(void) {
     if (c.own_stream) cudaStreamDestroy(c.own_stream);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     if (c.d2h_stream) cudaStreamDestroy(c.d2h_stream);
+    for (auto &st : c.stage_stream) {
+        if (st) cudaStreamDestroy(st);
+        st = nullptr;
+    }
     c.own_stream = c.stream = c.copy_stream = c.d2h_stream = nullptr;
     c.inited = false;
     return HMMB_OK;

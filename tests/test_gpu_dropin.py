@@ -210,14 +210,22 @@ def _pinned_copy(a):
     return buf, p
 
 
-def test_pipelined_upload_matches_plain_create():
+@pytest.mark.parametrize("S,ragged", [(40000, False), (80000, False), (60000, True)])
+def test_pipelined_upload_matches_plain_create(S, ragged):
     """engine.bw_fit on a large PINNED codeword buffer takes the pipelined path (chunked upload on the
     copy stream, first E-step in stages behind it, parameters uploaded by the create); results must be
     bit-identical to create + set_params + iterate on the same data, and a codeword >= M must still
-    surface as IndexError."""
+    surface as IndexError.  36 MB of codewords: two upload chunks -> two stages on the compute stream;
+    72 MB: four stages alternating between the two side streams; ragged: stage boundaries from the
+    sequence offsets (lengths descending inside each word, as the blocked layout wants them)."""
     from hmm_training_b200 import _lib, engine
-    N, M, W, S, T = 4, 256, 6, 40000, 150  # 36 MB of codewords: two upload chunks -> two pipeline stages
+    N, M, W, T = 4, 256, 6, 150
     obs, offsets, wos = synthetic.fixed_length_codewords(3, W, S, T, N, M)
+    if ragged:
+        rng = np.random.default_rng(11)
+        lens = np.concatenate([np.sort(rng.integers(120, 2 * T + 1, size=S))[::-1] for _ in range(W)]).astype(np.int64)
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        obs = rng.integers(0, M, size=int(offsets[-1])).astype(np.uint8)
     pi0, A0, B0 = engine.default_init(N, M)
     pi0, A0, B0 = np.tile(pi0, (W, 1)), np.tile(A0, (W, 1, 1)), np.tile(B0, (W, 1, 1))
     pinned, handle = _pinned_copy(obs)

@@ -608,7 +608,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
             d_in = up.d_raw;  // already on its way (copy stream); launch_prepare waits on the chunk events
         } else if (!obs_on_device) {
             HMMB_TRY(dev_alloc(&d_tmp, in_bytes));
-            HMMB_CUDA(cudaMemcpyAsync(d_tmp, src, in_bytes, cudaMemcpyHostToDevice, c.stream));
+            HMMB_TRY(h2d_big(d_tmp, src, in_bytes, c.stream));  // pageable codewords: through the pinned bounce buffers
             d_in = d_tmp;
         } else {
             d_in = src;
@@ -881,7 +881,7 @@ static int bw_set_params_impl(hmmb_bw *h, const double *pi0, const double *A0, c
     const size_t nB = (size_t)W * N * M, nA = (size_t)W * N * N, nP = (size_t)W * N;
     HMMB_TRY(dev_alloc_t(&tmp, nB + nA + nP));
     if (sync) {
-        HMMB_CUDA(cudaMemcpyAsync(tmp, B0, nB * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        HMMB_TRY(h2d_big(tmp, B0, nB * sizeof(double), c.stream));
         HMMB_CUDA(cudaMemcpyAsync(tmp + nB, A0, nA * sizeof(double), cudaMemcpyHostToDevice, c.stream));
         HMMB_CUDA(cudaMemcpyAsync(tmp + nB + nA, pi0, nP * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     } else {
@@ -904,7 +904,7 @@ static int bw_set_params_impl(hmmb_bw *h, const double *pi0, const double *A0, c
             c.pstage_bytes = bytes;
         }
         double *ps = static_cast<double *>(c.pstage);
-        memcpy(ps, B0, nB * sizeof(double));
+        par_memcpy(ps, B0, nB * sizeof(double));
         memcpy(ps + nB, A0, nA * sizeof(double));
         memcpy(ps + nB + nA, pi0, nP * sizeof(double));
         HMMB_TRY(h2d_small(tmp, ps, bytes));
@@ -1248,7 +1248,7 @@ int hmmb_bw_get_params(hmmb_bw_t *h, int finalize, double *pi, double *A, double
     HMMB_TRY(dev_alloc_t(&tmp, nB + nA + nP));
     HMMB_LAUNCH("bw_finalize", k_bw_finalize, W, RED_THREADS, 0, h->d_pi, h->d_A, h->d_Bt, N, M, finalize, tmp + nB + nA,
                 tmp + nB, tmp);
-    if (B) HMMB_CUDA(cudaMemcpyAsync(B, tmp, nB * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (B) HMMB_TRY(d2h_big(B, tmp, nB * sizeof(double), c.stream));
     if (A) HMMB_CUDA(cudaMemcpyAsync(A, tmp + nB, nA * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     if (pi) HMMB_CUDA(cudaMemcpyAsync(pi, tmp + nB + nA, nP * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     HMMB_CUDA(cudaStreamSynchronize(c.stream));
@@ -1418,13 +1418,16 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
         }
         PendingPrepare &p = *s.pend;
         int bdone = 0;
+        // a pageable result matrix cannot leave stage by stage (its copies would block the host between the
+        // stages): it goes through the bounce buffers after the last stage
+        const bool ll_pinned = ll_out && host_is_pinned(ll_out);
         cudaEvent_t scored = event_get();
         for (int j = 0; j < p.nstage; ++j) {
             HMMB_CUDA(cudaStreamWaitEvent(c.stream, p.up->ev[p.ev_index[j]], 0));
             HMMB_TRY(launch_repack_range(s, p.up->d_raw, p.idx_bytes, bdone, p.blk_end[j], s.d_bad));
             HMMB_TRY(bidiag ? launch_score_special<true>(s, W, d_pi, d_A, d_Bt, d_ll, d_nan, bdone, p.blk_end[j])
                             : launch_score_special<false>(s, W, d_pi, d_A, d_Bt, d_ll, d_nan, bdone, p.blk_end[j]));
-            if (ll_out) {
+            if (ll_out && ll_pinned) {
                 // scoring has a single "word", so block b holds utterances [32 b, 32 b + 32) of the (identity) order
                 const int64_t u0 = (int64_t)bdone * 32, u1 = std::min<int64_t>(U, (int64_t)p.blk_end[j] * 32);
                 HMMB_CUDA(cudaEventRecord(scored, c.stream));
@@ -1440,6 +1443,7 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
         HMMB_CUDA(cudaMemcpyAsync(&flags[0], d_nan, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
         HMMB_CUDA(cudaMemcpyAsync(&flags[1], s.d_bad, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
         if (argmax_out) HMMB_CUDA(cudaMemcpyAsync(argmax_out, d_arg, (size_t)U * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        if (ll_out && !ll_pinned) HMMB_TRY(d2h_big(ll_out, d_ll, (size_t)U * W * sizeof(double), c.stream));
         HMMB_CUDA(cudaStreamSynchronize(c.stream));
         HMMB_CUDA(cudaStreamSynchronize(c.d2h_stream));
         s.pend.reset();
@@ -1453,8 +1457,8 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
             const int eg = (int)std::max<int64_t>(1, (warps + BW_WARPS - 1) / BW_WARPS);
             HMMB_LAUNCH("score_exact", (k_score_exact<uint16_t, true>), eg, BW_THREADS, 0, s.d_obs, s.d_foff, s.d_len, s.d_order, U, N, M, W, d_pi, d_A, d_Bt, d_ll, d_nan);
             HMMB_LAUNCH("score_argmax", k_argmax_first, (unsigned)((U + 255) / 256), 256, 0, d_ll, U, W, d_arg);
-            if (ll_out) HMMB_CUDA(cudaMemcpyAsync(ll_out, d_ll, (size_t)U * W * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
             if (argmax_out) HMMB_CUDA(cudaMemcpyAsync(argmax_out, d_arg, (size_t)U * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+            if (ll_out) HMMB_TRY(d2h_big(ll_out, d_ll, (size_t)U * W * sizeof(double), c.stream));
             HMMB_CUDA(cudaStreamSynchronize(c.stream));
         }
         return HMMB_OK;
@@ -1497,8 +1501,8 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
         }
     }
     HMMB_LAUNCH("score_argmax", k_argmax_first, (unsigned)((U + 255) / 256), 256, 0, d_ll, U, W, d_arg);
-    if (ll_out) HMMB_CUDA(cudaMemcpyAsync(ll_out, d_ll, (size_t)U * W * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     if (argmax_out) HMMB_CUDA(cudaMemcpyAsync(argmax_out, d_arg, (size_t)U * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    if (ll_out) HMMB_TRY(d2h_big(ll_out, d_ll, (size_t)U * W * sizeof(double), c.stream));
     HMMB_CUDA(cudaStreamSynchronize(c.stream));
     return HMMB_OK;
 }

@@ -71,6 +71,9 @@ struct Ctx {
     void *pstage = nullptr;
     size_t pstage_bytes = 0;
     cudaEvent_t pstage_busy = nullptr;
+    // two pinned bounce buffers for large copies from / to PAGEABLE host memory (h2d_big / d2h_big)
+    void *bounce[2] = {nullptr, nullptr};
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
 };
 
 Ctx &ctx();
@@ -79,6 +82,15 @@ int require_init();
 int dev_alloc(void **p, size_t bytes);  // cached cudaMalloc (256 B granularity)
 void dev_free(void *p);                 // returns the block to the cache
 void dev_release_cache();
+
+// Large copies between pageable host memory and the device: the driver's own staging moves ~10 GB/s; these go
+// through two pinned bounce buffers with a multi-threaded memcpy of one chunk overlapping the DMA of the other.
+// Pinned (or small) buffers take a plain cudaMemcpyAsync.  h2d_big returns when `src` may be reused (the last DMA
+// may still be in flight on `st`); d2h_big returns with `dst` complete (it synchronises `st`).
+bool host_is_pinned(const void *p);
+void par_memcpy(void *dst, const void *src, size_t bytes);
+int h2d_big(void *dst, const void *src, size_t bytes, cudaStream_t st);
+int d2h_big(void *dst, const void *src, size_t bytes, cudaStream_t st);
 
 int phase_id(const char *name);
 void phase_begin(int id);

@@ -98,6 +98,101 @@ static cudaEvent_t get_event() {
 cudaEvent_t event_get() { return get_event(); }
 void event_put(cudaEvent_t e) { g_ctx.event_pool.push_back(e); }
 
+bool host_is_pinned(const void *p) {
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, p) == cudaSuccess &&
+                        (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    (void)cudaGetLastError();
+    return pinned;
+}
+
+void par_memcpy(void *dst, const void *src, size_t bytes) {
+#ifdef _OPENMP
+    const int nt = bytes >= (size_t(1) << 20) ? omp_get_max_threads() : 1;
+#else
+    const int nt = 1;
+#endif
+    if (nt <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t slice = ((bytes + nt - 1) / nt + 4095) & ~size_t(4095);
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int t = 0; t < nt; ++t) {
+        const size_t lo = std::min(bytes, slice * t), hi = std::min(bytes, lo + slice);
+        if (hi > lo) memcpy((char *)dst + lo, (const char *)src + lo, hi - lo);
+    }
+}
+
+static constexpr size_t BOUNCE_BYTES = size_t(8) << 20;
+static constexpr size_t BIG_COPY_MIN = size_t(4) << 20;
+
+static int bounce_ready() {
+    Ctx &c = g_ctx;
+    for (int b = 0; b < 2; ++b) {
+        if (!c.bounce[b]) {
+            if (cudaHostAlloc(&c.bounce[b], BOUNCE_BYTES, cudaHostAllocDefault) != cudaSuccess) {
+                (void)cudaGetLastError();
+                c.bounce[b] = nullptr;
+                return HMMB_ERR_OOM;
+            }
+        }
+        if (!c.bounce_ev[b]) HMMB_CUDA(cudaEventCreateWithFlags(&c.bounce_ev[b], cudaEventDisableTiming));
+    }
+    return HMMB_OK;
+}
+
+int h2d_big(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    Ctx &c = g_ctx;
+    if (bytes == 0) return HMMB_OK;
+    if (bytes < BIG_COPY_MIN || getenv("HMMB_NO_BOUNCE") || host_is_pinned(src) || bounce_ready() != HMMB_OK) {
+        HMMB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return HMMB_OK;
+    }
+    int k = 0;
+    for (size_t lo = 0; lo < bytes; lo += BOUNCE_BYTES, ++k) {
+        const size_t n = std::min(BOUNCE_BYTES, bytes - lo);
+        const int b = k & 1;
+        HMMB_CUDA(cudaEventSynchronize(c.bounce_ev[b]));  // the DMA that last read this buffer (never recorded: returns at once)
+        par_memcpy(c.bounce[b], (const char *)src + lo, n);
+        HMMB_CUDA(cudaMemcpyAsync((char *)dst + lo, c.bounce[b], n, cudaMemcpyHostToDevice, st));
+        HMMB_CUDA(cudaEventRecord(c.bounce_ev[b], st));
+    }
+    return HMMB_OK;
+}
+
+int d2h_big(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    Ctx &c = g_ctx;
+    if (bytes == 0) return HMMB_OK;
+    if (bytes < BIG_COPY_MIN || getenv("HMMB_NO_BOUNCE") || host_is_pinned(dst) || bounce_ready() != HMMB_OK) {
+        HMMB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        HMMB_CUDA(cudaStreamSynchronize(st));
+        return HMMB_OK;
+    }
+    // both buffers may still be the source of an earlier h2d_big on another stream
+    for (int b = 0; b < 2; ++b) HMMB_CUDA(cudaEventSynchronize(c.bounce_ev[b]));
+    const size_t nchunk = (bytes + BOUNCE_BYTES - 1) / BOUNCE_BYTES;
+    auto issue = [&](size_t k) -> int {
+        const size_t lo = k * BOUNCE_BYTES, n = std::min(BOUNCE_BYTES, bytes - lo);
+        HMMB_CUDA(cudaMemcpyAsync(c.bounce[k & 1], (const char *)src + lo, n, cudaMemcpyDeviceToHost, st));
+        HMMB_CUDA(cudaEventRecord(c.bounce_ev[k & 1], st));
+        return HMMB_OK;
+    };
+    auto drain = [&](size_t k) -> int {
+        const size_t lo = k * BOUNCE_BYTES, n = std::min(BOUNCE_BYTES, bytes - lo);
+        HMMB_CUDA(cudaEventSynchronize(c.bounce_ev[k & 1]));
+        par_memcpy((char *)dst + lo, c.bounce[k & 1], n);
+        return HMMB_OK;
+    };
+    HMMB_TRY(issue(0));
+    for (size_t k = 1; k < nchunk; ++k) {
+        HMMB_TRY(issue(k));      // chunk k crosses PCIe while chunk k - 1 is copied out of its buffer
+        HMMB_TRY(drain(k - 1));
+    }
+    HMMB_TRY(drain(nchunk - 1));
+    return HMMB_OK;
+}
+
 void phase_begin(int id) {
     Ctx &c = g_ctx;
     PhaseRec r;
@@ -198,6 +293,12 @@ int hmmb_shutdown(void) {
     if (c.pstage) cudaFreeHost(c.pstage);
     c.pstage = nullptr;
     c.pstage_bytes = 0;
+    for (int b = 0; b < 2; ++b) {
+        if (c.bounce[b]) cudaFreeHost(c.bounce[b]);
+        if (c.bounce_ev[b]) cudaEventDestroy(c.bounce_ev[b]);
+        c.bounce[b] = nullptr;
+        c.bounce_ev[b] = nullptr;
+    }
     if (c.stage_busy) { cudaEventDestroy(c.stage_busy); c.stage_busy = nullptr; }
     if (c.pstage_busy) { cudaEventDestroy(c.pstage_busy); c.pstage_busy = nullptr; }
     for (auto ev : c.event_pool) cudaEventDestroy(ev);

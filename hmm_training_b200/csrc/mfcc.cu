@@ -170,7 +170,7 @@ extern "C" int hmmb_mfcc_frames(const double *Y, int64_t F, int L, int y_on_devi
     const double *dYp = Y;
     if (!y_on_device) {
         HMMB_TRY(dev_alloc(&dY.p, (size_t)F * L * sizeof(double)));
-        HMMB_CUDA(cudaMemcpyAsync(dY.p, Y, (size_t)F * L * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        HMMB_TRY(h2d_big(dY.p, Y, (size_t)F * L * sizeof(double), c.stream));
         dYp = static_cast<const double *>(dY.p);
     }
     HMMB_CUDA(cudaMemcpyAsync(dW.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
@@ -191,7 +191,6 @@ extern "C" int hmmb_mfcc_frames(const double *Y, int64_t F, int L, int y_on_devi
                     static_cast<const float *>(dW.p), static_cast<const int *>(dR.p), static_cast<const double *>(dD.p),
                     static_cast<double *>(dO.p));
     }
-    HMMB_CUDA(cudaMemcpyAsync(mfcc_out, dO.p, (size_t)F * MFCC_COEF * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-    HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    HMMB_TRY(d2h_big(mfcc_out, dO.p, (size_t)F * MFCC_COEF * sizeof(double), c.stream));
     return HMMB_OK;
 }

@@ -332,11 +332,10 @@ int hmmb_vq_encode(const double *X, int64_t F, const double *C, int K, int32_t *
             HMMB_TRY(vq_launch(0, dX.as<double>() + f0 * 13, n, dC.as<double>(), K, dI.as<int32_t>() + f0, nullptr, nullptr));
         }
     } else {
-        HMMB_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)F * 13 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        HMMB_TRY(h2d_big(dX.p, X, (size_t)F * 13 * sizeof(double), c.stream));  // pageable frames: pinned bounce buffers
         HMMB_TRY(vq_launch(0, dX.as<double>(), F, dC.as<double>(), K, dI.as<int32_t>(), nullptr, nullptr));
     }
-    HMMB_CUDA(cudaMemcpyAsync(idx_out, dI.p, (size_t)F * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
-    HMMB_CUDA(cudaStreamSynchronize(c.stream));
+    HMMB_TRY(d2h_big(idx_out, dI.p, (size_t)F * sizeof(int32_t), c.stream));
     return HMMB_OK;
 }
 
@@ -360,7 +359,7 @@ int hmmb_lbg_fit(const double *X, int64_t F, int x_on_device, int K, int max_ite
     const double *dX = X;
     if (!x_on_device && F > 0) {
         HMMB_TRY(dev_alloc(&dXb.p, (size_t)F * 13 * sizeof(double)));
-        HMMB_CUDA(cudaMemcpyAsync(dXb.p, X, (size_t)F * 13 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        HMMB_TRY(h2d_big(dXb.p, X, (size_t)F * 13 * sizeof(double), c.stream));
         dX = dXb.as<double>();
     }
     HMMB_TRY(dev_alloc(&dCa.p, (size_t)Kmax * 13 * sizeof(double)));

@@ -295,6 +295,15 @@ def test_pipelined_scorer_matches_plain(tiny, monkeypatch):
         ll0, arg0 = engine.score(pinned, offsets, N, M, pi, A, B)
         assert np.array_equal(ll, ll0, equal_nan=True) and np.array_equal(arg, arg0)
         assert not np.isnan(ll).any()
+        # a pinned result matrix leaves stage by stage on the D2H stream; the pageable one above went through
+        # the bounce buffers after the last stage
+        monkeypatch.delenv("HMMB_SCORE_NO_PIPELINE", raising=False)
+        ll_pin, hll = _pinned_copy(np.zeros((U, W)))
+        try:
+            ll1, arg1 = engine.score(pinned, offsets, N, M, pi, A, B, out_ll=ll_pin)
+            assert np.array_equal(ll1, ll, equal_nan=True) and np.array_equal(arg1, arg)
+        finally:
+            _lib.load().hmmb_host_free(hll)
         if tiny:
             fin = np.isfinite(ll)
             assert fin.any() and (ll[fin] < -700).any()  # the denormal / exact paths were exercised
@@ -303,3 +312,34 @@ def test_pipelined_scorer_matches_plain(tiny, monkeypatch):
         assert_close(ll[sub], ref, "pipelined scorer vs oracle")
     finally:
         _lib.load().hmmb_host_free(handle)
+
+
+def test_large_pageable_parameters_round_trip():
+    """Parameter sets above 4 MB in PAGEABLE memory cross PCIe through the library's pinned bounce buffers
+    (multi-threaded memcpy overlapping the DMA) in both directions; set -> get must return the same bits, and
+    HMMB_NO_BOUNCE (plain cudaMemcpyAsync) must agree."""
+    from hmm_training_b200 import engine
+    rng = np.random.default_rng(23)
+    N, M, W, T = 8, 1024, 150, 12  # B: 150 x 8 x 1024 doubles = 9.8 MB -> two bounce chunks
+    obs = rng.integers(0, M, size=W * T).astype(np.uint16)
+    offsets = np.arange(W + 1, dtype=np.int64) * T
+    wos = np.arange(W, dtype=np.int32)
+    pi = rng.dirichlet(np.ones(N), size=W)
+    A = rng.dirichlet(np.ones(N), size=(W, N))
+    B = rng.dirichlet(np.ones(M), size=(W, N))
+    outs = []
+    for env in (None, "1"):
+        if env:
+            os.environ["HMMB_NO_BOUNCE"] = env
+        try:
+            with engine.BaumWelch(obs, offsets, wos, W, N, M) as bw:
+                bw.set_params(pi, A, B)
+                got = bw.params(finalize=False)
+                bw.iterate(2, 1e-6, 2)
+                outs.append(got + bw.params())
+        finally:
+            os.environ.pop("HMMB_NO_BOUNCE", None)
+    for x, y in zip(outs[0][:3], (pi, A, B)):
+        assert np.array_equal(x, y)
+    for x, y in zip(outs[0], outs[1]):
+        assert np.array_equal(x, y, equal_nan=True)

@@ -433,3 +433,62 @@ def test_large_roundtrip_properties():
     assert_close(ll[np.arange(500), wos[sub]], ll_seq[sub], "E-step LL vs scorer", rtol=1e-12, atol=0)
     C = synthetic.random_codebook(3, 256)
     assert np.array_equal(engine.vq_encode(C, C), np.arange(256))
+
+
+@pytest.mark.parametrize("cfg", ["config3", "config4"])
+def test_baseline_full_size_properties(cfg):
+    """BASELINE configs 3 and 4 IN FULL (10 words x 100 000 sequences x T = 200, N = 4, M = 256 = 200 M frames;
+    1000 words x 500 sequences x T = 200, N = 16, M = 1024 = 100 M frames — 7 / 13 GB on the device), through
+    properties that need the oracle only on a sample:
+      (1) the E-step's per-sequence log-likelihood equals the oracle's forward pass on sequences drawn from
+          the first, the last and random CTAs of the launch;
+      (2) checksum of checksums: every word's convergence statistic is the log_sum_exp (hmm_training.py:503)
+          of its per-sequence values;
+      (3) words are independent: one word trained alone (its own CTA partition) gives the same model;
+      (4) EM does not decrease the statistic, rows of pi / A / B sum to 1, the left-to-right zero pattern of A
+          is preserved."""
+    N, M, W, S, T, family = (4, 256, 10, 100_000, 200, "n4_left_to_right") if cfg == "config3" else \
+                            (16, 1024, 1000, 500, 200, "left_to_right")
+    obs, offsets, wos = synthetic.fixed_length_codewords(1000, W, S, T, N, M)
+    R = W * S
+    pi0, A0, B0 = engine.default_init(N, M)
+    with engine.BaumWelch(obs, offsets, wos, W, N, M) as bw:
+        bw.set_params(np.tile(pi0, (W, 1)), np.tile(A0, (W, 1, 1)), np.tile(B0, (W, 1, 1)))
+        assert bw.kernel_family() == family
+        bw.iterate(2, 1e-6, 100)
+        pi_raw, A_raw, B_raw = bw.params(finalize=False)
+        bw.iterate(1, 1e-6, 100)  # E-step with the parameters above; seq_ll belongs to them
+        ll_seq = bw.seq_ll()
+        pi, A, B = bw.params(finalize=True)
+        hist, iters = bw.history(100)
+    assert np.all(iters == 3)
+    # (4)
+    assert np.allclose(pi.sum(axis=1), 1, atol=1e-12) and np.allclose(A.sum(axis=2), 1, atol=1e-12)
+    assert np.allclose(B.sum(axis=2), 1, atol=1e-9)
+    assert np.all(np.diff(hist[:, :3], axis=1) > -1e-6)
+    assert np.array_equal(A == 0, np.tile(A0 == 0, (W, 1, 1)))
+    assert np.all(ll_seq > -np.inf)
+    # (1)
+    rng = np.random.default_rng(4)
+    sample = np.unique(np.concatenate([np.arange(64), np.arange(R - 64, R), rng.choice(R, 272, replace=False)]))
+    for r in sample:
+        w = int(wos[r])
+        ref = O.calculate_log_likelihood(obs[offsets[r]:offsets[r + 1]].astype(np.int64), A_raw[w], B_raw[w], pi_raw[w])
+        assert_close(ll_seq[r:r + 1], np.array([ref]), f"full-size E-step LL of sequence {r} vs oracle forward")
+    # (2)
+    x = ll_seq.reshape(W, S)
+    m = x.max(axis=1)
+    assert_close(hist[:, 2], m + np.log(np.exp(x - m[:, None]).sum(axis=1)), "statistic = log_sum_exp of sequence LLs",
+                 rtol=1e-12, atol=0)
+    # (3)
+    w = 7
+    off_w = offsets[w * S:(w + 1) * S + 1] - offsets[w * S]
+    with engine.BaumWelch(obs[offsets[w * S]:offsets[(w + 1) * S]], off_w, np.zeros(S, dtype=np.int32), 1, N, M) as bw:
+        bw.set_params(pi0[None], A0[None], B0[None])
+        bw.iterate(3, 1e-6, 100)
+        pi1, A1, B1 = bw.params(finalize=True)
+        h1, _ = bw.history(100)
+    assert_close(h1[0, :3], hist[w, :3], "word alone: statistic", rtol=1e-12, atol=0)
+    assert_close(A1[0], A[w], "word alone: A", rtol=1e-10)
+    assert_close(pi1[0], pi[w], "word alone: pi", rtol=1e-10)
+    assert_close(B1[0], B[w], "word alone: B", rtol=1e-10)

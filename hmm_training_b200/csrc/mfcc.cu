@@ -8,9 +8,9 @@
 //   Slaney mel filter bank (26 bands, 0 .. sr/2, float32 weights with Slaney area normalisation) ->
 //   10 log10(max(1e-10, .)) clipped at (max - 80 dB) -> DCT-II (ortho) -> first 13 coefficients.
 //
-// One warp per frame.  The L x (L/2+1) DFT is evaluated directly in fp64 (lane = bins lane, lane+32, ...;
-// twiddles from an L-entry shared table indexed by (k*n mod L), kept incrementally): ~2 * 160 * 320 FMAs
-// per frame — the front-end moves 2.5 KB of samples per frame over PCIe, so arithmetic is not what bounds it.
+// One warp per frame.  The DFT of the real frame is evaluated directly in fp64 on its even / odd folded samples
+// (lane = bins lane, lane+32, ...; twiddles from an L-entry shared table indexed by (k*m mod L), kept
+// incrementally): ~2 * 161 * 160 FMAs per frame — the front-end moves 2.5 KB of samples per frame over PCIe.
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -56,19 +56,36 @@ k_mfcc_frames(const double *__restrict__ Y, int64_t F, int L, const double *__re
         // windowed frame: y * (0.5 - 0.5 cos(2 pi n / L))  (periodic Hann, as scipy's get_window(fftbins=True))
         for (int n = lane; n < L; n += 32) sX[n] = Y[f * L + n] * (0.5 - 0.5 * sCos[n]);
         __syncwarp();
+        // Real input: cos(2 pi k n / L) is even and sin odd under n -> L - n, so
+        //   Re X_k = x_0 [+ (-1)^k x_{L/2}] + sum_{m=1}^{H-1} (x_m + x_{L-m}) cos(2 pi k m / L)
+        //   Im X_k =                        - sum_{m=1}^{H-1} (x_m - x_{L-m}) sin(2 pi k m / L),   H = ceil(L / 2):
+        // half the multiply-adds of the plain sum.  The folded samples replace x_m (even part) and x_{L-m} (odd part).
+        const int H = (L + 1) / 2;
+        for (int m = 1 + lane; m < H; m += 32) {
+            const double a = sX[m], b = sX[L - m];
+            sX[m] = a + b;
+            sX[L - m] = a - b;
+        }
+        __syncwarp();
         // DFT bins k = lane + 32 j
         double re[BPL], im[BPL];
         int idx[BPL];
+        const double x0 = sX[0], xh = (L & 1) ? 0.0 : sX[L / 2];
 #pragma unroll
-        for (int j = 0; j < BPL; ++j) { re[j] = im[j] = 0.0; idx[j] = 0; }
-        for (int n = 0; n < L; ++n) {
-            const double x = sX[n];
+        for (int j = 0; j < BPL; ++j) {
+            const int k = lane + 32 * j;
+            re[j] = x0 + ((k & 1) ? -xh : xh);
+            im[j] = 0.0;
+            idx[j] = k;  // k * m mod L at m = 1 (k <= L / 2 < L)
+        }
+        for (int m = 1; m < H; ++m) {
+            const double xe = sX[m], xo = sX[L - m];
 #pragma unroll
             for (int j = 0; j < BPL; ++j) {
                 const int k = lane + 32 * j;
                 if (k < nb) {
-                    re[j] = fma(x, sCos[idx[j]], re[j]);
-                    im[j] = fma(-x, sSin[idx[j]], im[j]);
+                    re[j] = fma(xe, sCos[idx[j]], re[j]);
+                    im[j] = fma(-xo, sSin[idx[j]], im[j]);
                     idx[j] += k;
                     if (idx[j] >= L) idx[j] -= L;
                 }
@@ -167,29 +184,55 @@ extern "C" int hmmb_mfcc_frames(const double *Y, int64_t F, int L, int y_on_devi
     HMMB_TRY(dev_alloc(&dR.p, range.size() * sizeof(int)));
     HMMB_TRY(dev_alloc(&dD.p, dct.size() * sizeof(double)));
     HMMB_TRY(dev_alloc(&dO.p, (size_t)F * MFCC_COEF * sizeof(double)));
-    const double *dYp = Y;
-    if (!y_on_device) {
-        HMMB_TRY(dev_alloc(&dY.p, (size_t)F * L * sizeof(double)));
-        HMMB_TRY(h2d_big(dY.p, Y, (size_t)F * L * sizeof(double), c.stream));
-        dYp = static_cast<const double *>(dY.p);
-    }
     HMMB_CUDA(cudaMemcpyAsync(dW.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
     HMMB_CUDA(cudaMemcpyAsync(dR.p, range.data(), range.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
     HMMB_CUDA(cudaMemcpyAsync(dD.p, dct.data(), dct.size() * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     double *tcos = static_cast<double *>(dT.p), *tsin = tcos + L;
     HMMB_LAUNCH("mfcc", k_mfcc_tables, (L + 255) / 256, 256, 0, L, tcos, tsin);
     const size_t smem = ((size_t)2 * L + (size_t)MFCC_WARPS * (L + nb + MFCC_MELS)) * sizeof(double);
-    const int64_t grid = std::min<int64_t>((F + MFCC_WARPS - 1) / MFCC_WARPS, (int64_t)c.sm_count * 8);
-    if (nb <= 32 * MFCC_BPL_SMALL) {
-        HMMB_CUDA(cudaFuncSetAttribute(k_mfcc_frames<MFCC_BPL_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        HMMB_LAUNCH("mfcc", k_mfcc_frames<MFCC_BPL_SMALL>, (unsigned)grid, MFCC_WARPS * 32, smem, dYp, F, L, tcos, tsin,
-                    static_cast<const float *>(dW.p), static_cast<const int *>(dR.p), static_cast<const double *>(dD.p),
-                    static_cast<double *>(dO.p));
+    const bool small = nb <= 32 * MFCC_BPL_SMALL;
+    if (small) HMMB_CUDA(cudaFuncSetAttribute(k_mfcc_frames<MFCC_BPL_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else HMMB_CUDA(cudaFuncSetAttribute(k_mfcc_frames<MFCC_BPL_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // frames [f0, f0 + n) of a device-resident sample matrix -> rows [f0, f0 + n) of dO
+    auto launch = [&](const double *dYp, int64_t f0, int64_t n) -> int {
+        const int64_t grid = std::min<int64_t>((n + MFCC_WARPS - 1) / MFCC_WARPS, (int64_t)c.sm_count * 8);
+        double *o = static_cast<double *>(dO.p) + f0 * MFCC_COEF;
+        if (small) {
+            HMMB_LAUNCH("mfcc", k_mfcc_frames<MFCC_BPL_SMALL>, (unsigned)grid, MFCC_WARPS * 32, smem, dYp + f0 * L, n, L, tcos, tsin,
+                        static_cast<const float *>(dW.p), static_cast<const int *>(dR.p), static_cast<const double *>(dD.p), o);
+        } else {
+            HMMB_LAUNCH("mfcc", k_mfcc_frames<MFCC_BPL_LARGE>, (unsigned)grid, MFCC_WARPS * 32, smem, dYp + f0 * L, n, L, tcos, tsin,
+                        static_cast<const float *>(dW.p), static_cast<const int *>(dR.p), static_cast<const double *>(dD.p), o);
+        }
+        return HMMB_OK;
+    };
+    if (y_on_device) {
+        HMMB_TRY(launch(Y, 0, F));
     } else {
-        HMMB_CUDA(cudaFuncSetAttribute(k_mfcc_frames<MFCC_BPL_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        HMMB_LAUNCH("mfcc", k_mfcc_frames<MFCC_BPL_LARGE>, (unsigned)grid, MFCC_WARPS * 32, smem, dYp, F, L, tcos, tsin,
-                    static_cast<const float *>(dW.p), static_cast<const int *>(dR.p), static_cast<const double *>(dD.p),
-                    static_cast<double *>(dO.p));
+        HMMB_TRY(dev_alloc(&dY.p, (size_t)F * L * sizeof(double)));
+        const double *dYp = static_cast<const double *>(dY.p);
+        const int64_t chunk = std::max<int64_t>(1, (int64_t(16) << 20) / ((int64_t)L * (int64_t)sizeof(double)));  // ~16 MB of samples
+        if (host_is_pinned(Y) && F >= 2 * chunk) {
+            // pinned samples go up in chunks on the copy stream and every chunk is transformed as soon as it has
+            // landed: the kernel (30 M frames/s at L = 320) hides behind the PCIe transfer (21 M frames/s)
+            cudaEvent_t fence = event_get();  // recycled device blocks may still be in use on the compute stream
+            HMMB_CUDA(cudaEventRecord(fence, c.stream));
+            HMMB_CUDA(cudaStreamWaitEvent(c.copy_stream, fence, 0));
+            event_put(fence);
+            for (int64_t f0 = 0; f0 < F; f0 += chunk) {
+                const int64_t n = std::min<int64_t>(chunk, F - f0);
+                HMMB_CUDA(cudaMemcpyAsync(static_cast<double *>(dY.p) + f0 * L, Y + f0 * L, (size_t)n * L * sizeof(double),
+                                          cudaMemcpyHostToDevice, c.copy_stream));
+                cudaEvent_t landed = event_get();
+                HMMB_CUDA(cudaEventRecord(landed, c.copy_stream));
+                HMMB_CUDA(cudaStreamWaitEvent(c.stream, landed, 0));
+                event_put(landed);
+                HMMB_TRY(launch(dYp, f0, n));
+            }
+        } else {
+            HMMB_TRY(h2d_big(dY.p, Y, (size_t)F * L * sizeof(double), c.stream));
+            HMMB_TRY(launch(dYp, 0, F));
+        }
     }
     HMMB_TRY(d2h_big(mfcc_out, dO.p, (size_t)F * MFCC_COEF * sizeof(double), c.stream));
     return HMMB_OK;

@@ -54,3 +54,27 @@ def test_audio_processor_matches_oracle(tmp_path):
     _close(ap.mfcc_matrix(audio), MO.mfcc_recording(audio))
     with pytest.raises(ValueError):
         engine.mfcc_frames(np.zeros(320))
+
+
+def test_mfcc_chunked_upload_matches_plain():
+    """Samples in PINNED host memory go up in ~16 MB chunks on the copy stream with the kernel running behind
+    them; pageable samples go through the bounce buffers in one piece.  Same bits either way, and a sample of
+    the frames against the oracle."""
+    import ctypes
+    from hmm_training_b200 import _lib
+    rng = np.random.default_rng(9)
+    F, L = 20000, 320  # 51 MB of samples: four chunks
+    Y = _speechlike(rng, F, L, 2000.0)
+    plain = engine.mfcc_frames(Y, 16000)
+    lib = _lib.load()
+    p = lib.hmmb_host_alloc(Y.nbytes)
+    assert p
+    try:
+        Yp = np.ctypeslib.as_array((ctypes.c_double * Y.size).from_address(p)).reshape(Y.shape)
+        Yp[...] = Y
+        chunked = engine.mfcc_frames(Yp, 16000)
+    finally:
+        lib.hmmb_host_free(p)
+    assert np.array_equal(plain, chunked)
+    pick = rng.choice(F, 50, replace=False)
+    _close(plain[pick], np.stack([MO.mfcc_frame(Y[i], 16000) for i in pick]))

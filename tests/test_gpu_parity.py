@@ -111,6 +111,53 @@ def test_baum_welch_matches_oracle_seeded(N, M, T):
         assert np.array_equal(floored_set(B[w], M), floored_set(Bo, M))
 
 
+@pytest.mark.parametrize("N,M,T,S,family", [
+    (4, 256, 6000, 3, "n4_left_to_right"),   # long horizons: thousands of rescales; the exact kernel at long T
+    (4, 512, 40, 40, "n4_left_to_right"),    # the largest alphabet the warp-private count tables hold
+    (4, 513, 40, 40, "generic"),             # one more codeword: lanes-per-state kernels, u16 symbols
+    (5, 4096, 60, 20, "generic"),            # wide alphabet, odd state count
+    (16, 1400, 30, 40, "left_to_right"),     # B^T of 175 KB: the largest the left-to-right kernels keep in shared memory
+    (16, 1700, 30, 40, "generic"),           # beyond it
+])
+def test_baum_welch_size_limits_match_oracle(N, M, T, S, family):
+    """Maximum sizes of each kernel family (and the first size past each limit) against the numpy oracle,
+    default left-to-right init, 3 iterations."""
+    rng = np.random.default_rng(N * 100003 + M * 17 + T)
+    W = 2
+    corpus = [synthetic.clustered_sequences(rng, S, N=N, M=M, tmin=max(1, T - T // 8), tmax=T, shift=7 * w,
+                                            spread=max(2, M // (2 * N))) for w in range(W)]
+    obs, offsets, wos = synthetic.pack_corpus(corpus, M)
+    pi0, A0, B0 = engine.default_init(N, M)
+    init = (np.tile(pi0, (W, 1)), np.tile(A0, (W, 1, 1)), np.tile(B0, (W, 1, 1)))
+    with engine.BaumWelch(obs, offsets, wos, W, N, M) as bw:
+        bw.set_params(*init)
+        assert bw.kernel_family() == family
+        bw.iterate(3, 1e-6, 3)
+        pi, A, B = bw.params()
+        hist, iters = bw.history(3)
+        exact_passes, handovers = bw.diagnostics()
+    if T < 1000:
+        assert (exact_passes, handovers) == (0, 0)
+    else:
+        # Known limitation (DESIGN.md section 4): the forward pass's scalar error bound is a rigorous but loose upper
+        # bound that grows a little every step, so with peaked (trained) emissions sequences of several thousand
+        # frames are handed to the exact log-space kernel from the second iteration on: correct, but slower.
+        assert handovers == 0 and exact_passes in (0, 2 * W * S)
+    # At T = 6000 log-space arithmetic itself (the reference's, the oracle's and k_bw_exact's) carries ~1e-9 of
+    # rounding noise: log alpha ~ -2e4 is held to 2e-12 absolute per operation and the recursion is 6000 steps deep,
+    # so two correct log-space evaluations already differ by several 1e-9 in the small entries of B.
+    rtol = 1e-9 if T < 1000 else 1e-7
+    for w in range(W):
+        Ao, Bo, pio, h, it = O.hmm_training(corpus[w], N=N, M=M, max_iterations=3, init=(pi0, A0, B0), return_history=True)
+        assert it == iters[w]
+        assert_close(hist[w, :it], h, f"N{N} M{M} T{T} w{w} ll", rtol=rtol)
+        assert_close(A[w], Ao, f"N{N} M{M} T{T} w{w} A", rtol=rtol)
+        assert_close(B[w], Bo, f"N{N} M{M} T{T} w{w} B", rtol=rtol)
+        assert_close(pi[w], pio, f"N{N} M{M} T{T} w{w} pi", rtol=rtol)
+        assert_same_support(A[w], Ao)
+        assert np.array_equal(floored_set(B[w], M), floored_set(Bo, M))
+
+
 def _ltr_init(rng, W, N, M, kind):
     """Left-to-right (upper-bidiagonal A) initial models: 'default' = the generalised reference
     defaults, 'random' = random self/next probabilities and random dense B, 'zeros' = B with

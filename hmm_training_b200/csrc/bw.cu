@@ -62,7 +62,10 @@ __global__ void k_check_bidiag(const double *__restrict__ A, int W, int N, int32
     }
 }
 
-template <bool BIDIAG>
+// VECB: per-state error bound of the forward recursion (needed for utterances of thousands of frames); the scalar
+// bound is ~10 instructions per step cheaper and enough below SCORE4_SCALAR_BOUND_MAX_T frames (bw4_kernels.cuh)
+constexpr int SCORE4_SCALAR_BOUND_MAX_T = 1000;
+template <bool BIDIAG, bool VECB>
 __global__ void __launch_bounds__(BW_THREADS)
 k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4 *__restrict__ obs_blk,
          const int32_t *__restrict__ len_sorted, const int32_t *__restrict__ order, const double *__restrict__ pi,
@@ -83,7 +86,7 @@ k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4
         const Blk bk = blks[b];
         const int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
         bool af;
-        const double ll = fwd4_run<BIDIAG, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, reinterpret_cast<const double2 *>(sB),
+        const double ll = fwd4_run<BIDIAG, false, VECB>(T, bk.tmax, obs_blk + bk.obs_base + lane, reinterpret_cast<const double2 *>(sB),
                                                   reinterpret_cast<const double2 *>(sB) + M, sBmax, sBmask, a, p, rmax, mk, nullptr, af);
         if (lane < bk.nseq) {
             ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
@@ -1342,8 +1345,13 @@ static int launch_score_special(SeqSet &s, int W, const double *d_pi, const doub
     bpc = std::min(bpc, 64);
     dim3 g((unsigned)((nb + bpc - 1) / bpc), (unsigned)W);
     const size_t smem = (size_t)s.M * 5 * sizeof(double) + (size_t)((s.M + 15) & ~15);
-    HMMB_LAUNCH("score", k_score4<BIDIAG>, g, BW_THREADS, smem, s.d_blks + b0, nb, bpc, (const uint4 *)s.d_obs, s.d_len,
-                s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll, d_nan);
+    if (s.tmax_all > SCORE4_SCALAR_BOUND_MAX_T) {
+        HMMB_LAUNCH("score", (k_score4<BIDIAG, true>), g, BW_THREADS, smem, s.d_blks + b0, nb, bpc, (const uint4 *)s.d_obs, s.d_len,
+                    s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll, d_nan);
+    } else {
+        HMMB_LAUNCH("score", (k_score4<BIDIAG, false>), g, BW_THREADS, smem, s.d_blks + b0, nb, bpc, (const uint4 *)s.d_obs, s.d_len,
+                    s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll, d_nan);
+    }
     return HMMB_OK;
 }
 

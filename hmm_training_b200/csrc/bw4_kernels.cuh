@@ -168,12 +168,17 @@ __device__ __forceinline__ double tiny_if(unsigned m, int j) { return __hiloint2
 // FMA chains as the addend of every alive state: a product that underflows stays (barely)
 // positive, a normal value is unchanged.
 //
-// Precision guard: each step adds 4 * 2^-1074 (worst-case absolute error of four
-// denormal / clamped values) to a scalar bound E, propagated with
-//   E' = (E * rmax * max_j b_j(o_t) + seeds) * scale  >=  sum_j |error of alpha-hat_t(j)|
-// (units of 2^-1000).  E stays ~1e-320 of the step's mass unless the states that carried the
-// sequence die; when it exceeds 1e-12 the sequence is handed over.
-template <bool BIDIAG, bool SPILL>
+// Precision guard: each step adds 2^-1074 per state (worst-case absolute error of a denormal /
+// clamped value) to an error bound that is propagated along with the values (units of 2^-1000);
+// when its total exceeds 1e-12 of the step's mass the sequence is handed over.
+//   VECB (default): per state, e' = (b(o_t) .* (A^T e) + seeds) * scale — the exact linear recursion of the
+//     errors.  It stays ~1e-320 of the mass unless the states that carried the sequence die, for any T.
+//   !VECB: scalar E' = (E * rmax * max_j b_j(o_t) + seeds) * scale >= sum_j e'_j, 10 instructions cheaper per
+//     step but loose: it assumes the error sits in the most probable state, so at every left-to-right
+//     transition it grows by ~1 / a_i,i+1 against the true mass; fine for utterance lengths (used by the
+//     issue-bound scorer when no utterance exceeds SCORE4_SCALAR_BOUND_MAX_T), trips after a few thousand
+//     frames with peaked emissions.
+template <bool BIDIAG, bool SPILL, bool VECB = true>
 __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restrict__ op,
                                            const double2 *__restrict__ sB01, const double2 *__restrict__ sB23,
                                            const double *__restrict__ sBmax,
@@ -182,7 +187,7 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
                                            double2 *__restrict__ sp, bool &allfull) {
     using S16 = Sym<uint16_t>;
     double al0 = 0.0, al1 = 0.0, al2 = 0.0, al3 = 0.0;
-    double E = 0.0;  // error bound, units of 2^-1000
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;  // error bounds, units of 2^-1000: per state (VECB) or e0 = their sum
     long long esum = 0;
     unsigned m = 0u;    // alive set
     bool stop = false;  // dead (impossible) or flagged for the exact path
@@ -244,7 +249,7 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
                     const int code = exact_products4(n0, n1, n2, n3, b01.x, b01.y, b23.x, b23.y, o, &Ex);
                     if (code == 0) {
                         stop = true;
-                    } else if ((code == 2 && t > 0) || E > 0.0) {
+                    } else if ((code == 2 && t > 0) || ((e0 + e1) + (e2 + e3)) > 0.0) {
                         stop = true;  // the surviving states had lost their bits: exact path
                         ll = nan_mark();
                     } else {
@@ -258,8 +263,31 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
                     const double sc = pow2_rescale(ssum, esum);
                     allf = allf && (__double2hiint(sc) >= 0x3ff00000);  // scale >= 1 cannot flush a denormal alpha
                     al0 = at0 * sc; al1 = at1 * sc; al2 = at2 * sc; al3 = at3 * sc;
-                    E = fma(E, rmax * sBmax[sym], 4.0 * ERR_UNIT) * sc;
-                    if (!(E <= ERR_LIMIT)) {
+                    if (!VECB) {
+                        e0 = fma(e0, rmax * sBmax[sym], 4.0 * ERR_UNIT) * sc;  // scalar bound (see above)
+                    } else {
+                    // error bounds follow the same linear recursion as the values (t = 0: pi is exact), plus the
+                    // worst-case rounding of one denormal / clamped value per state
+                    double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
+                    if (t > 0) {
+                        if (BIDIAG) {
+                            f0 = e0 * a[0];
+                            f1 = fma(e1, a[1], e0 * a[4]);
+                            f2 = fma(e2, a[2], e1 * a[5]);
+                            f3 = fma(e3, a[3], e2 * a[6]);
+                        } else {
+                            f0 = fma(e3, a[12], fma(e2, a[8], fma(e1, a[4], e0 * a[0])));
+                            f1 = fma(e3, a[13], fma(e2, a[9], fma(e1, a[5], e0 * a[1])));
+                            f2 = fma(e3, a[14], fma(e2, a[10], fma(e1, a[6], e0 * a[2])));
+                            f3 = fma(e3, a[15], fma(e2, a[11], fma(e1, a[7], e0 * a[3])));
+                        }
+                    }
+                    e0 = fma(f0, b01.x, ERR_UNIT) * sc;
+                    e1 = fma(f1, b01.y, ERR_UNIT) * sc;
+                    e2 = fma(f2, b23.x, ERR_UNIT) * sc;
+                    e3 = fma(f3, b23.y, ERR_UNIT) * sc;
+                    }
+                    if (!(((e0 + e1) + (e2 + e3)) <= ERR_LIMIT)) {
                         stop = true;
                         ll = nan_mark();
                     }

@@ -112,7 +112,7 @@ def test_baum_welch_matches_oracle_seeded(N, M, T):
 
 
 @pytest.mark.parametrize("N,M,T,S,family", [
-    (4, 256, 6000, 3, "n4_left_to_right"),   # long horizons: thousands of rescales; the exact kernel at long T
+    (4, 256, 6000, 3, "n4_left_to_right"),   # long horizons: thousands of rescales, per-state error bound
     (4, 512, 40, 40, "n4_left_to_right"),    # the largest alphabet the warp-private count tables hold
     (4, 513, 40, 40, "generic"),             # one more codeword: lanes-per-state kernels, u16 symbols
     (5, 4096, 60, 20, "generic"),            # wide alphabet, odd state count
@@ -136,16 +136,10 @@ def test_baum_welch_size_limits_match_oracle(N, M, T, S, family):
         pi, A, B = bw.params()
         hist, iters = bw.history(3)
         exact_passes, handovers = bw.diagnostics()
-    if T < 1000:
-        assert (exact_passes, handovers) == (0, 0)
-    else:
-        # Known limitation: the forward pass's scalar error bound is a rigorous but loose upper
-        # bound that grows a little every step, so with peaked (trained) emissions sequences of several thousand
-        # frames are handed to the exact log-space kernel from the second iteration on: correct, but slower.
-        assert handovers == 0 and exact_passes in (0, 2 * W * S)
-    # At T = 6000 log-space arithmetic itself (the reference's, the oracle's and k_bw_exact's) carries ~1e-9 of
-    # rounding noise: log alpha ~ -2e4 is held to 2e-12 absolute per operation and the recursion is 6000 steps deep,
-    # so two correct log-space evaluations already differ by several 1e-9 in the small entries of B.
+    assert (exact_passes, handovers) == (0, 0)  # the per-state error bound keeps even T = 6000 on the fast path
+    # At T = 6000 the ORACLE's log-space arithmetic (like the reference's) carries ~1e-9 of rounding noise: log alpha
+    # ~ -2e4 is held to 2e-12 absolute per operation and the recursion is 6000 steps deep, so the small entries of B
+    # of two correct evaluations differ by several 1e-9 (the exact log-space kernel differs from the oracle by as much).
     rtol = 1e-9 if T < 1000 else 1e-7
     for w in range(W):
         Ao, Bo, pio, h, it = O.hmm_training(corpus[w], N=N, M=M, max_iterations=3, init=(pi0, A0, B0), return_history=True)
@@ -366,6 +360,24 @@ def _tiny_models(rng, W, N, M):
                 if j != keep:
                     B[w, j, k] = tiny[rng.integers(0, len(tiny))]
     return pi, A, B
+
+
+def test_scoring_long_utterances():
+    """Utterances of 3000 frames against trained (peaked, 1e-20-floored) left-to-right models, own and foreign:
+    k_score4 switches to the per-state error bound above 1000 frames (the scalar bound would hand every such
+    utterance to the exact kernel); results against the oracle's log-space forward pass."""
+    rng = np.random.default_rng(77)
+    N, M, T, S, W = 4, 256, 3000, 3, 3
+    corpus = [synthetic.clustered_sequences(rng, S, N=N, M=M, tmin=T - 200, tmax=T, shift=11 * w, spread=24) for w in range(W)]
+    obs, offsets, wos = synthetic.pack_corpus(corpus, M)
+    pi0, A0, B0 = engine.default_init(N, M)
+    pi, A, B, _, _ = engine.bw_fit(obs, offsets, wos, W, N, M, np.tile(pi0, (W, 1)), np.tile(A0, (W, 1, 1)),
+                                   np.tile(B0, (W, 1, 1)), max_iterations=3)
+    ll, arg = engine.score(obs, offsets, N, M, pi, A, B)
+    ref = O.score_batch([u for c in corpus for u in c], [(A[w], B[w], pi[w]) for w in range(W)])
+    assert not np.isnan(ll).any()
+    assert_close(ll, ref, "long utterances", rtol=1e-8)
+    assert np.array_equal(arg, O.argmax_first(ref)) and np.array_equal(arg, wos)
 
 
 @pytest.mark.parametrize("N,M", [(4, 16), (6, 16)])

@@ -353,18 +353,33 @@ k_bw_mstep(const double *__restrict__ accum, int64_t astride, const double *__re
     const double nseq = acc[N + N * N + (size_t)M * N];
 
     // B denominators: sum over all t of gamma_t(j) = column sums of the counts (:462-472)
-    for (int j = 0; j < N; ++j) {
+    if (RED_THREADS % N == 0) {
+        // N divides the CTA size: a thread's elements tid, tid + RED_THREADS, ... all belong to state tid % N, so the
+        // [M][N] table is read once, coalesced, and the per-thread sums are folded in a fixed order
+        __shared__ double sThread[RED_THREADS];
         double s = 0.0;
-        for (int k = tid; k < M; k += RED_THREADS) s += cnt[(size_t)k * N + j];
+        for (int e = tid; e < M * N; e += RED_THREADS) s += cnt[e];
+        sThread[tid] = s;
+        __syncthreads();
+        if (tid < N) {
+            double d = 0.0;
+            for (int q = tid; q < RED_THREADS; q += N) d += sThread[q];
+            sDen[tid] = d;
+        }
+    } else {
+        for (int j = 0; j < N; ++j) {
+            double s = 0.0;
+            for (int k = tid; k < M; k += RED_THREADS) s += cnt[(size_t)k * N + j];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) sPart[warp][j] = s;
-    }
-    __syncthreads();
-    if (tid < N) {
-        double s = 0.0;
-        for (int q = 0; q < RED_THREADS / 32; ++q) s += sPart[q][tid];
-        sDen[tid] = s;
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) sPart[warp][j] = s;
+        }
+        __syncthreads();
+        if (tid < N) {
+            double s = 0.0;
+            for (int q = 0; q < RED_THREADS / 32; ++q) s += sPart[q][tid];
+            sDen[tid] = s;
+        }
     }
     __syncthreads();
     // B (:474-497): no finite term -> 1e-20 floor; empty denominator -> row stays -inf (0)

@@ -284,7 +284,7 @@ def test_scoring_matches_reference_golden(kernel_family):
     assert np.array_equal(arg, O.argmax_first(g["ll"]))
 
 
-@pytest.mark.parametrize("N,M", [(4, 256), (6, 32), (16, 1024)])
+@pytest.mark.parametrize("N,M", [(4, 256), (6, 32), (16, 1024), (4, 512), (4, 513), (5, 4096), (32, 64), (1, 7)])
 def test_scoring_matches_oracle_with_structural_zeros(N, M):
     rng = np.random.default_rng(N + M)
     W, U = 5, 70

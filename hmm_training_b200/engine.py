@@ -7,7 +7,7 @@ Everything here runs on the GPU through libhmmb200.so; nothing falls back to the
 from __future__ import annotations
 
 import ctypes
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, Optional, Tuple
 
 import numpy as np
 

@@ -22,7 +22,7 @@ import random
 import sys
 from collections import defaultdict
 from pathlib import Path
-from typing import Dict, List
+from typing import Dict
 
 from .codevector_classes import DataStorage, load_mfcc_matrix
 from .hmm_classes import DataStorageHMM

@@ -4,7 +4,6 @@ the CPU oracle on seeded inputs.  Needs a GPU: run with ``-m gpu`` on the B200 b
 Tolerances: indices bit-exact; A/B/pi and per-iteration LL within
 |x - ref| <= 1e-9*|ref| + 1e-30; zero pattern of A/pi and the set of floored B entries equal.
 """
-import os
 
 import numpy as np
 import pytest

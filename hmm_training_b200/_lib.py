@@ -38,6 +38,11 @@ SYMBOLS = [
     ("hmmb_phase_ms", _c.c_double, [_c.c_char_p, _lp]),
     ("hmmb_phase_reset", _c.c_int, []),
     ("hmmb_set_profiling", _c.c_int, [_c.c_int]),
+    ("hmmb_comm_unique_id", _c.c_int, [_c.c_void_p, _c.c_int]),
+    ("hmmb_comm_init", _c.c_int, [_c.c_int, _c.c_int, _c.c_void_p]),
+    ("hmmb_comm_allreduce", _c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p]),
+    ("hmmb_comm_rank", _c.c_int, [_ip, _ip]),
+    ("hmmb_comm_destroy", _c.c_int, []),
     ("hmmb_vq_encode", _c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p]),
     ("hmmb_vq_encode_dev", _c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),
     ("hmmb_lbg_fit", _c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_void_p,

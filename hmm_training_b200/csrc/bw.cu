@@ -959,6 +959,11 @@ int hmmb_bw_set_params(hmmb_bw_t *h, const double *pi0, const double *A0, const 
 
 int hmmb_bw_set_dist(hmmb_bw_t *h, int rank, int world, hmmb_allreduce_fn allreduce, void *user) {
     HMMB_TRY(require_init());
+    if (world > 1 && !allreduce) {  // no hook given: the library's own communicator, if one was created
+        int cw = 1;
+        hmmb_comm_rank(nullptr, &cw);
+        if (cw == world) allreduce = hmmb_comm_allreduce;
+    }
     if (!h || world < 1 || rank < 0 || rank >= world || (world > 1 && !allreduce)) {
         set_error("hmmb_bw_set_dist: bad arguments (rank=%d world=%d)", rank, world);
         return HMMB_ERR_ARG;

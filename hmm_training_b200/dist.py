@@ -76,6 +76,24 @@ def make_allreduce(group=None, device: str = "cuda", overlap: bool = False):
     return fn
 
 
+def native_comm_init(rank: int, world: int, group=None) -> None:
+    """Create the library's OWN NCCL communicator (hmmb_comm_init) — the path a C caller without torch takes.  The
+    128-byte NCCL id is made on rank 0 and travels through torch.distributed here; afterwards pass
+    ``allreduce="native"`` to engine.bw_fit / BaumWelch.set_dist / engine.lbg_fit."""
+    import torch.distributed as dist
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(lib.hmmb_comm_unique_id(buf, 128))
+    box = [buf.raw if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    _lib.check(lib.hmmb_comm_init(int(rank), int(world), box[0]))
+
+
+def native_comm_destroy() -> None:
+    _lib.check(_lib.load().hmmb_comm_destroy())
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous shard [lo, hi) of n items for `rank`; sizes differ by at most one."""
     base, rem = divmod(n, world)

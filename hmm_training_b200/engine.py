@@ -63,6 +63,10 @@ def _wrap_allreduce(fn: Optional[Callable[[int, int], None]]):
     """fn(dev_ptr, n_doubles) -> None, wrapped as the C hook; returns (cfunc, keepalive)."""
     if fn is None:
         return None, None
+    if isinstance(fn, str):
+        if fn != "native":
+            raise ValueError("allreduce must be a callable, None or 'native'")
+        return _lib.load().hmmb_comm_allreduce, None  # the library's own NCCL communicator (dist.native_comm_init)
 
     def hook(dev_ptr, n, _user):
         try:

@@ -65,6 +65,17 @@ int hmmb_set_profiling(int enabled);       /* event timing around every kernel (
  * shim implements it with torch.distributed.all_reduce over NCCL.  NULL = single GPU. */
 typedef int (*hmmb_allreduce_fn)(void *dev_buf, int64_t n_doubles, void *user);
 
+/* Built-in NCCL communicator for callers without their own collective.  libnccl.so.2 is
+ * opened with dlopen at the first call (inside a PyTorch process that is the copy torch has already mapped).
+ * Rank 0 obtains the 128-byte id with hmmb_comm_unique_id and distributes it out of band; every rank then calls
+ * hmmb_comm_init (collective, after hmmb_init on its GPU).  hmmb_comm_allreduce is an hmmb_allreduce_fn: pass it
+ * to hmmb_bw_set_dist / hmmb_lbg_fit (hmmb_bw_set_dist also falls back to it when its hook argument is NULL). */
+int hmmb_comm_unique_id(void *id_out, int id_bytes /* >= 128 */);
+int hmmb_comm_init(int rank, int world, const void *nccl_id);
+int hmmb_comm_allreduce(void *dev_buf, int64_t n_doubles, void *user);
+int hmmb_comm_rank(int *rank, int *world);   /* world = 1 while no communicator exists */
+int hmmb_comm_destroy(void);
+
 /* ------------------------------------------------------------------ VQ encode
  * Replaces get_observations, HMM/hmm_training.py:82-120: per frame argmin_k of
  * sqrt(sum_{d=1..12} (x_d - c_kd)^2), strict '<' (lowest index wins ties); dimension 0

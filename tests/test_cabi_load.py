@@ -47,3 +47,21 @@ def test_product_package_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
                 assert "/root/reference" not in text, f"{f} reads the reference tree"
+
+
+def test_native_communicator_api_without_ranks():
+    """hmmb_comm_* (the library's own NCCL plumbing, libnccl via dlopen): without a communicator the all-reduce
+    hook fails loudly, the reported world size is 1, and rank 0 can obtain a 128-byte id (no GPU needed)."""
+    import ctypes
+    lib = _lib.load()
+    assert lib.hmmb_comm_allreduce(None, 0, None) == _lib.ERR_ARG
+    assert b"no communicator" in lib.hmmb_last_error()
+    r, w = ctypes.c_int32(-1), ctypes.c_int32(-1)
+    assert lib.hmmb_comm_rank(ctypes.byref(r), ctypes.byref(w)) == 0 and (r.value, w.value) == (0, 1)
+    assert lib.hmmb_comm_unique_id(ctypes.create_string_buffer(16), 16) == _lib.ERR_ARG  # buffer too small
+    buf = ctypes.create_string_buffer(128)
+    rc = lib.hmmb_comm_unique_id(buf, 128)
+    if rc == _lib.ERR_UNSUPPORTED:
+        pytest.skip("libnccl.so.2 not present")
+    assert rc == 0 and any(buf.raw)
+    assert lib.hmmb_comm_destroy() == 0  # nothing to destroy

@@ -54,6 +54,16 @@ for name, groups in (("plain", 1), ("overlap", 3)):
         bw.set_overlap(groups)
         bw.iterate(3, 1e-6, 3)
         ltr[name] = bw.params() + bw.history(3)
+# the library's own NCCL communicator (hmmb_comm_init; libnccl opened with dlopen) instead of the torch hook:
+# a two-rank sum has one order, so the results must be identical bit for bit
+hdist.native_comm_init(rank, world)
+out_native = engine.bw_fit(sobs, soff, wos[mine], W, N, M, np.tile(pi0, (W, 1)), np.tile(A0, (W, 1, 1)), np.tile(B0, (W, 1, 1)),
+                           max_iterations=10, allreduce="native", rank=rank, world=world)
+for x, y in zip(out, out_native):
+    assert np.array_equal(x, y, equal_nan=True), "native communicator disagrees with the torch.distributed hook"
+C2 = engine.lbg_fit(X[lo:hi], 32, 100, 0.001, allreduce="native")[0]
+assert np.allclose(C, C2, rtol=1e-12, atol=1e-12)  # LBG sums use fp64 atomics: order-dependent at 1e-16
+hdist.native_comm_destroy()
 np.savez(os.environ["HMMB_OUT"] + f".{rank}.npz", pi=out[0], A=out[1], B=out[2], hist=out[3], iters=out[4], C=C,
          lbg_iters=iters, assign=assign, **{f"ltr_{k}_{i}": v for k, r in ltr.items() for i, v in enumerate(r)})
 torch.cuda.synchronize()

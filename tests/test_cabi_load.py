@@ -65,3 +65,29 @@ def test_native_communicator_api_without_ranks():
         pytest.skip("libnccl.so.2 not present")
     assert rc == 0 and any(buf.raw)
     assert lib.hmmb_comm_destroy() == 0  # nothing to destroy
+
+
+def _build_c_caller(tmp_path):
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    _lib.load()  # builds the library if needed
+    exe = str(tmp_path / "c_caller")
+    subprocess.run(["gcc", "-std=c11", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_caller.c"), "-L", os.path.join(ROOT, "hmm_training_b200"),
+                    "-lhmmb200", "-lm", "-o", exe], check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "hmm_training_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    return exe, env
+
+
+def test_plain_c_caller_compiles_against_the_header(tmp_path):
+    """include/hmmb200.h is a C header (no C++ / torch types): examples/c_caller.c builds with gcc -std=c11 -Werror
+    and links against the library; without a GPU it stops at hmmb_init with the no-fallback message."""
+    import subprocess
+    import torch
+    exe, env = _build_c_caller(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: tests/test_gpu_dropin.py runs the example")
+    r = subprocess.run([exe], env=env, capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr

@@ -343,3 +343,15 @@ def test_large_pageable_parameters_round_trip():
         assert np.array_equal(x, y)
     for x, y in zip(outs[0], outs[1]):
         assert np.array_equal(x, y, equal_nan=True)
+
+
+def test_plain_c_caller_trains_and_recognises(tmp_path):
+    """examples/c_caller.c: the C ABI used from plain C (hmmb_bw_fit, hmmb_score, hmmb_vq_encode) — exit code 0 means
+    the statistic did not decrease, B rows sum to 1, every utterance was recognised as its own word and every
+    centroid encoded to itself."""
+    import subprocess
+    from test_cabi_load import _build_c_caller
+    exe, env = _build_c_caller(tmp_path)
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "16 of 16 utterances" in r.stdout

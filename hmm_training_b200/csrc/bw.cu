@@ -188,8 +188,8 @@ struct EarlyUpload {
     cudaEvent_t ev[MAX_CHUNKS] = {};
     cudaEvent_t t0 = nullptr;       // HMMB_TIMING: start of the upload (copy stream)
     bool active() const { return nchunk > 0; }
-    // queue chunks [issued, upto) on the copy stream.  The first half goes out before the host-side
-    // sorting / blocking (PCIe works while the host does), the second half only after the (small)
+    // queue chunks [issued, upto) on the copy stream.  The first chunks go out before the host-side
+    // sorting / blocking (PCIe works while the host does), the rest only after the (small)
     // per-sequence metadata has been queued: copies of different streams share one DMA queue, and the
     // metadata must not wait behind the whole codeword stream.
     int issue(int upto) {
@@ -267,7 +267,7 @@ struct SeqSet {
 };
 
 // Small host-to-device copies of a build.  While a codeword upload is in flight on the copy stream they go
-// through that stream as well — one DMA queue, so they keep their place between the two halves of the upload
+// through that stream as well — one DMA queue, so they keep their place between the first chunks of the upload and the rest
 // instead of being served after it (copies of different streams are not served in issue order) — and
 // h2d_join() orders the compute stream behind them.
 static int h2d_small(void *dst, const void *src, size_t bytes) {
@@ -593,7 +593,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         HMMB_TRY(dev_alloc(&s.d_obs, (size_t)std::max<int64_t>(s.frames, 1) * s.sym_bytes));
     }
     // the caller's own small uploads (accumulator layout, initial parameters) also go ahead of the
-    // second half of the codewords in the DMA queue
+    // rest of the codewords in the DMA queue
     if (mid_hook) HMMB_TRY((*mid_hook)());
     HMMB_TRY(h2d_join());
     c.h2d_on_copy = false;
@@ -827,7 +827,7 @@ int hmmb_bw_create_ex(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_o
     const bool have_params = pi0 && A0 && B0;
     // everything that follows the sequence set (buffers sized by it, the small uploads, optionally the
     // initial parameters).  In a pipelined create it runs INSIDE seqset_build, between the metadata and the
-    // second half of the codeword upload, so that none of it waits behind that upload.
+    // rest of the codeword upload, so that none of it waits behind that upload.
     bool finished = false;
     std::function<int()> finish = [&]() -> int {
         finished = true;
@@ -1392,7 +1392,7 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
     int32_t *d_arg = nullptr;
     int32_t *d_nan = nullptr;  // set by the scorers when the precision guard marked a pair
     bool models_up = false;
-    // model parameters -> device.  In the pipelined scorer this runs inside seqset_build, between the two halves
+    // model parameters -> device.  In the pipelined scorer this runs inside seqset_build, between the first chunks and the rest
     // of the codeword upload and on the same DMA queue (see hmmb_bw_create_ex).
     std::function<int()> upload_models = [&]() -> int {
         models_up = true;
@@ -1415,8 +1415,8 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
         HMMB_LAUNCH("score_load", k_load_clamped, (unsigned)std::min<size_t>((nP + 255) / 256, 1024), 256, 0, tmp + nB + nA, (int64_t)nP, d_pi);
         return HMMB_OK;
     };
-    // Pipelined scorer (N = 4, pinned codewords in length-descending order, small models): the two halves of the
-    // upload are repacked and scored as they land, and each half's rows of the [U, W] matrix start their way back
+    // Pipelined scorer (N = 4, pinned codewords in length-descending order, small models): the stages of the
+    // upload are repacked and scored as they land, and each stage's rows of the [U, W] matrix start their way back
     // to the host while the other half is still being scored.
     const bool pipeline = !ltr && nB * sizeof(double) <= (size_t(4) << 20) && !getenv("HMMB_SCORE_NO_PIPELINE");
     HMMB_TRY(seqset_build(s, obs, idx_bytes, obs_on_device, offsets, nullptr, U, 1, N, M, ltr ? LAYOUT_LTR : LAYOUT_AUTO,

@@ -258,7 +258,7 @@ def test_pipelined_upload_matches_plain_create(S, ragged):
 
 @pytest.mark.parametrize("tiny", [False, True])
 def test_pipelined_scorer_matches_plain(tiny, monkeypatch):
-    """Recognition on a large PINNED codeword buffer runs in two stages behind the upload, with each half's
+    """Recognition on a large PINNED codeword buffer runs in stages behind the upload, with each stage's
     rows of the [U, W] matrix copied back while the other half is scored; results must equal the unpipelined
     path bit for bit — also when the precision guard marks pairs (denormal emissions) and everything is sent
     again after the exact log-space recomputation."""

@@ -1417,7 +1417,7 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
     };
     // Pipelined scorer (N = 4, pinned codewords in length-descending order, small models): the stages of the
     // upload are repacked and scored as they land, and each stage's rows of the [U, W] matrix start their way back
-    // to the host while the other half is still being scored.
+    // to the host while the next stage is being scored.
     const bool pipeline = !ltr && nB * sizeof(double) <= (size_t(4) << 20) && !getenv("HMMB_SCORE_NO_PIPELINE");
     HMMB_TRY(seqset_build(s, obs, idx_bytes, obs_on_device, offsets, nullptr, U, 1, N, M, ltr ? LAYOUT_LTR : LAYOUT_AUTO,
                           pipeline, pipeline ? &upload_models : nullptr, score_stages()));

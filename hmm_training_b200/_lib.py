@@ -45,8 +45,12 @@ SYMBOLS = [
     ("hmmb_comm_destroy", _c.c_int, []),
     ("hmmb_vq_encode", _c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p]),
     ("hmmb_vq_encode_dev", _c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    ("hmmb_vq_encode_ex", _c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int64,
+                                     _lp]),
     ("hmmb_lbg_fit", _c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_void_p,
                                 _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    ("hmmb_lbg_fit_ex", _c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_double, _c.c_void_p,
+                                   _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     ("hmmb_bw_create", _c.c_int, [_c.POINTER(_c.c_void_p), _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                   _c.c_int64, _c.c_int, _c.c_int, _c.c_int]),
     ("hmmb_bw_create_ex", _c.c_int, [_c.POINTER(_c.c_void_p), _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,

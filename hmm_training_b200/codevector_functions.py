@@ -96,11 +96,18 @@ def createCodeVector(raw_data_vocabulary: List[RawDataMFCC], centroids_quantity:
     print("=" * 50)
 
     X = frames_matrix(raw_data_vocabulary)
-    C, gens, assign, iters, gdist = engine.lbg_fit(X, centroids_quantity, max_iterations, epsilon)
+    C, gens, assign, iters, gdist, hist = engine.lbg_fit(X, centroids_quantity, max_iterations, epsilon, history=True)
     n_gen = len(iters)
     for g in range(1, n_gen + 1):
+        # the reference's progress lines (:472, :512-516), replayed from the per-pass summed distances
         print(f"\nGeneration {g}: Creating {1 << g} centroids")
-        print(f"  Converged after {int(iters[g - 1])} iterations (diff=n/a)")
+        prev, diff = 0.0, epsilon + 100
+        for it, gd in enumerate(hist[g - 1], start=1):
+            diff = abs(prev - float(gd))
+            prev = float(gd)
+            if it % 10 == 0:
+                print(f"  Iteration {it}: dist={gd:.6f}, diff={diff:.6f}")
+        print(f"  Converged after {int(iters[g - 1])} iterations (diff={diff:.6f})")
     if n_gen > 0:
         for frame, cid in zip(raw_data_vocabulary, assign):
             frame.generation = n_gen

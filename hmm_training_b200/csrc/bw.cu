@@ -692,7 +692,7 @@ struct hmmb_bw {
     bool bidiag = false;          // every word's A is upper-bidiagonal (checked in set_params)
     int64_t *d_seq_begin = nullptr;
     // precision guard: sticky per-sequence hand-over flags, counters, exact-kernel scratch
-    uint8_t *d_flag = nullptr;
+    uint8_t *d_flag = nullptr, *d_flag_base = nullptr;  // d_flag = d_flag_base + FLAG_HDR
     int32_t *d_newflags = nullptr;
     int64_t *d_nexact = nullptr;
     double *d_exact_scratch = nullptr;
@@ -710,6 +710,9 @@ struct hmmb_bw {
     bool params_set = false, any_active = true;
 };
 
+// alpha-hat spill of the N = 4 kernels (behind its front padding, see bw_finish_create)
+static double2 *spill4(hmmb_bw *h) { return reinterpret_cast<double2 *>(h->d_spill) + (size_t)BWD4_SPILL_PAD * 64; }
+
 static void bw_release(hmmb_bw *h) {
     h->pend_release.reset();
     h->s.release();
@@ -719,7 +722,7 @@ static void bw_release(hmmb_bw *h) {
     dev_free(h->d_pi); dev_free(h->d_A); dev_free(h->d_Bt); dev_free(h->d_spill); dev_free(h->d_llseq);
     dev_free(h->d_accum); dev_free(h->d_partials); dev_free(h->d_prev); dev_free(h->d_hist); dev_free(h->d_active);
     dev_free(h->d_iters); dev_free(h->d_any); dev_free(h->d_cta_begin); dev_free(h->d_seq_begin);
-    dev_free(h->d_bzero); dev_free(h->d_flag); dev_free(h->d_newflags); dev_free(h->d_nexact); dev_free(h->d_exact_scratch);
+    dev_free(h->d_bzero); dev_free(h->d_flag_base); dev_free(h->d_newflags); dev_free(h->d_nexact); dev_free(h->d_exact_scratch);
 }
 
 static int bw_alloc_accum(hmmb_bw *h) {
@@ -753,7 +756,8 @@ static int bw_finish_create(hmmb_bw *h, int64_t R) {
     TRYF(dev_alloc_t(&h->d_iters, (size_t)W));
     TRYF(dev_alloc_t(&h->d_any, 1));
     TRYF(dev_alloc_t(&h->d_bzero, (size_t)W));
-    TRYF(dev_alloc_t(&h->d_flag, (size_t)std::max<int64_t>(R, 1)));
+    TRYF(dev_alloc_t(&h->d_flag_base, (size_t)std::max<int64_t>(R, 1) + FLAG_HDR));  // header: see raise_flag
+    h->d_flag = h->d_flag_base + FLAG_HDR;
     TRYF(dev_alloc_t(&h->d_newflags, 1));
     TRYF(dev_alloc_t(&h->d_nexact, 1));
     {
@@ -768,7 +772,9 @@ static int bw_finish_create(hmmb_bw *h, int64_t R) {
     TRYF(h2d_small(h->d_seq_begin, s.seq_begin.data(), (W + 1) * sizeof(int64_t)));
     size_t spill_bytes;
     if (s.special4) {
-        spill_bytes = (size_t)std::max<int64_t>(s.spill_steps, 1) * 64 * sizeof(double2);
+        // + BWD4_SPILL_PAD rows in front: k_bw_bwd4 loads row t - 2 unconditionally (for t < 2 that is the tail of
+        // the previous block, or this padding for the first block; the values are never used)
+        spill_bytes = (size_t)(std::max<int64_t>(s.spill_steps, 1) + BWD4_SPILL_PAD) * 64 * sizeof(double2);
         TRYF(dev_alloc_t(&h->d_partials, (size_t)std::max(s.ncta, 1) * h->pstride));
         TRYF(dev_alloc_t(&h->d_cta_begin, (size_t)W + 1));
         TRYF(dev_alloc_t(&h->d_allfull, (size_t)std::max<int64_t>(R, 1)));
@@ -940,7 +946,7 @@ static int bw_set_params_impl(hmmb_bw *h, const double *pi0, const double *A0, c
     HMMB_LAUNCH("bw_load", k_fill_i32, (unsigned)((W + 255) / 256), 256, 0, h->d_active, (int64_t)W, 1);
     HMMB_LAUNCH("bw_load", k_fill_i32, (unsigned)((W + 255) / 256), 256, 0, h->d_iters, (int64_t)W, 0);
     if (h->d_hist) HMMB_LAUNCH("bw_load", k_fill, 64, 256, 0, h->d_hist, (int64_t)W * h->hist_cap, (double)NAN);
-    HMMB_CUDA(cudaMemsetAsync(h->d_flag, 0, (size_t)std::max<int64_t>(h->s.R, 1), c.stream));
+    HMMB_CUDA(cudaMemsetAsync(h->d_flag_base, 0, (size_t)std::max<int64_t>(h->s.R, 1) + FLAG_HDR, c.stream));
     HMMB_CUDA(cudaMemsetAsync(h->d_newflags, 0, sizeof(int32_t), c.stream));
     HMMB_CUDA(cudaMemsetAsync(h->d_nexact, 0, sizeof(int64_t), c.stream));
     h->n_backward_handover = 0;
@@ -1024,22 +1030,22 @@ static int launch_generic_estep(hmmb_bw *h) {
     return HMMB_OK;
 }
 
-template <bool BIDIAG>
+template <bool BIDIAG, int MT>
 static int launch_special_estep(hmmb_bw *h) {
     Ctx &c = ctx();
     SeqSet &s = h->s;
     if (s.ncta == 0) { s.pend.reset(); return HMMB_OK; }
     const size_t smem_f = (size_t)h->M * 5 * sizeof(double) + (size_t)((h->M + 15) & ~15);
     const size_t smem_b = (size_t)h->M * 4 * sizeof(double) * (1 + BW_WARPS) + (size_t)BW_THREADS * 4 * sizeof(double);
-    HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwd4<BIDIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwd4<BIDIAG, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     // forward + backward of the CTA work items [c0, c1)
     auto launch_range = [&](int c0, int c1) -> int {
         if (c1 <= c0) return HMMB_OK;
         HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, c1 - c0, BW_THREADS, smem_f, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
-                    s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag,
+                    s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_flag,
                     h->d_allfull);
-        HMMB_LAUNCH("bw_backward", k_bw_bwd4<BIDIAG>, c1 - c0, BW_THREADS, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
-                    s.d_len, h->d_A, h->d_Bt, h->M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero,
+        HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT>), c1 - c0, BW_THREADS, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
+                    s.d_len, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_bzero,
                     h->d_allfull, h->d_partials + (size_t)c0 * h->pstride, h->pstride, h->d_flag, h->d_newflags);
         return HMMB_OK;
     };
@@ -1101,16 +1107,20 @@ static int launch_special_estep(hmmb_bw *h) {
         }
         h->check_bad = true;
         h->pend_release = std::move(s.pend);  // raw buffer + events: released after the next stream sync
-        // flagged sequences only exist from the second iteration on (flags are set by this forward pass):
-        // the exact kernel runs after the stages; it and the backward pass are independent
-        return launch_exact<uint16_t, true>(h);
+        // sequences this forward pass handed over are redone by the exact kernel after the stages (their
+        // accumulator contributions are independent of the backward pass); the per-CTA statistic, taken inside
+        // k_bw_bwd4 while those sequences still carried their NaN mark, is then retaken
+        HMMB_TRY((launch_exact<uint16_t, true>(h)));
+        HMMB_LAUNCH("bw_exact", k_bw_llstat_fix, s.ncta, BW_THREADS, 0, s.d_work, s.d_blks, h->d_llseq, h->d_active,
+                    h->d_flag, h->d_partials, h->pstride, h->M);
+        return HMMB_OK;
     }
     HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
-                s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag,
+                s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_flag,
                 h->d_allfull);
     HMMB_TRY((launch_exact<uint16_t, true>(h)));
-    HMMB_LAUNCH("bw_backward", k_bw_bwd4<BIDIAG>, s.ncta, BW_THREADS, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
-                s.d_len, h->d_A, h->d_Bt, h->M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero,
+    HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT>), s.ncta, BW_THREADS, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
+                s.d_len, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_bzero,
                 h->d_allfull, h->d_partials, h->pstride, h->d_flag, h->d_newflags);
     return HMMB_OK;
 }
@@ -1163,7 +1173,10 @@ static int launch_ltr_estep(hmmb_bw *h) {
 static int bw_estep(hmmb_bw *h) {
     if (h->use_ltr) return h->N == 16 ? launch_ltr_estep<16>(h) : launch_ltr_estep<8>(h);
     SeqSet &s = h->s;
-    if (s.special4) return h->bidiag ? launch_special_estep<true>(h) : launch_special_estep<false>(h);
+    if (s.special4) {
+        if (h->M == 256) return h->bidiag ? launch_special_estep<true, 256>(h) : launch_special_estep<false, 256>(h);
+        return h->bidiag ? launch_special_estep<true, 0>(h) : launch_special_estep<false, 0>(h);
+    }
 #define GEN(NPV)                                                                               \
     case NPV:                                                                                  \
         return s.sym_bytes == 1 ? launch_generic_estep<NPV, uint8_t>(h) : launch_generic_estep<NPV, uint16_t>(h);
@@ -1221,7 +1234,11 @@ int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync
                         h->d_cta_begin, h->d_llseq, h->d_seq_begin, h->d_accum, h->astride, h->nacc,
                         h->d_accum + (size_t)h->W * h->astride, h->rank, h->W, h->d_active);
             if (h->allreduce && h->world > 1) {
+                static int pid_ar = -1;
+                if (pid_ar < 0) pid_ar = phase_id("bw_allreduce");
+                if (c.profiling) phase_begin(pid_ar);  // CUDA events around the collective on the launching stream
                 int rc = h->allreduce(h->d_accum, h->accum_n, h->user);
+                if (c.profiling) phase_end(pid_ar);
                 if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
             }
         }

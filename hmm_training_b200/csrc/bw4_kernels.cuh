@@ -386,7 +386,7 @@ k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         if (T > 0) {
             ll_seq[bk.first + lane] = ll;
             allfull[bk.first + lane] = af ? 1 : 0;
-            if (ll != ll) flag[bk.first + lane] = 1;  // precision guard: hand over (sticky)
+            if (ll != ll) raise_flag(flag, bk.first + lane);  // precision guard: hand over (sticky)
         }
     }
 }
@@ -394,17 +394,29 @@ k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
 // ---------------------------------------------------------------- backward + accumulate
 // Warp-private emission-count update in precomputed rank order (see k_repack_blocks4): one
 // conflict-free read-modify-write round per rank, rank 0 (distinct codewords) being the bulk.
-__device__ __forceinline__ void cnt_update4(double2 *__restrict__ cw01, double2 *__restrict__ cw23, bool act,
-                                            unsigned sym, int rank, double g0, double g1, double g2, double g3) {
-    const int maxrank = __reduce_max_sync(0xffffffffu, act ? rank : 0);
-    for (int r = 0; r <= maxrank; ++r) {
-        if (act && rank == r) {
-            double2 c01 = cw01[sym], c23 = cw23[sym];
-            c01.x += g0; c01.y += g1; c23.x += g2; c23.y += g3;
-            cw01[sym] = c01; cw23[sym] = c23;
-        }
+// Round 0 and round 1 (taken on ~93 % of the steps of the benchmark data) are written out; only ranks >= 2
+// loop.  row01 = this lane's (j = 0, 1) row of the warp's table, the (j = 2, 3) row sits M entries further.
+__device__ __forceinline__ void cnt_rmw4(double2 *__restrict__ row01, int M, double g0, double g1, double g2, double g3) {
+    double2 c01 = row01[0], c23 = row01[M];
+    c01.x += g0; c01.y += g1; c23.x += g2; c23.y += g3;
+    row01[0] = c01; row01[M] = c23;
+}
+__device__ __forceinline__ void cnt_update4(double2 *__restrict__ cw01, int M, bool act, unsigned sym, int rank,
+                                            double g0, double g1, double g2, double g3) {
+    const int myrank = act ? rank : -1;
+    const int maxrank = __reduce_max_sync(0xffffffffu, myrank);
+    double2 *row01 = cw01 + sym;
+    if (myrank == 0) cnt_rmw4(row01, M, g0, g1, g2, g3);
+    if (maxrank > 0) {  // warp-uniform
         __syncwarp();
+        if (myrank == 1) cnt_rmw4(row01, M, g0, g1, g2, g3);
+#pragma unroll 1
+        for (int r = 2; r <= maxrank; ++r) {
+            __syncwarp();
+            if (myrank == r) cnt_rmw4(row01, M, g0, g1, g2, g3);
+        }
     }
+    __syncwarp();
 }
 
 // all four non-negative doubles strictly positive? (integer pipe: x > 0 <=> hi|lo != 0)
@@ -420,15 +432,47 @@ __device__ __forceinline__ double zero_to_tiny(double x) {
     const int hi = __double2hiint(x), lo = __double2loint(x);
     return __hiloint2double(hi, lo | (((hi | lo) == 0) ? 1 : 0));
 }
+// smallest denormal if x > 0, else +0.0 (non-negative input; integer pipe)
+__device__ __forceinline__ double pos_to_tiny(double x) {
+    return __hiloint2double(0, ((__double2hiint(x) | __double2loint(x)) != 0) ? 1 : 0);
+}
+// Asynchronous 16-byte global -> shared copy (LDGSTS): the codeword chunk of the next 8 steps lands in a per-thread
+// shared-memory slot without holding registers while it is in flight.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+constexpr int BWD4_SPILL_PAD = 2;    // rows of padding in front of the alpha spill (see the step macro)
 constexpr int BWD_L2_PREFETCH = 12;  // steps ahead of use for prefetch.global.L2 of the alpha spill
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr double LEAN_MIN = 0x1p-500;  // the lean backward step needs its three sums above this
+constexpr unsigned LEAN_MIN_HI = (1023u - 500u) << 20;  // high word of LEAN_MIN = 2^-500
+
+// Normalisation without a division per step.  sum_i alpha_t(i) beta_t(i) = P(O|lambda) at EVERY t (it is what the
+// reference subtracts as logP, :389-410), and every rescale here is an exact power of two, so
+//     norm_t = sum_i alpha-hat_t(i) beta-hat_t(i) = norm_{T-1} * 2^k_t   up to rounding.
+// One true division per sequence gives rref = 1 / norm_{T-1}; afterwards r_t = rref * 2^-k_t comes from exponent
+// arithmetic: x = norm_t * rref ~ 2^k_t (1 + d); a quarter added to x's mantissa makes the exponent field read k_t
+// whether d is just above or just below zero.
+__device__ __forceinline__ double recip_from_ref(double norm, double rref) {
+    const double x = norm * rref;
+    const int e = (__double2hiint(x) + 0x00040000) & 0x7ff00000;
+    return __hiloint2double(__double2hiint(rref) - e + 0x3ff00000, __double2loint(rref));
+}
+// The same identity is the backward pass's precision check: |norm_t * r_t - 1| must stay at rounding level
+// (~T * 1e-16).  A beta-hat that lost its bits in a denormal / clamped value and later carries the sequence
+// (or any other loss in alpha-hat or beta-hat that matters for gamma) shows up here as a deviation of
+// sum_i alpha_t(i) beta_t(i) from P(O); beyond NORM_TOL the sequence is handed to the exact log-space kernel.
+constexpr double NORM_TOL = 1e-10;
+__device__ __forceinline__ bool norm_consistent(double norm, double r) { return fabs(fma(norm, r, -1.0)) <= NORM_TOL; }
 
 // State of one lane's backward recursion.
 template <bool BIDIAG>
 struct Bwd4State {
     double v0, v1, v2, v3;        // v_j = b_j(o_{t+1}) * beta-hat_{t+1}(j)
     double X[BIDIAG ? 7 : 16];    // sum_t u_i w_j (a_ij applied at the flush)
+    double rref;                  // 1 / sum_i alpha-hat_{T-1}(i): reference of the normalisation (see above)
     unsigned seenX;               // (i,j) pairs for which a finite xi term existed
     bool imprecise;
     bool vpos;                    // every v_j > 0 (lets the lean path skip the structural masks)
@@ -479,6 +523,9 @@ __device__ __noinline__ void bwd4_step_slow(Bwd4State<BIDIAG> &st, const double 
         r = norm > 0.0 ? 1.0 / norm : 0.0;
     } else {
         r = 1.0 / norm;
+        // sum_i alpha_t(i) beta_t(i) must still be P(O) (times a power of two): the backward precision check
+        if (last) st.rref = r;
+        else if (!norm_consistent(norm, recip_from_ref(norm, st.rref))) st.imprecise = true;
     }
     g0 *= r; g1 *= r; g2 *= r; g3 *= r;
     if (g0 == 0.0 && al0 > 0.0 && h0 > 0.0) g0 = tiny_pos();
@@ -525,24 +572,73 @@ __device__ __noinline__ void bwd4_step_slow(Bwd4State<BIDIAG> &st, const double 
     st.vpos = (v0 > 0.0) & (v1 > 0.0) & (v2 > 0.0) & (v3 > 0.0);
 }
 
+// (max, sum exp(. - max)) of log P_r over the sequences of one CTA work item, in a fixed order; the pairs of a
+// word's CTAs are combined by k_bw_reduce (HMM/hmm_training.py:503).  NaN marks (sequences still waiting for the
+// exact kernel) and -inf (impossible sequences) drop out.  Called by all BW_THREADS threads; out[0..1].
+__device__ __forceinline__ void cta_ll_stat(const Blk *__restrict__ blks, const CtaWork &cw, const double *__restrict__ ll_seq,
+                                            double (*sRed)[20], double *__restrict__ out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r0 = blks[cw.blk_begin].first, r1 = blks[cw.blk_end - 1].first + blks[cw.blk_end - 1].nseq;
+    double m = neg_inf();
+    for (int r = r0 + tid; r < r1; r += BW_THREADS) m = fmax(m, ll_seq[r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) sRed[warp][0] = m;
+    __syncthreads();
+    m = fmax(fmax(sRed[0][0], sRed[1][0]), fmax(sRed[2][0], sRed[3][0]));
+    double sum = 0.0;
+    if (m > neg_inf())
+        for (int r = r0 + tid; r < r1; r += BW_THREADS) {
+            const double l = ll_seq[r];
+            if (l > neg_inf()) sum += exp(l - m);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) sRed[warp][1] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        out[0] = m;
+        out[1] = ((sRed[0][1] + sRed[1][1]) + sRed[2][1]) + sRed[3][1];
+    }
+}
+
+// Pipelined first E-step only: there the exact kernel runs AFTER the staged backward passes, so a sequence the
+// forward pass handed over still carried its NaN mark when k_bw_bwd4 took the CTA's statistic.  Once the exact
+// kernel has filled in those log-likelihoods this kernel retakes every CTA's pair (it returns at once if no flag
+// was ever raised), which makes the staged pass equal to forward -> exact -> backward.
+__global__ void __launch_bounds__(BW_THREADS)
+k_bw_llstat_fix(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const double *__restrict__ ll_seq,
+                const int32_t *__restrict__ active, const uint8_t *__restrict__ flag, double *__restrict__ partials,
+                int64_t pstride, int M) {
+    if (!any_flag_raised(flag)) return;
+    __shared__ double sRed[BW_WARPS][20];
+    const CtaWork cw = work[blockIdx.x];
+    if (!active[cw.word]) return;
+    cta_ll_stat(blks, cw, ll_seq, sRed, partials + (size_t)blockIdx.x * pstride + 20 + (size_t)M * 4);
+}
+
 // Partial layout per CTA (and accumulator layout per word): [pi N][xi N*N][cnt M*N].
 //
 // The time loop is unrolled by two with fixed roles per parity of t, so that the two-deep
 // alpha-hat prefetch (P0 / P1) needs no register-to-register copies.
-template <bool BIDIAG>
+// MT = 256 (the reference's codebook size, CodeVector/main.py) makes every shared-memory offset a literal;
+// MT = 0 takes M at run time.
+template <bool BIDIAG, int MT>
 __global__ void __launch_bounds__(BW_THREADS, BIDIAG ? 4 : 3)
 k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
-          const int32_t *__restrict__ len_sorted, const double *__restrict__ A, const double *__restrict__ Bt, int M,
+          const int32_t *__restrict__ len_sorted, const double *__restrict__ A, const double *__restrict__ Bt, int M_rt,
           const double2 *__restrict__ spill, const double *__restrict__ ll_seq, const int32_t *__restrict__ active,
           const int32_t *__restrict__ b_has_zero, const uint8_t *__restrict__ allfull, double *__restrict__ partials,
           int64_t pstride, uint8_t *__restrict__ flag, int32_t *__restrict__ new_flags) {
     using S16 = Sym<uint16_t>;
+    const int M = MT ? MT : M_rt;
     extern __shared__ double smem[];
     double *sB = smem;                              // B^T: [M] double2 (b0,b1) then [M] double2 (b2,b3)
     double *sCnt = smem + (size_t)M * 4;            // [4 warps] x { [M] double2 (j=0,1), [M] double2 (j=2,3) }
     double *sPi = sCnt + (size_t)M * 4 * BW_WARPS;  // [128 threads][4] gamma_0 sums
     __shared__ double sRed[BW_WARPS][20];
     __shared__ unsigned sSeen;
+    __shared__ uint4 sW[2][BW_THREADS];  // codeword chunks in flight (cp.async), double-buffered per thread
 
     const CtaWork cw = work[blockIdx.x];
     double *part = partials + (size_t)blockIdx.x * pstride;
@@ -565,7 +661,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     const double tiny = tiny_pos();
     __syncthreads();
 
-    double2 *cntw01 = reinterpret_cast<double2 *>(sCnt + (size_t)warp * M * 4), *cntw23 = cntw01 + M;
+    double2 *cntw01 = reinterpret_cast<double2 *>(sCnt + (size_t)warp * M * 4);  // (j = 2, 3) rows M entries further
     const double2 *sB01 = reinterpret_cast<const double2 *>(sB), *sB23 = sB01 + M;
     double *mypi = sPi + (size_t)tid * 4;
     Bwd4State<BIDIAG> st;
@@ -586,6 +682,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         st.v0 = st.v1 = st.v2 = st.v3 = 0.0;
         st.imprecise = false;
         st.vpos = false;
+        st.rref = 1.0;
         const uint4 *op = obs_blk + bk.obs_base + lane;
         const double2 *sp = spill + bk.spill_base * 64 + lane;
         const int nch = (bk.tmax + SPC4 - 1) / SPC4;
@@ -599,7 +696,9 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
             if (ta & 1) { P1_01 = xa01; P1_23 = xa23; P0_01 = xb01; P0_23 = xb23; }
             else        { P0_01 = xa01; P0_23 = xa23; P1_01 = xb01; P1_23 = xb23; }
         }
-        uint4 wnext = __ldg(op + (size_t)(nch - 1) * 32);
+        int wbuf = 0;
+        cp_async16(&sW[0][tid], op + (size_t)(nch - 1) * 32);
+        cp_async_commit();
 
 // One backward step at time T_ (parity C_ = T_ & 1 is a literal; O_ = the other parity).
 #define HMMB_BWD_STEP(T_, C_, O_, SP_)                                                                              \
@@ -611,10 +710,10 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
             const unsigned sym = packed & SYM_MASK;                                                                 \
             const bool act = t < T;                                                                                 \
             const double al0 = P##C_##_01.x, al1 = P##C_##_01.y, al2 = P##C_##_23.x, al3 = P##C_##_23.y;            \
-            if (t >= 2 && t - 2 < T) {                                                                              \
-                P##C_##_01 = __ldcs(spt - 2 * 64);                                                                  \
-                P##C_##_23 = __ldcs(spt - 2 * 64 + 32);                                                             \
-            }                                                                                                       \
+            /* unconditional, two steps ahead: a row at or beyond a lane's own T is never used, and for t < 2 */   \
+            /* the load lands in the previous block's tail / the front padding of the spill (BWD4_SPILL_PAD)  */   \
+            P##C_##_01 = __ldcs(spt - 2 * 64);                                                                      \
+            P##C_##_23 = __ldcs(spt - 2 * 64 + 32);                                                                 \
             if (t >= BWD_L2_PREFETCH && t - BWD_L2_PREFETCH < T) { /* pull the spill towards L2 well ahead */      \
                 prefetch_l2(spt - BWD_L2_PREFETCH * 64);                                                            \
                 prefetch_l2(spt - BWD_L2_PREFETCH * 64 + 32);                                                       \
@@ -622,7 +721,20 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
             double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;                                                          \
             if (act) {                                                                                              \
                 bool done = false;                                                                                  \
-                if (lean_ok && st.vpos && t != T - 1) {                                                             \
+                if (t == T - 1) {                                                                                   \
+                    /* first step of the sequence, inline: log beta_{T-1} = 0 (:363), so beta-hat = 1, gamma =  */  \
+                    /* alpha-hat / sum alpha-hat, no xi term, v = b(o_{T-1}).  The one true division of the      */  \
+                    /* sequence; every later step derives its 1 / norm from it (recip_from_ref).                */  \
+                    const double n0 = (al0 + al1) + (al2 + al3); /* in [1, 2): the forward pass rescaled it */     \
+                    const double r0 = 1.0 / n0;                                                                     \
+                    st.rref = r0;                                                                                   \
+                    g0 = fma(al0, r0, pos_to_tiny(al0)); g1 = fma(al1, r0, pos_to_tiny(al1));                       \
+                    g2 = fma(al2, r0, pos_to_tiny(al2)); g3 = fma(al3, r0, pos_to_tiny(al3));                       \
+                    const double2 b01 = sB01[sym], b23 = sB23[sym];                                                 \
+                    st.v0 = b01.x; st.v1 = b01.y; st.v2 = b23.x; st.v3 = b23.y;                                     \
+                    st.vpos = all_pos4(b01.x, b01.y, b23.x, b23.y);                                                 \
+                    done = true;                                                                                    \
+                } else if (lean_ok && st.vpos) {                                                                    \
                     /* lean path: beta_t(i) ~ q_i = sum_j a_ij v_j (:163-199); gamma_t(i) = al_i q_i / norm   */   \
                     /* (:389-394); xi_t(i,j) = al_i a_ij v_j / norm (:397-410); norm = sum_i al_i q_i.  The    */   \
                     /* denormal addends keep a finite-but-underflowed log value (barely) positive.            */   \
@@ -642,14 +754,17 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                     const double qs = (q0 + q1) + (q2 + q3);                                                        \
                     const double c0 = al0 * q0, c1 = al1 * q1, c2 = al2 * q2, c3 = al3 * q3;                        \
                     const double norm = (c0 + c1) + (c2 + c3);                                                      \
+                    const double r = recip_from_ref(norm, st.rref); /* 1 / norm without a division */              \
                     const double sc = pow2_rescale_noacc(qs);                                                       \
                     const double h0 = q0 * sc, h1 = q1 * sc, h2 = q2 * sc, h3 = q3 * sc; /* beta-hat_t */          \
                     const double2 b01 = sB01[sym], b23 = sB23[sym];                                                 \
                     const double nv0 = fma(b01.x, h0, tiny), nv1 = fma(b01.y, h1, tiny);                            \
                     const double nv2 = fma(b23.x, h2, tiny), nv3 = fma(b23.y, h3, tiny);                            \
                     const double vs = (nv0 + nv1) + (nv2 + nv3);                                                    \
-                    if ((norm >= LEAN_MIN) & (qs >= LEAN_MIN) & (vs >= LEAN_MIN) && (apos || all_pos4(al0, al1, al2, al3))) { \
-                        const double r = 1.0 / norm;                                                                \
+                    /* the three sums are positive doubles: compare their high words on the integer pipe */        \
+                    const unsigned lo3 = min(min((unsigned)__double2hiint(norm), (unsigned)__double2hiint(qs)),     \
+                                             (unsigned)__double2hiint(vs));                                         \
+                    if ((lo3 >= LEAN_MIN_HI) & norm_consistent(norm, r) && (apos || all_pos4(al0, al1, al2, al3))) { \
                         g0 = fma(c0, r, tiny); g1 = fma(c1, r, tiny); g2 = fma(c2, r, tiny); g3 = fma(c3, r, tiny); \
                         const double u0 = al0 * r, u1 = al1 * r, u2 = al2 * r, u3 = al3 * r;                        \
                         if (BIDIAG) {                                                                               \
@@ -677,7 +792,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                     /* taken and stays in registers on the lean path                                     */         \
                     Bwd4State<BIDIAG> tmp = st;                                                                     \
                     double g[4];                                                                                    \
-                    bwd4_step_slow<BIDIAG>(tmp, a, sB01, sB23, sym, t == T - 1, al0, al1, al2, al3, g);             \
+                    bwd4_step_slow<BIDIAG>(tmp, a, sB01, sB23, sym, false, al0, al1, al2, al3, g);                  \
                     st = tmp;                                                                                       \
                     g0 = g[0]; g1 = g[1]; g2 = g[2]; g3 = g[3];                                                     \
                 }                                                                                                   \
@@ -686,14 +801,19 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                 }                                                                                                   \
             }                                                                                                       \
             /* emission-count numerators (:460-500): warp-private rows, conflict-free rank order */                \
-            cnt_update4(cntw01, cntw23, act, sym, (int)(packed >> SYM_BITS), g0, g1, g2, g3);                       \
+            cnt_update4(cntw01, M, act, sym, (int)(packed >> SYM_BITS), g0, g1, g2, g3);                            \
         }                                                                                                           \
     }
 
         const double2 *spp = sp + (size_t)(nch * SPC4 - 2) * 64;  // alpha-hat row of the even step of the pair
         for (int c = nch - 1; c >= 0; --c) {
-            uint4 w = wnext;
-            if (c > 0) wnext = __ldg(op + (size_t)(c - 1) * 32);  // prefetch the next 8 codewords
+            cp_async_wait_all();  // (issued eight steps ago)
+            uint4 w = sW[wbuf][tid];
+            wbuf ^= 1;
+            if (c > 0) {  // the next 8 codewords, straight into the other slot
+                cp_async16(&sW[wbuf][tid], op + (size_t)(c - 1) * 32);
+                cp_async_commit();
+            }
 #pragma unroll 1
             for (int pr = SPC4 / 2 - 1; pr >= 0; --pr) {
                 HMMB_BWD_STEP(c * SPC4 + 2 * pr + 1, 1, 0, spp + 64)
@@ -703,7 +823,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         }
 #undef HMMB_BWD_STEP
         if (st.imprecise) {  // sticky hand-over; the host redoes this E-step once (hmmb_bw_iterate)
-            flag[bk.first + lane] = 1;
+            raise_flag(flag, bk.first + lane);
             atomicAdd(new_flags, 1);
         }
     }
@@ -753,33 +873,9 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         const size_t o = (size_t)(j >> 1) * 2 * M + (size_t)sym * 2 + (j & 1);  // split (j=0,1) / (j=2,3) arrays
         part[20 + e] = ((sCnt[o] + sCnt[(size_t)M * 4 + o]) + sCnt[(size_t)M * 8 + o]) + sCnt[(size_t)M * 12 + o];
     }
-    // ---- this CTA's share of the convergence statistic log_sum_exp_r log P_r (:503): (max, sum exp(. - max))
-    // over its own sequences, combined over the word's CTAs in fixed order by k_bw_reduce
-    {
-        const int r0 = blks[cw.blk_begin].first, r1 = blks[cw.blk_end - 1].first + blks[cw.blk_end - 1].nseq;
-        double m = neg_inf();
-        for (int r = r0 + tid; r < r1; r += BW_THREADS) m = fmax(m, ll_seq[r]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-        __syncthreads();  // sRed is free again
-        if (lane == 0) sRed[warp][0] = m;
-        __syncthreads();
-        m = fmax(fmax(sRed[0][0], sRed[1][0]), fmax(sRed[2][0], sRed[3][0]));
-        double sum = 0.0;
-        if (m > neg_inf())
-            for (int r = r0 + tid; r < r1; r += BW_THREADS) {
-                const double l = ll_seq[r];
-                if (l > neg_inf()) sum += exp(l - m);
-            }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) sRed[warp][1] = sum;
-        __syncthreads();
-        if (tid == 0) {
-            part[20 + (size_t)M * 4] = m;
-            part[20 + (size_t)M * 4 + 1] = ((sRed[0][1] + sRed[1][1]) + sRed[2][1]) + sRed[3][1];
-        }
-    }
+    // ---- this CTA's share of the convergence statistic log_sum_exp_r log P_r (:503)
+    __syncthreads();  // sRed is free again
+    cta_ll_stat(blks, cw, ll_seq, sRed, part + 20 + (size_t)M * 4);
 }
 
 }  // namespace hmmb

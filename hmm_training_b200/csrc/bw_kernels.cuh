@@ -60,7 +60,7 @@ k_bw_fwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
                                                    sStage[warp]);
         if (T > 0 && j == 0) {
             ll_seq[r] = ll;
-            if (ll != ll) flag[r] = 1;  // precision guard: hand over to the exact kernel (sticky)
+            if (ll != ll) raise_flag(flag, r);  // precision guard: hand over to the exact kernel (sticky)
         }
     }
 }
@@ -208,7 +208,7 @@ k_bw_bwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
         {
             const unsigned bal = __ballot_sync(0xffffffffu, imprecise && T > 0);
             if (((bal >> gbase) & gmask) != 0u && T > 0 && i == 0) {
-                flag[r] = 1;
+                raise_flag(flag, r);
                 atomicAdd(new_flags, 1);
             }
             imprecise = false;
@@ -229,6 +229,7 @@ k_bw_exact(const void *__restrict__ obs, const int64_t *__restrict__ base_sorted
            const double *__restrict__ A, const double *__restrict__ Bt, double *__restrict__ ll_seq,
            const int32_t *__restrict__ active, const uint8_t *__restrict__ flag, double *__restrict__ scratch,
            int64_t scratch_stride, double *__restrict__ accum, int64_t astride, int64_t *__restrict__ n_exact) {
+    if (!any_flag_raised(flag)) return;  // nothing was ever handed over: no scan of the R flags
     const int lane = threadIdx.x & 31;
     const int64_t gw = (int64_t)blockIdx.x * BW_WARPS + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * BW_WARPS;

@@ -95,7 +95,6 @@ __device__ __forceinline__ unsigned max_hiN(const double (&x)[N]) {
     for (int i = 0; i < N; ++i) m = max(m, (unsigned)__double2hiint(x[i]));
     return m;
 }
-constexpr unsigned LEAN_MIN_HI = (1023u - 500u) << 20;  // high word of LEAN_MIN = 2^-500
 
 // Exponent-split products (see exact_products4): out_j = n_j*b_j * 2^-E.  Arrays in local memory.
 template <int NS>
@@ -328,7 +327,7 @@ k_bw_fwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         if (T > 0) {
             ll_seq[bk.first + lane] = ll;
             allfull[bk.first + lane] = af ? 1 : 0;
-            if (ll != ll) flag[bk.first + lane] = 1;  // precision guard: hand over (sticky)
+            if (ll != ll) raise_flag(flag, bk.first + lane);  // precision guard: hand over (sticky)
         }
     }
 }
@@ -702,7 +701,7 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
             }
         }
         if (imprecise) {  // sticky hand-over; the host redoes this E-step once (hmmb_bw_iterate)
-            flag[bk.first + lane] = 1;
+            raise_flag(flag, bk.first + lane);
             atomicAdd(new_flags, 1);
         }
     }

@@ -55,6 +55,18 @@ constexpr double ERR_UNIT = 0x1p-74;              // smallest denormal (2^-1074)
 constexpr double ERR_LIMIT = 1e-12 * 0x1p1000;    // relative bound 1e-12 in the same units
 constexpr double SUBNORMAL_LIMIT = 0x1p-1021;
 
+// Per-sequence hand-over flags (sticky, uint8 [R]) carry a 16-byte header in front of the array whose first int is
+// "some flag is set": the exact kernel, launched every iteration, returns at once while it is zero instead of
+// scanning R flags.
+constexpr int FLAG_HDR = 16;
+__device__ __forceinline__ void raise_flag(uint8_t *flag, int64_t i) {
+    flag[i] = 1;
+    *reinterpret_cast<volatile int *>(flag - FLAG_HDR) = 1;
+}
+__device__ __forceinline__ bool any_flag_raised(const uint8_t *flag) {
+    return *reinterpret_cast<const volatile int *>(flag - FLAG_HDR) != 0;
+}
+
 __device__ __forceinline__ double nan_mark() { return __longlong_as_double(0x7ff8000000000000LL); }
 // zero or denormal (non-negative input): exponent field is 0
 __device__ __forceinline__ bool is_sub(double x) { return (unsigned)__double2hiint(x) < 0x00100000u; }

@@ -35,16 +35,27 @@ def default_init(N: int, M: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
 
 
 # ------------------------------------------------------------------------------- VQ / LBG
-def vq_encode(X: np.ndarray, C: np.ndarray) -> np.ndarray:
+def vq_encode(X: np.ndarray, C: np.ndarray, near_ties: bool = False, near_cap: int = 1 << 20):
     """Nearest-centroid indices (int32 [F]) of frames X [F,13] against codebook C [K,13];
-    dims 1..12 only, lowest index wins ties (HMM/hmm_training.py:95-118)."""
+    dims 1..12 only, lowest index wins ties (HMM/hmm_training.py:95-118).
+
+    near_ties=True also returns the parity contract's near-tie report: (idx, near, n_near) with ``near`` the
+    ascending frame numbers (at most near_cap of them) whose two smallest distances differ by less than 1e-12
+    relative — exact ties between duplicate centroids included — and n_near their total count.  Those are the
+    frames whose index could differ under another BLAS's summation order in the reference's np.linalg.norm."""
     X = c_f64(X)
     C = c_f64(C)
     if X.ndim != 2 or X.shape[1] != 13 or C.ndim != 2 or C.shape[1] != 13:
         raise ValueError("Vectors must be of size 13.")  # codevector_functions.py:84
     idx = np.empty(X.shape[0], dtype=np.int32)
-    check(_lib.load().hmmb_vq_encode(ptr(X), X.shape[0], ptr(C), C.shape[0], ptr(idx)))
-    return idx
+    if not near_ties:
+        check(_lib.load().hmmb_vq_encode(ptr(X), X.shape[0], ptr(C), C.shape[0], ptr(idx)))
+        return idx
+    near = np.empty(max(min(int(near_cap), X.shape[0]), 1), dtype=np.int32)
+    n_near = ctypes.c_int64(0)
+    check(_lib.load().hmmb_vq_encode_ex(ptr(X), X.shape[0], ptr(C), C.shape[0], ptr(idx), ptr(near), len(near),
+                                        ctypes.byref(n_near)))
+    return idx, near[:min(n_near.value, len(near))].copy(), int(n_near.value)
 
 
 def mfcc_frames(Y: np.ndarray, sr: float = 16000.0) -> np.ndarray:
@@ -83,11 +94,12 @@ def _wrap_allreduce(fn: Optional[Callable[[int, int], None]]):
 
 def lbg_fit(X, K: int = 256, max_iterations: int = 100, epsilon: float = 0.001,
             allreduce: Optional[Callable[[int, int], None]] = None, x_dev_ptr: Optional[int] = None,
-            F: Optional[int] = None):
+            F: Optional[int] = None, history: bool = False):
     """LBG codebook (CodeVector/codevector_functions.py:442-531) on frames X [F,13].
 
     Returns (centroids [Kout,13], generations list of arrays, assign int32 [F],
-    iters_per_generation int32 [n_gen], last global distance per generation)."""
+    iters_per_generation int32 [n_gen], last global distance per generation); with history=True a sixth item:
+    the list (one array per generation) of the summed distance after every Lloyd pass (:503, printed at :512-516)."""
     lib = _lib.load()
     if x_dev_ptr is None:
         X = c_f64(X)
@@ -107,16 +119,20 @@ def lbg_fit(X, K: int = 256, max_iterations: int = 100, epsilon: float = 0.001,
     assign = np.zeros(max(F, 1), dtype=np.int32)
     iters = np.zeros(max(n_gen, 1), dtype=np.int32)
     gdist = np.zeros(max(n_gen, 1))
+    hist = np.full((max(n_gen, 1), max(int(max_iterations), 1)), np.nan) if history else None
     cfn, keep = _wrap_allreduce(allreduce)
-    rc = check(lib.hmmb_lbg_fit(xp, F, on_dev, K, int(max_iterations), float(epsilon), ptr(C), ptr(gens),
-                                ptr(assign), ptr(iters), ptr(gdist),
-                                ctypes.cast(cfn, ctypes.c_void_p) if cfn else None, None))
+    rc = check(lib.hmmb_lbg_fit_ex(xp, F, on_dev, K, int(max_iterations), float(epsilon), ptr(C), ptr(gens),
+                                   ptr(assign), ptr(iters), ptr(gdist), ptr(hist),
+                                   ctypes.cast(cfn, ctypes.c_void_p) if cfn else None, None))
     del keep
     out, pos = [gens[0:1].copy()], 1
     for g in range(1, n_gen + 1):
         out.append(gens[pos:pos + (1 << g)].copy())
         pos += 1 << g
-    return C[:rc].copy(), out, assign[:F], iters[:n_gen], gdist[:n_gen]
+    res = (C[:rc].copy(), out, assign[:F], iters[:n_gen], gdist[:n_gen])
+    if history:
+        res += ([hist[g, :iters[g]].copy() for g in range(n_gen)],)
+    return res
 
 
 # ------------------------------------------------------------------------------- Baum-Welch

@@ -84,6 +84,14 @@ int hmmb_vq_encode(const double *X, int64_t F, const double *C, int K, int32_t *
 /* same on device-resident buffers; d_dist (nullable) receives the winning distance       */
 int hmmb_vq_encode_dev(const double *dX, int64_t F, const double *dC, int K, int32_t *d_idx,
                        double *d_dist);
+/* hmmb_vq_encode + the near-tie report of the parity contract (BASELINE.json north_star: "codeword indices
+ * bit-exact (near-ties within a stated epsilon documented)"): near_out [near_cap] (nullable if near_cap == 0)
+ * receives, in ascending order, the frames whose two smallest distances differ by less than 1e-12 relative
+ * ((d2 - d1) / d1 < 1e-12, exact ties included) — the frames whose index, decided by hmm_training.py:112's
+ * strict '<', could differ under another BLAS's summation order; *n_near_out = how many there are (it may
+ * exceed near_cap).  At most 2^31-1 frames per call.                                                        */
+int hmmb_vq_encode_ex(const double *X, int64_t F, const double *C, int K, int32_t *idx_out, int32_t *near_out,
+                      int64_t near_cap, int64_t *n_near_out);
 
 /* ------------------------------------------------------------------ LBG codebook
  * Replaces createCodeVector, CodeVector/codevector_functions.py:442-531 (with
@@ -99,6 +107,12 @@ int hmmb_vq_encode_dev(const double *dX, int64_t F, const double *dC, int K, int
 int hmmb_lbg_fit(const double *X, int64_t F, int x_on_device, int K, int max_iter, double eps,
                  double *C_out, double *gens_out, int32_t *assign_out, int32_t *iters_per_gen,
                  double *gdist_out, hmmb_allreduce_fn allreduce, void *user);
+/* same + gdist_hist [n_gen, max(max_iter, 1)] (nullable): the summed distance after EVERY Lloyd pass of every
+ * generation (row g holds iters_per_gen[g] values) — what the reference prints as dist / diff every tenth pass
+ * and as the final diff of a generation (codevector_functions.py:509-516).                                   */
+int hmmb_lbg_fit_ex(const double *X, int64_t F, int x_on_device, int K, int max_iter, double eps,
+                    double *C_out, double *gens_out, int32_t *assign_out, int32_t *iters_per_gen,
+                    double *gdist_out, double *gdist_hist, hmmb_allreduce_fn allreduce, void *user);
 
 /* ------------------------------------------------------------------ Baum-Welch
  * Replaces hmm_training, HMM/hmm_training.py:265-541, batched over W word models:

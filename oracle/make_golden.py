@@ -160,7 +160,8 @@ def _lbg_case(ref, name, X, K, max_iter, eps=0.001):
                         gens=gens_flat, gen_sizes=np.array([len(g) for g in gens]),
                         assign=np.array([f.parent_centroid_id for f in frames], dtype=np.int32),
                         generation=np.array([f.generation for f in frames], dtype=np.int32),
-                        iters=np.array(iters, dtype=np.int32))
+                        iters=np.array(iters, dtype=np.int32),
+                        stdout=np.array(buf.getvalue()))  # the reference's own prints (progress lines, :472, :512-516)
     print(f"  {name}: iters {iters}", flush=True)
 
 

@@ -256,6 +256,45 @@ def test_pipelined_upload_matches_plain_create(S, ragged):
         _lib.load().hmmb_host_free(handle)
 
 
+def test_pipelined_upload_with_forward_handover():
+    """in the pipelined first E-step the exact kernel runs after the staged backward passes, so
+    the per-CTA convergence statistic taken inside k_bw_bwd4 missed every sequence the forward precision guard had
+    handed over in that very pass.  Warm start from models with denormal / 1e-300 / zero emissions (what saved
+    reference models look like after safe_exp underflow): the pipelined fit must reproduce the plain path's
+    log-likelihood history bit for bit, and the case must actually exercise the exact kernel."""
+    from hmm_training_b200 import _lib, engine
+    from test_gpu_parity import _tiny_models
+    N, M, W, S = 4, 16, 3, 70000
+    rng = np.random.default_rng(9)
+    pi0, A0, B0 = _tiny_models(rng, W, N, M)
+    lens = np.concatenate([np.sort(rng.integers(2, 60, size=S))[::-1] for _ in range(W)]).astype(np.int64)
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    obs = rng.integers(0, M, size=int(offsets[-1])).astype(np.uint8)
+    wos = np.repeat(np.arange(W, dtype=np.int32), S)
+    assert obs.nbytes >= 4 << 20  # large enough for the chunked upload
+    pinned, handle = _pinned_copy(obs)
+    try:
+        with engine.BaumWelch(pinned, offsets, wos, W, N, M, pipeline_upload=True, init=(pi0, A0, B0)) as bw:
+            bw.iterate(3, -1.0, 3)
+            a = bw.params() + bw.history(3)
+            exact_a, _ = bw.diagnostics()
+        with engine.BaumWelch(obs, offsets, wos, W, N, M) as bw:  # pageable input: plain path
+            bw.set_params(pi0, A0, B0)
+            bw.iterate(3, -1.0, 3)
+            b = bw.params() + bw.history(3)
+            exact_b, _ = bw.diagnostics()
+        assert exact_a > 0 and exact_a == exact_b
+        assert np.isfinite(b[3][:, 0]).all()
+        # the statistic of the first iteration is reduced in a fixed order: bit-identical; everything downstream of the
+        # exact kernel's fp64 atomics (parameters, later iterations) agrees to rounding
+        assert np.array_equal(a[3][:, 0], b[3][:, 0])
+        assert np.array_equal(a[4], b[4])
+        for x, y, what in zip(a[:4], b[:4], ("pi", "A", "B", "history")):
+            assert_close(x, y, what, rtol=1e-11)
+    finally:
+        _lib.load().hmmb_host_free(handle)
+
+
 @pytest.mark.parametrize("tiny", [False, True])
 def test_pipelined_scorer_matches_plain(tiny, monkeypatch):
     """Recognition on a large PINNED codeword buffer runs in stages behind the upload, with each stage's

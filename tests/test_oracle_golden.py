@@ -69,3 +69,28 @@ def test_oracle_errors():
         O.hmm_training([np.array([], dtype=np.int64)], max_iterations=1)
     with pytest.raises(ValueError):
         vq_oracle.lbg(np.zeros((0, 13)), 4)
+
+
+def test_chunked_em_iteration_equals_pinned_trainer():
+    """oracle.em_iteration_chunked (used by the full-size GPU parity tests) is the loop body of the pinned
+    hmm_training, reduced chunk by chunk with log_sum_exp: one and two iterations must agree to rounding,
+    including the 1e-20 floor pattern and structural zeros."""
+    import numpy as np
+    from hmm_training_b200 import synthetic
+    from oracle import hmm_oracle as O
+    corpus = synthetic.word_corpus(3, 2, 24)
+    for w, seqs in enumerate(corpus):
+        init = O.default_init(4, 256)
+        A1, B1, p1, h, it = O.hmm_training(seqs, max_iterations=1, return_history=True)
+        (A2, B2, p2), ll = O.em_iteration_chunked(seqs, init, 256, chunk=5, procs=2 if w else 1)
+        assert abs(ll - h[0]) <= 1e-12 * abs(h[0])
+        for x, y in ((A1, A2), (B1, B2), (p1, p2)):
+            assert np.array_equal(x == 0, y == 0)
+            assert np.all(np.abs(x - y) <= 1e-12 * np.abs(x) + 1e-300)
+        # a second iteration chained from the un-normalised log parameters
+        lp, lA, lB = O.mstep_from_logsums(O.merge_logsums([O.estep_logsums(seqs, O.safe_log(init[0]), O.safe_log(init[1]),
+                                                                           O.safe_log(init[2]), 256)]), 4, 256)
+        (A3, B3, p3), _ = O.em_iteration_chunked(seqs, (O.safe_exp(lp), O.safe_exp(lA), O.safe_exp(lB)), 256, chunk=7)
+        A4, B4, p4 = O.hmm_training(seqs, max_iterations=2, epsilon=-1.0)
+        for x, y in ((A4, A3), (B4, B3), (p4, p3)):
+            assert np.all(np.abs(x - y) <= 1e-11 * np.abs(x) + 1e-300)

@@ -150,3 +150,59 @@ def bind_to_gpu_cpus(device_index: int) -> int:
         return len(target)
     except Exception:
         return 0
+
+
+# ----------------------------------------------------------------------------- pure shards
+def _gather_rows(local: np.ndarray, counts: Sequence[int], group=None, device: str = "cuda") -> np.ndarray:
+    """All-gather of per-rank row blocks (rank r holds counts[r] rows) into the full array on every rank.  The
+    blocks are padded to the largest one so that one all_gather moves them (NCCL over NVLink for device='cuda',
+    gloo for the CPU tests of this plumbing)."""
+    import torch
+    import torch.distributed as dist
+    world = len(counts)
+    if world == 1:
+        return local
+    mx = max(int(c) for c in counts)
+    shape = (mx,) + tuple(local.shape[1:])
+    pad = np.zeros(shape, dtype=local.dtype)
+    pad[: local.shape[0]] = local
+    t = torch.from_numpy(pad)
+    if device != "cpu":
+        t = t.cuda()
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    return np.concatenate([o.cpu().numpy()[: int(c)] for o, c in zip(outs, counts)], axis=0)
+
+
+def score_sharded(obs, offsets, N: int, M: int, pi, A, B, rank: int, world: int, group=None, device: str = "cuda",
+                  gather: bool = True, scorer=None):
+    """test_hmm's scoring loop (HMM/hmm_testing.py:139-153) sharded over `world` ranks: rank r scores the contiguous
+    utterance range shard_range(U, r, world) against all models on its GPU; no collective on the data path, the
+    [U_r, W] blocks and argmax vectors are all-gathered afterwards (gather=False returns the local block and its
+    range instead).  Returns (ll [U, W], argmax [U]) on every rank."""
+    from . import engine
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    U = len(offsets) - 1
+    lo, hi = shard_range(U, rank, world)
+    loc_off = offsets[lo:hi + 1] - offsets[lo]
+    loc_obs = obs[int(offsets[lo]):int(offsets[hi])]
+    ll, arg = (scorer or engine.score)(loc_obs, loc_off, N, M, pi, A, B)
+    if not gather:
+        return ll, arg, (lo, hi)
+    counts = [shard_range(U, r, world)[1] - shard_range(U, r, world)[0] for r in range(world)]
+    return (_gather_rows(np.ascontiguousarray(ll), counts, group, device),
+            _gather_rows(np.ascontiguousarray(arg), counts, group, device))
+
+
+def vq_encode_sharded(X: np.ndarray, C: np.ndarray, rank: int, world: int, group=None, device: str = "cuda",
+                      gather: bool = True, encoder=None):
+    """get_observations' frame loop (HMM/hmm_training.py:95-118) sharded over ranks: contiguous frame ranges, no
+    collective on the data path, indices all-gathered afterwards."""
+    from . import engine
+    F = X.shape[0]
+    lo, hi = shard_range(F, rank, world)
+    idx = (encoder or engine.vq_encode)(X[lo:hi], C)
+    if not gather:
+        return idx, (lo, hi)
+    counts = [shard_range(F, r, world)[1] - shard_range(F, r, world)[0] for r in range(world)]
+    return _gather_rows(np.ascontiguousarray(idx), counts, group, device)

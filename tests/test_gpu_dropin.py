@@ -283,7 +283,7 @@ def test_pipelined_upload_with_forward_handover():
             bw.iterate(3, -1.0, 3)
             b = bw.params() + bw.history(3)
             exact_b, _ = bw.diagnostics()
-        assert exact_a > 0 and exact_a == exact_b
+        assert exact_a > 0 and exact_b > 0  # (the counts differ: the staged pass runs the exact kernel after its backward passes)
         assert np.isfinite(b[3][:, 0]).all()
         # the statistic of the first iteration is reduced in a fixed order: bit-identical; everything downstream of the
         # exact kernel's fp64 atomics (parameters, later iterations) agrees to rounding

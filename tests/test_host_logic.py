@@ -149,6 +149,51 @@ def test_allreduce_hook_and_llstats_gather_over_gloo():
     assert np.array_equal(res[0][1], res[1][1])
 
 
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hmm_training_b200 import synthetic
+    from oracle import vq_oracle
+    rng = np.random.default_rng(4)
+    seqs = [rng.integers(0, 16, size=int(rng.integers(1, 30))) for _ in range(37)]  # ragged, not divisible by 2
+    obs = np.concatenate(seqs).astype(np.uint8)
+    offsets = np.concatenate([[0], np.cumsum([len(x) for x in seqs])]).astype(np.int64)
+    W, N, M = 3, 4, 16
+    pi = rng.dirichlet(np.ones(N), size=W); A = rng.dirichlet(np.ones(N), size=(W, N)); B = rng.dirichlet(np.ones(M), size=(W, N))
+
+    def cpu_scorer(o, off, N_, M_, pi_, A_, B_):  # the oracle stands in for the GPU scorer: this test is about the shards
+        ss = [o[off[u]:off[u + 1]].astype(np.int64) for u in range(len(off) - 1)]
+        ll = O.score_batch(ss, [(A_[w], B_[w], pi_[w]) for w in range(len(pi_))]) if ss else np.zeros((0, len(pi_)))
+        return ll, O.argmax_first(ll).astype(np.int32) if len(ss) else np.zeros(0, np.int32)
+
+    ll, arg = hdist.score_sharded(obs, offsets, N, M, pi, A, B, rank, world, device="cpu", scorer=cpu_scorer)
+    X = synthetic.mfcc_mixture(1, 101, K=8); C = synthetic.random_codebook(2, 8)
+    idx = hdist.vq_encode_sharded(X, C, rank, world, device="cpu", encoder=vq_oracle.encode)
+    full_ll, full_arg = cpu_scorer(obs, offsets, N, M, pi, A, B)
+    q.put((rank, bool(np.array_equal(ll, full_ll)), bool(np.array_equal(arg, full_arg)),
+           bool(np.array_equal(idx, vq_oracle.encode(X, C)))))
+    dist.destroy_process_group()
+
+
+def test_sharded_scoring_and_encoding_over_gloo():
+    """world_size 2 on CPU: utterance / frame ranges per rank, blocks all-gathered in rank order (config 5's
+    "1-8 B200" path; the per-shard compute is the GPU's in production and the oracle's here)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] and r[2] and r[3] for r in res)
+
+
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU: exactly one JSON
     line on stdout with the contract's keys, everything else on stderr."""

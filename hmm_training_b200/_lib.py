@@ -38,6 +38,7 @@ SYMBOLS = [
     ("hmmb_phase_ms", _c.c_double, [_c.c_char_p, _lp]),
     ("hmmb_phase_reset", _c.c_int, []),
     ("hmmb_set_profiling", _c.c_int, [_c.c_int]),
+    ("hmmb_peak_probe", _c.c_int, [_c.c_int, _dp]),
     ("hmmb_comm_unique_id", _c.c_int, [_c.c_void_p, _c.c_int]),
     ("hmmb_comm_init", _c.c_int, [_c.c_int, _c.c_int, _c.c_void_p]),
     ("hmmb_comm_allreduce", _c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p]),

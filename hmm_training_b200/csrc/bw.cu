@@ -95,6 +95,86 @@ k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4
     }
 }
 
+// Scorer with the eightfold-replicated B^T (conflict-free gather, see fwd4_run) and the lean forward pass
+// (score4_lean_run) for models that allow it; 8 warps per CTA, one model per CTA, M <= SCORE4R_MAX_M.
+// Shared memory: [M * 8] double2 (b0, b1), [M * 8] double2 (b2, b3), [M] per-codeword max, [M] support masks.
+constexpr int SCORE4R_WARPS = 8;
+constexpr int SCORE4R_REP = 8;
+constexpr int SCORE4R_MAX_M = 256;  // 64 KB of replicated B^T: three CTAs per SM
+template <bool BIDIAG, bool VECB>
+__global__ void __launch_bounds__(SCORE4R_WARPS * 32, 2)
+k_score4r(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4 *__restrict__ obs_blk,
+          const int32_t *__restrict__ len_sorted, const int32_t *__restrict__ order, const double *__restrict__ pi,
+          const double *__restrict__ A, const double *__restrict__ Bt, int M, int W, double *__restrict__ ll_out,
+          int32_t *__restrict__ any_nan) {
+    extern __shared__ double sB[];
+    constexpr int REP = SCORE4R_REP, NT = SCORE4R_WARPS * 32;
+    // fixed SCORE4R_MAX_M-entry layout whatever M is: the second table sits at a literal offset from the first
+    double2 *sB01 = reinterpret_cast<double2 *>(sB), *sB23 = sB01 + (size_t)SCORE4R_MAX_M * REP;
+    double *sBmax = reinterpret_cast<double *>(sB23 + (size_t)SCORE4R_MAX_M * REP);
+    unsigned char *sBmask = reinterpret_cast<unsigned char *>(sBmax + M);
+    const int w = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int has_zero = 0;
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(Bt + (size_t)w * M * 4);
+        for (int e = tid; e < M * REP; e += NT) {
+            const int sym = e / REP;
+            const double2 x = __ldg(src + 2 * sym), y = __ldg(src + 2 * sym + 1);
+            sB01[e] = x;
+            sB23[e] = y;
+            if (e % REP == 0) {
+                sBmax[sym] = fmax(fmax(x.x, x.y), fmax(y.x, y.y));
+                const unsigned char mb = (unsigned char)((x.x > 0.0 ? 1 : 0) | (x.y > 0.0 ? 2 : 0) | (y.x > 0.0 ? 4 : 0) | (y.y > 0.0 ? 8 : 0));
+                sBmask[sym] = mb;
+                has_zero |= (mb != 0xF);
+            }
+        }
+    }
+    double a[BIDIAG ? 7 : 16], p[4], rmax;
+    Masks4 mk;
+    load_Api4<BIDIAG>(pi, A, w, a, p, rmax, mk);
+    const bool b_has_zero = __syncthreads_or(has_zero) != 0;
+    // alive sets without emission zeros: m_0 = support of pi, m_t = lutF(m_t-1); lean from the first t with m_t = all
+    int tstar = -1;
+    {
+        unsigned m = mk.pmask;
+        for (int t = 0; t < 4 && tstar < 0; ++t) {
+            if (m == 0xFu && lut4(mk.lutF, 0xFu) == 0xFu) tstar = t;
+            m = lut4(mk.lutF, m);
+        }
+    }
+    const bool lean_model = !b_has_zero && tstar >= 0;
+    const int slot = lane & (REP - 1);
+    const int b0 = blockIdx.x * blocks_per_cta;
+    const int b1 = min(nblk, b0 + blocks_per_cta);
+    for (int b = b0 + warp; b < b1; b += SCORE4R_WARPS) {
+        const Blk bk = blks[b];
+        const int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
+        const uint4 *op = obs_blk + bk.obs_base + lane;
+        double ll;
+        bool redo = !lean_model;
+        if (lean_model) {
+            bool bad;
+            ll = score4_lean_run<BIDIAG, REP>(T, bk.tmax, op, sB01 + slot, sB01 + slot + (size_t)SCORE4R_MAX_M * REP, a, p, mk, tstar, bad);
+            redo = __any_sync(0xffffffffu, bad && T > 0);
+            if (redo) {  // (rare) the marked lanes again, with the full structural / precision logic
+                bool af;
+                const double ll2 = fwd4_run<BIDIAG, false, VECB, REP>(bad ? T : 0, bk.tmax, op, sB01, sB23, sBmax, sBmask, a, p, rmax,
+                                                                      mk, nullptr, af, slot);
+                if (bad) ll = ll2;
+            }
+        } else {
+            bool af;
+            ll = fwd4_run<BIDIAG, false, VECB, REP>(T, bk.tmax, op, sB01, sB23, sBmax, sBmask, a, p, rmax, mk, nullptr, af, slot);
+        }
+        if (lane < bk.nseq) {
+            ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
+            if (ll != ll) *any_nan = 1;  // precision guard marked this pair: k_score_exact has work to do
+        }
+    }
+}
+
 template <int NP, typename SymT>
 __global__ void __launch_bounds__(BW_THREADS)
 k_scoreG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, const int32_t *__restrict__ len_sorted,
@@ -1361,6 +1441,24 @@ static int launch_score_special(SeqSet &s, int W, const double *d_pi, const doub
     if (b1 < 0) b1 = s.nblk;
     const int nb = b1 - b0;  // blocks [b0, b1) (a stage of the pipelined scorer, or all of them)
     if (nb <= 0) return HMMB_OK;
+    if (s.M <= SCORE4R_MAX_M && !getenv("HMMB_SCORE_NO_REPLICAS")) {
+        // replicated-B scorer: 8 warps per CTA, 2 CTAs per SM, about six waves of CTAs
+        int bpc = std::max(SCORE4R_WARPS, (int)(((int64_t)nb * W + c.sm_count * 12 - 1) / (c.sm_count * 12)));
+        bpc = (bpc + SCORE4R_WARPS - 1) / SCORE4R_WARPS * SCORE4R_WARPS;
+        bpc = std::min(bpc, 128);
+        dim3 g((unsigned)((nb + bpc - 1) / bpc), (unsigned)W);
+        const size_t smem = (size_t)SCORE4R_MAX_M * SCORE4R_REP * 2 * sizeof(double2) + (size_t)s.M * sizeof(double) + (size_t)((s.M + 15) & ~15);
+        if (s.tmax_all > SCORE4_SCALAR_BOUND_MAX_T) {
+            HMMB_CUDA(cudaFuncSetAttribute((k_score4r<BIDIAG, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HMMB_LAUNCH("score", (k_score4r<BIDIAG, true>), g, SCORE4R_WARPS * 32, smem, s.d_blks + b0, nb, bpc, (const uint4 *)s.d_obs,
+                        s.d_len, s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll, d_nan);
+        } else {
+            HMMB_CUDA(cudaFuncSetAttribute((k_score4r<BIDIAG, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HMMB_LAUNCH("score", (k_score4r<BIDIAG, false>), g, SCORE4R_WARPS * 32, smem, s.d_blks + b0, nb, bpc, (const uint4 *)s.d_obs,
+                        s.d_len, s.d_order, d_pi, d_A, d_Bt, s.M, W, d_ll, d_nan);
+        }
+        return HMMB_OK;
+    }
     // each CTA re-uses one model's B for several 32-utterance blocks
     int bpc = std::max(BW_WARPS, (s.nblk * W + c.sm_count * 16 - 1) / (c.sm_count * 16));
     bpc = (bpc + BW_WARPS - 1) / BW_WARPS * BW_WARPS;

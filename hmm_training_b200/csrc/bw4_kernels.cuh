@@ -21,6 +21,8 @@
 // Skipped terms are exact zeros, so the results are bit-identical to the dense kernel.
 #pragma once
 
+#include <type_traits>
+
 #include "hmm_device.cuh"
 
 namespace hmmb {
@@ -178,13 +180,17 @@ __device__ __forceinline__ double tiny_if(unsigned m, int j) { return __hiloint2
 //     transition it grows by ~1 / a_i,i+1 against the true mass; fine for utterance lengths (used by the
 //     issue-bound scorer when no utterance exceeds SCORE4_SCALAR_BOUND_MAX_T), trips after a few thousand
 //     frames with peaked emissions.
-template <bool BIDIAG, bool SPILL, bool VECB = true>
+//
+// REP = 8: B^T is stored eight times, entry (sym, r) at index sym * 8 + r, and a lane reads replica r = lane & 7:
+// the eight lanes of a quarter-warp then always hit eight different 16-byte bank slots, so the gather is free of
+// bank conflicts whatever the codewords are (used by the scorer, whose only shared-memory traffic it is).
+template <bool BIDIAG, bool SPILL, bool VECB = true, int REP = 1>
 __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restrict__ op,
                                            const double2 *__restrict__ sB01, const double2 *__restrict__ sB23,
                                            const double *__restrict__ sBmax,
                                            const unsigned char *__restrict__ sBmask, const double *a,
                                            const double (&p)[4], double rmax, const Masks4 &mk,
-                                           double2 *__restrict__ sp, bool &allfull) {
+                                           double2 *__restrict__ sp, bool &allfull, int slot = 0) {
     using S16 = Sym<uint16_t>;
     double al0 = 0.0, al1 = 0.0, al2 = 0.0, al3 = 0.0;
     double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;  // error bounds, units of 2^-1000: per state (VECB) or e0 = their sum
@@ -204,7 +210,7 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
             const int t = c * SPC4 + s;
             const unsigned sym = S16::pop_front(w) & SYM_MASK;
             if (t < T && !stop) {
-                const double2 b01 = sB01[sym], b23 = sB23[sym];
+                const double2 b01 = sB01[sym * REP + slot], b23 = sB23[sym * REP + slot];
                 const unsigned r = (t == 0) ? mk.pmask : lut4(mk.lutF, m);  // reachable before emission
                 m = r & (unsigned)sBmask[sym];
                 double n0, n1, n2, n3, at0, at1, at2, at3;
@@ -306,23 +312,91 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
     return ll;
 }
 
-// CTA prologue shared by the forward-type kernels: B^T of word w -> shared memory with the
-// per-codeword max_j b_j and support mask, A and pi -> registers, rmax = largest row sum of A.
-template <bool BIDIAG>
-__device__ __forceinline__ void load_model4(const double *__restrict__ pi, const double *__restrict__ A,
-                                            const double *__restrict__ Bt, int w, int M, double *sB, double *sBmax,
-                                            unsigned char *sBmask, double *a, double (&p)[4], double &rmax,
-                                            Masks4 &mk) {
-    const int tid = threadIdx.x;
-    const double2 *src = reinterpret_cast<const double2 *>(Bt + (size_t)w * M * 4);
-    double2 *dst = reinterpret_cast<double2 *>(sB);
-    for (int e = tid; e < M; e += BW_THREADS) {
-        const double2 x = __ldg(src + 2 * e), y = __ldg(src + 2 * e + 1);
-        dst[e] = x;      // sB01
-        dst[M + e] = y;  // sB23
-        sBmax[e] = fmax(fmax(x.x, x.y), fmax(y.x, y.y));
-        sBmask[e] = (unsigned char)((x.x > 0.0 ? 1 : 0) | (x.y > 0.0 ? 2 : 0) | (y.x > 0.0 ? 4 : 0) | (y.y > 0.0 ? 8 : 0));
+// ---------------------------------------------------------------- lean forward pass of the scorer
+// calculate_log_likelihood (HMM/hmm_testing.py:49-104) for models whose B has no zero and whose alive set becomes
+// all four states within the first three frames (every left-to-right model entered in state 0, and every model
+// with positive pi): from frame tstar on, "alpha_t(j) is finite" holds for every j and needs no bookkeeping.
+//
+// No error bound is carried.  Instead every step checks, on the integer pipe, that all four alpha_t(j) b_j(o_t) are
+// NORMAL doubles within 2^900 of each other.  While that holds no value was ever denormal or clamped, every
+// operation rounded a normal result (an underflowing addend inside a normal sum changes it by less than half an
+// ulp), so the values carry only the ordinary relative error ~t * 2^-52 and the log-likelihood meets the 1e-9
+// contract by eight orders.  The first step that fails the check marks the lane; marked lanes are redone by
+// fwd4_run with the full structural / precision logic.  The rescale is an exponent subtraction (exact, integer
+// pipe): al_j = at_j * 2^-e with e the exponent of the largest of the four.
+template <bool BIDIAG, int REP>
+__device__ __forceinline__ double score4_lean_run(int T, int tmax, const uint4 *__restrict__ op,
+                                                  const double2 *__restrict__ b01row, const double2 *__restrict__ b23row,
+                                                  const double *a, const double (&p)[4], const Masks4 &mk, int tstar,
+                                                  bool &bad_out) {
+    // b01row / b23row = the lane's replica column: entry of codeword sym at [sym * REP]
+    using S16 = Sym<uint16_t>;
+    double al0 = 0.0, al1 = 0.0, al2 = 0.0, al3 = 0.0;
+    int esum = 0;
+    bool bad = false;
+    unsigned m = 0u;
+    // one time step; MASKED (first chunk only): the alive set is still growing, dead states are exact zeros
+    auto step = [&](auto masked, int t, unsigned sym) {
+        constexpr bool MASKED = decltype(masked)::value;
+        const double2 b01 = b01row[sym * REP], b23 = b23row[sym * REP];
+        double n0, n1, n2, n3;
+        if (MASKED && t == 0) {
+            n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3];
+        } else {
+            matvec_fwd<BIDIAG>(a, al0, al1, al2, al3, n0, n1, n2, n3);
+        }
+        const double at0 = n0 * b01.x, at1 = n1 * b01.y, at2 = n2 * b23.x, at3 = n3 * b23.y;
+        unsigned h0 = (unsigned)__double2hiint(at0), h1 = (unsigned)__double2hiint(at1);
+        unsigned h2 = (unsigned)__double2hiint(at2), h3 = (unsigned)__double2hiint(at3);
+        const unsigned hmax = max(max(h0, h1), max(h2, h3));
+        const bool growing = MASKED && t < tstar;  // (warp-uniform)
+        if (growing) {  // leave the structurally dead states out of the minimum
+            m = (t == 0) ? mk.pmask : lut4(mk.lutF, m);
+            h0 = (m & 1u) ? h0 : hmax; h1 = (m & 2u) ? h1 : hmax;
+            h2 = (m & 4u) ? h2 : hmax; h3 = (m & 8u) ? h3 : hmax;
+        }
+        const unsigned hmin = min(min(h0, h1), min(h2, h3));
+        // all four normal, finite, and within 2^900 of the largest
+        bad = bad || (hmin < 0x00100000u) || (hmax >= 0x7fe00000u) || (hmax - hmin > (900u << 20));
+        const int eb = (int)(hmax & 0x7ff00000u) - 0x3ff00000;
+        esum += eb >> 20;
+        // exact scale by 2^-e: subtract from the exponent field
+        al0 = __hiloint2double(__double2hiint(at0) - eb, __double2loint(at0));
+        al1 = __hiloint2double(__double2hiint(at1) - eb, __double2loint(at1));
+        al2 = __hiloint2double(__double2hiint(at2) - eb, __double2loint(at2));
+        al3 = __hiloint2double(__double2hiint(at3) - eb, __double2loint(at3));
+        if (growing) {  // exact zeros of the dead states stay zeros
+            al0 = (m & 1u) ? al0 : 0.0; al1 = (m & 2u) ? al1 : 0.0;
+            al2 = (m & 4u) ? al2 : 0.0; al3 = (m & 8u) ? al3 : 0.0;
+        }
+    };
+    const int nch = (tmax + SPC4 - 1) / SPC4;
+    uint4 wnext = nch > 0 ? __ldg(op) : make_uint4(0, 0, 0, 0);
+    for (int c = 0; c < nch; ++c) {
+        uint4 w = wnext;
+        if (c + 1 < nch) wnext = __ldg(op + (size_t)(c + 1) * 32);
+        if (c == 0) {
+#pragma unroll 1
+            for (int s = 0; s < SPC4; ++s) {
+                const unsigned sym = S16::pop_front(w) & SYM_MASK;
+                if (s < T) step(std::true_type{}, s, sym);
+            }
+        } else {
+#pragma unroll 4
+            for (int s = 0; s < SPC4; ++s) {
+                const unsigned sym = S16::pop_front(w) & SYM_MASK;
+                if (c * SPC4 + s < T) step(std::false_type{}, c * SPC4 + s, sym);
+            }
+        }
     }
+    bad_out = bad;
+    return log((al0 + al1) + (al2 + al3)) + (double)esum * LN2;
+}
+
+// A and pi of word w -> registers, rmax = largest row sum of A, structural masks.
+template <bool BIDIAG>
+__device__ __forceinline__ void load_Api4(const double *__restrict__ pi, const double *__restrict__ A, int w, double *a,
+                                          double (&p)[4], double &rmax, Masks4 &mk) {
     const double *Aw = A + (size_t)w * 16;
     rmax = 0.0;
 #pragma unroll
@@ -340,6 +414,26 @@ __device__ __forceinline__ void load_model4(const double *__restrict__ pi, const
 #pragma unroll
     for (int q = 0; q < 4; ++q) p[q] = __ldg(pi + (size_t)w * 4 + q);
     mk = make_masks4(Aw, pi + (size_t)w * 4);
+}
+
+// CTA prologue shared by the forward-type kernels: B^T of word w -> shared memory with the
+// per-codeword max_j b_j and support mask, A and pi -> registers, rmax = largest row sum of A.
+template <bool BIDIAG>
+__device__ __forceinline__ void load_model4(const double *__restrict__ pi, const double *__restrict__ A,
+                                            const double *__restrict__ Bt, int w, int M, double *sB, double *sBmax,
+                                            unsigned char *sBmask, double *a, double (&p)[4], double &rmax,
+                                            Masks4 &mk) {
+    const int tid = threadIdx.x;
+    const double2 *src = reinterpret_cast<const double2 *>(Bt + (size_t)w * M * 4);
+    double2 *dst = reinterpret_cast<double2 *>(sB);
+    for (int e = tid; e < M; e += BW_THREADS) {
+        const double2 x = __ldg(src + 2 * e), y = __ldg(src + 2 * e + 1);
+        dst[e] = x;      // sB01
+        dst[M + e] = y;  // sB23
+        sBmax[e] = fmax(fmax(x.x, x.y), fmax(y.x, y.y));
+        sBmask[e] = (unsigned char)((x.x > 0.0 ? 1 : 0) | (x.y > 0.0 ? 2 : 0) | (y.x > 0.0 ? 4 : 0) | (y.y > 0.0 ? 8 : 0));
+    }
+    load_Api4<BIDIAG>(pi, A, w, a, p, rmax, mk);
 }
 
 template <bool BIDIAG>

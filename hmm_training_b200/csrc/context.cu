@@ -231,6 +231,48 @@ int phase_collect() {
 
 using namespace hmmb;
 
+// Arithmetic peak of this GPU for the roofline of the compute-bound kernels (VQ prefilter: fp32 FFMA; exact
+// distances and the scorer: fp64 DFMA): eight independent FMA chains per thread, nothing else in the loop.
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_probe(T *__restrict__ out, int iters, T seed) {
+    T a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = seed + (T)(threadIdx.x + u);
+    const T b = (T)0.999999, c = (T)1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = a[u] * b + c;  // contracted to one FMA
+    }
+    T s = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += a[u];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename T>
+static int fma_probe(double *tflops) {
+    hmmb::Ctx &c = hmmb::ctx();
+    const int grid = c.sm_count * 8, iters = sizeof(T) == 8 ? 4096 : 16384;
+    T *buf = nullptr;
+    HMMB_TRY(hmmb::dev_alloc_t(&buf, (size_t)grid * 256));
+    cudaEvent_t e0 = hmmb::event_get(), e1 = hmmb::event_get();
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 4; ++rep) {  // first launch = warm-up
+        HMMB_CUDA(cudaEventRecord(e0, c.stream));
+        HMMB_LAUNCH("peak_probe", k_fma_probe<T>, grid, 256, 0, buf, iters, (T)1);
+        HMMB_CUDA(cudaEventRecord(e1, c.stream));
+        HMMB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        HMMB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    hmmb::event_put(e0);
+    hmmb::event_put(e1);
+    hmmb::dev_free(buf);
+    *tflops = 2.0 * grid * 256.0 * 8.0 * iters / (best_ms * 1e-3) / 1e12;
+    return HMMB_OK;
+}
+
 extern "C" {
 
 int hmmb_init(int device) {
@@ -389,6 +431,12 @@ int hmmb_phase_reset(void) {
         c.phase_n[i] = 0;
     }
     return HMMB_OK;
+}
+
+int hmmb_peak_probe(int what, double *tflops) {
+    HMMB_TRY(require_init());
+    if (!tflops || (what != 0 && what != 1)) { set_error("hmmb_peak_probe: what must be 0 (fp64) or 1 (fp32)"); return HMMB_ERR_ARG; }
+    return what == 0 ? fma_probe<double>(tflops) : fma_probe<float>(tflops);
 }
 
 int hmmb_set_profiling(int enabled) {

@@ -58,6 +58,9 @@ int64_t hmmb_launch_count(void);
 double hmmb_phase_ms(const char *phase, int64_t *launches);
 int hmmb_phase_reset(void);
 int hmmb_set_profiling(int enabled);       /* event timing around every kernel (default off) */
+/* Measured FMA throughput of this GPU in TFLOP/s (what = 0: fp64 DFMA, 1: fp32 FFMA; ~1 ms of dependent-chain-free
+ * FMAs, best of three): the denominator bench.py uses for the compute-bound kernels' roofline fractions.      */
+int hmmb_peak_probe(int what, double *tflops);
 
 /* Sum-allreduce hook for the multi-GPU path: called between the E-step and the M-step
  * (and once per Lloyd pass) with a DEVICE buffer of n doubles that must be summed in place

@@ -122,6 +122,33 @@ def combine_llstats(stats: Sequence[Tuple[float, float]]) -> float:
     return float(mx + np.log(s))
 
 
+def cpu_affinity_info(device_index: int) -> dict:
+    """What bind_to_gpu_cpus sees: CPUs NVML calls local to the GPU, CPUs this process may run on, their overlap."""
+    import os
+    info = {"cpu_count": os.cpu_count()}
+    try:
+        info["allowed"] = len(os.sched_getaffinity(0))
+    except Exception as exc:
+        info["allowed_error"] = repr(exc)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        phys = device_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(os.cpu_count() or 1, 1024) + 63) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        info["nvml_local"] = len(local)
+        info["overlap"] = len(local & os.sched_getaffinity(0))
+    except Exception as exc:
+        info["nvml_error"] = repr(exc)
+    return info
+
+
 def bind_to_gpu_cpus(device_index: int) -> int:
     """Pin the calling process to the CPUs NVML reports as local to GPU `device_index` (its NUMA node), so
     that the pinned host buffers it allocates afterwards (first touch) and the library's host threads sit

@@ -364,7 +364,7 @@ def time_baum_welch(env: Env, bw, steps: int, warmup: int, sampler=None):
     CUDA events on the launching stream, profiling events OFF (this is `value`); then the same number of
     iterations once more with the library's per-launch events on, for the per-kernel times of the roofline."""
     torch, lib, _lib = env.torch, env.lib, env._lib
-    cap = 2 * (warmup + steps) + 8
+    cap = 1 << 14  # max_iterations of the calls below: never reached (a word that reaches it stops being trained)
     bw.iterate(warmup, -1.0, cap, sync_each=False)
     env.barrier()
     l0 = lib.hmmb_launch_count()

@@ -1,12 +1,12 @@
 #!/bin/bash
 # N = 2: the multi-rank tests and the full bench line
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_multi.py -q -m gpu 2>&1 | tail -5
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2f_bench2.json 2> gpurun_out/r2f_bench2.err; echo "bench rc=$?"
-grep -v "^\[W\|NCCL\|^$" gpurun_out/r2f_bench2.err | tail -15
+
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2g_bench8.json 2> gpurun_out/r2g_bench8.err; echo "bench rc=$?"
+grep -v "^\[W\|NCCL\|^$" gpurun_out/r2g_bench8.err | tail -15
 python - <<'PY'
 import json
-d=json.load(open("gpurun_out/r2f_bench2.json"))
+d=json.load(open("gpurun_out/r2g_bench8.json"))
 for k in ("value","ms_per_step","gpu_launches","clocks","e2e","allreduce"):
     print(k, d.get(k))
 print("phases", {k:round(v["ms_per_launch"],4) for k,v in d["roofline"]["phases"].items()})

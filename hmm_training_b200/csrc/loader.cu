@@ -7,6 +7,8 @@
 // (and re-runs librosa on the raw samples); this scanner walks the text once, skips everything
 // that is not a key with memchr, and parses only the arrays behind "mfcc_vector" with strtod
 // (correctly rounded, so the values are bit-identical to Python's float()).
+#include <locale.h>
+
 #include <cerrno>
 #include <cstdlib>
 #include <cstring>
@@ -26,6 +28,12 @@ const char *skip_string(const char *s, const char *end) {
         if ((bs & 1) == 0) return p + 1;
     }
     return nullptr;
+}
+
+// the "C" locale for strtod_l: a comma-decimal LC_NUMERIC of the calling process must not change the parse
+locale_t c_locale() {
+    static locale_t loc = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+    return loc;
 }
 
 inline const char *skip_ws(const char *p, const char *end) {
@@ -66,7 +74,21 @@ extern "C" int64_t hmmb_frames_json_scan(const char *text, int64_t len, double *
             if (end - q >= 3 && memcmp(q, "NaN", 3) == 0) { v = NAN; stop = const_cast<char *>(q) + 3; }            // json.dump spellings
             else if (end - q >= 8 && memcmp(q, "Infinity", 8) == 0) { v = INFINITY; stop = const_cast<char *>(q) + 8; }
             else if (end - q >= 9 && memcmp(q, "-Infinity", 9) == 0) { v = -INFINITY; stop = const_cast<char *>(q) + 9; }
-            else v = strtod(q, &stop);
+            else {
+                // the token is copied (length clamped to the buffer) and NUL-terminated, so a file that ends inside
+                // a number is never read past `end`; strtod_l with the "C" locale ignores the process's LC_NUMERIC
+                char tok[64];
+                size_t len = 0;
+                while (len < sizeof(tok) - 1 && q + len < end) {
+                    const char ch = q[len];
+                    if (!((ch >= '0' && ch <= '9') || ch == '+' || ch == '-' || ch == '.' || ch == 'e' || ch == 'E')) break;
+                    tok[len++] = ch;
+                }
+                tok[len] = 0;
+                char *tstop = nullptr;
+                v = strtod_l(tok, &tstop, c_locale());
+                stop = const_cast<char *>(q) + (tstop - tok);
+            }
             if (stop == q) { set_error("frame JSON: bad number in mfcc_vector (frame %lld)", (long long)frames); return HMMB_ERR_ARG; }
             if (n < HMMB_DIM && mfcc_out && frames < cap_frames) mfcc_out[frames * HMMB_DIM + n] = v;
             ++n;

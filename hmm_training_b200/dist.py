@@ -61,6 +61,10 @@ def make_allreduce(group=None, device: str = "cuda", overlap: bool = False):
                 torch.cuda.current_stream().wait_stream(comm_stream)
             return
         if comm_stream is not None:
+            lib_stream = _lib.load().hmmb_get_stream()
+            if lib_stream and torch.cuda.current_stream().cuda_stream != lib_stream:
+                raise RuntimeError("overlapping all-reduce: torch's current stream is not the library's (call "
+                                   "dist.bind_torch_stream() and keep that stream current)")
             comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm_stream):
                 t = torch.as_tensor(_DeviceBuffer(ptr, n), device="cuda")
@@ -69,9 +73,17 @@ def make_allreduce(group=None, device: str = "cuda", overlap: bool = False):
         if device == "cpu":
             buf = (ctypes.c_double * n).from_address(ptr)
             t = torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            return
+        # The collective must be queued on the stream the library launches on: on any other stream it would race
+        # with k_bw_reduce / k_bw_mstep.  Run it there explicitly instead of trusting torch's current stream.
+        lib_stream = _lib.load().hmmb_get_stream()
+        t = torch.as_tensor(_DeviceBuffer(ptr, n), device="cuda")
+        if lib_stream and torch.cuda.current_stream().cuda_stream != lib_stream:
+            with torch.cuda.stream(torch.cuda.ExternalStream(lib_stream)):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         else:
-            t = torch.as_tensor(_DeviceBuffer(ptr, n), device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
     return fn
 

@@ -20,9 +20,6 @@ from .hmm_training import get_observations
 
 def _stack_models(all_hmm: Sequence[HMMTrained]):
     N, M = int(all_hmm[0].states), int(all_hmm[0].symbols)
-    for h in all_hmm:
-        if int(h.states) != N or int(h.symbols) != M:
-            raise ValueError("all models must share (states, symbols) to be scored in one batch")
     pi = np.stack([np.asarray(h.Pi, float) for h in all_hmm])
     A = np.stack([np.asarray(h.A, float) for h in all_hmm])
     B = np.stack([np.asarray(h.B, float) for h in all_hmm])
@@ -31,13 +28,32 @@ def _stack_models(all_hmm: Sequence[HMMTrained]):
 
 def score_all(observations: Sequence[np.ndarray], all_hmm: Sequence[HMMTrained]):
     """[U, W] log-likelihood matrix and the index of the winning model per utterance
-    (-1 = "unknown": every score is -inf, hmm_testing.py:161)."""
-    N, M, pi, A, B = _stack_models(all_hmm)
+    (-1 = "unknown": every score is -inf, hmm_testing.py:161).  The reference scores every (recording, model)
+    pair on its own (:139-153), so models of different shapes may sit in one list: they are grouped by
+    (states, symbols), each group is one launch, and the columns go back to list order before the argmax."""
     seqs = [np.asarray(o) for o in observations]
     if any(len(o) == 0 for o in seqs):
         raise IndexError("index 0 is out of bounds for axis 0 with size 0")  # hmm_testing.py:75
-    obs, offsets = _lib.pack_sequences(seqs, M)
-    return engine.score(obs, offsets, N, M, pi, A, B)
+    groups: Dict[Tuple[int, int], List[int]] = {}
+    for w, h in enumerate(all_hmm):
+        groups.setdefault((int(h.states), int(h.symbols)), []).append(w)
+    if len(groups) == 1:
+        N, M, pi, A, B = _stack_models(all_hmm)
+        obs, offsets = _lib.pack_sequences(seqs, M)
+        return engine.score(obs, offsets, N, M, pi, A, B)
+    ll = np.empty((len(seqs), len(all_hmm)))
+    for (N, M), cols in groups.items():
+        _, _, pi, A, B = _stack_models([all_hmm[w] for w in cols])
+        obs, offsets = _lib.pack_sequences(seqs, M)  # (a codeword >= this group's M raises IndexError, as B[:, o] would)
+        ll[:, cols], _ = engine.score(obs, offsets, N, M, pi, A, B)
+    # first model with the strictly largest score, from -inf (:143-153)
+    arg = np.full(len(seqs), -1, dtype=np.int32)
+    best = np.full(len(seqs), -np.inf)
+    for w in range(len(all_hmm)):
+        better = ll[:, w] > best
+        arg[better] = w
+        best[better] = ll[better, w]
+    return ll, arg
 
 
 def calculate_log_likelihood(recording_observations: np.ndarray, hmm: HMMTrained) -> float:

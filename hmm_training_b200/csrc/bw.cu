@@ -607,7 +607,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     int64_t obs_rows = 0;
     if (s.blocked()) {
         const int SPC = SPC4;  // packed u16 entries (codeword | conflict rank) per uint4
-        const int cta_warps = s.special4 ? BW_WARPS : LTR_WARPS;
+        const int cta_warps = s.special4 ? BWD4_MAX_WARPS : LTR_WARPS;
         std::vector<int> word_blk_begin(nwords + 1, 0);
         for (int w = 0; w < nwords; ++w) {
             word_blk_begin[w] = (int)blks.size();
@@ -626,9 +626,11 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         }
         word_blk_begin[nwords] = (int)blks.size();
         s.nblk = (int)blks.size();
-        // CTA work items: ~8 CTAs per SM in total (N = 4; the left-to-right kernels run one
-        // 8-warp CTA per SM: ~4 per SM), at least one warp-round each
-        const int target = s.special4 ? c.sm_count * 8 : c.sm_count * 4;
+        // CTA work items: ~2 per SM (N = 4) / ~4 per SM (left-to-right kernels, one 8-warp CTA per SM), at least one
+        // warp-round each
+        // (N = 4: one fat backward CTA per SM, about two waves; the forward kernel splits every item over FWD4_SPLIT CTAs)
+        static const int bw4_items_per_sm = getenv("HMMB_BW4_ITEMS_PER_SM") ? std::max(1, atoi(getenv("HMMB_BW4_ITEMS_PER_SM"))) : 2;
+        const int target = s.special4 ? c.sm_count * bw4_items_per_sm : c.sm_count * 4;
         int bpc = std::max(1, (s.nblk + target - 1) / target);
         if (bpc > 1 || !s.special4) bpc = (bpc + cta_warps - 1) / cta_warps * cta_warps;
         s.cta_begin.assign(nwords + 1, 0);
@@ -1110,21 +1112,33 @@ static int launch_generic_estep(hmmb_bw *h) {
     return HMMB_OK;
 }
 
-template <bool BIDIAG, int MT>
+// warps of the fat backward CTA and its dynamic shared memory: B^T (replicated REP times), one count table per warp,
+// the gamma_0 sums; as many warps as fit beside the kernel's static arrays (sRed, the codeword slots: ~19 KB)
+static int bwd4_warps(int M, int rep, bool bidiag, size_t smem_optin, size_t *smem) {
+    int nw = bidiag ? BWD4_MAX_WARPS : 12;
+    auto bytes = [&](int w) { return (size_t)M * rep * 4 * sizeof(double) + (size_t)w * M * 4 * sizeof(double) + (size_t)w * 4 * sizeof(double); };
+    const size_t avail = smem_optin > 20 * 1024 ? smem_optin - 20 * 1024 : 0;
+    while (nw > 1 && bytes(nw) > avail) --nw;
+    *smem = bytes(nw);
+    return nw;
+}
+
+template <bool BIDIAG, int MT, int REP>
 static int launch_special_estep(hmmb_bw *h) {
     Ctx &c = ctx();
     SeqSet &s = h->s;
     if (s.ncta == 0) { s.pend.reset(); return HMMB_OK; }
     const size_t smem_f = (size_t)h->M * 5 * sizeof(double) + (size_t)((h->M + 15) & ~15);
-    const size_t smem_b = (size_t)h->M * 4 * sizeof(double) * (1 + BW_WARPS) + (size_t)BW_THREADS * 4 * sizeof(double);
-    HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwd4<BIDIAG, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    size_t smem_b = 0;
+    const int bwd_threads = 32 * bwd4_warps(h->M, REP, BIDIAG, c.smem_optin, &smem_b);
+    HMMB_CUDA(cudaFuncSetAttribute((k_bw_bwd4<BIDIAG, MT, REP>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     // forward + backward of the CTA work items [c0, c1)
     auto launch_range = [&](int c0, int c1) -> int {
         if (c1 <= c0) return HMMB_OK;
-        HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, c1 - c0, BW_THREADS, smem_f, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
+        HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, (c1 - c0) * FWD4_SPLIT, BW_THREADS, smem_f, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
                     s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_flag,
-                    h->d_allfull);
-        HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT>), c1 - c0, BW_THREADS, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
+                    h->d_allfull, FWD4_SPLIT);
+        HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT, REP>), c1 - c0, bwd_threads, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
                     s.d_len, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_bzero,
                     h->d_allfull, h->d_partials + (size_t)c0 * h->pstride, h->pstride, h->d_flag, h->d_newflags);
         return HMMB_OK;
@@ -1195,11 +1209,11 @@ static int launch_special_estep(hmmb_bw *h) {
                     h->d_flag, h->d_partials, h->pstride, h->M);
         return HMMB_OK;
     }
-    HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
+    HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta * FWD4_SPLIT, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
                 s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_flag,
-                h->d_allfull);
+                h->d_allfull, FWD4_SPLIT);
     HMMB_TRY((launch_exact<uint16_t, true>(h)));
-    HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT>), s.ncta, BW_THREADS, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
+    HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT, REP>), s.ncta, bwd_threads, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
                 s.d_len, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_bzero,
                 h->d_allfull, h->d_partials, h->pstride, h->d_flag, h->d_newflags);
     return HMMB_OK;
@@ -1254,8 +1268,9 @@ static int bw_estep(hmmb_bw *h) {
     if (h->use_ltr) return h->N == 16 ? launch_ltr_estep<16>(h) : launch_ltr_estep<8>(h);
     SeqSet &s = h->s;
     if (s.special4) {
-        if (h->M == 256) return h->bidiag ? launch_special_estep<true, 256>(h) : launch_special_estep<false, 256>(h);
-        return h->bidiag ? launch_special_estep<true, 0>(h) : launch_special_estep<false, 0>(h);
+        if (h->M == 256) return h->bidiag ? launch_special_estep<true, 256, BWD4_REP>(h) : launch_special_estep<false, 256, BWD4_REP>(h);
+        if (h->M < 256) return h->bidiag ? launch_special_estep<true, 0, BWD4_REP>(h) : launch_special_estep<false, 0, BWD4_REP>(h);
+        return h->bidiag ? launch_special_estep<true, 0, 1>(h) : launch_special_estep<false, 0, 1>(h);
     }
 #define GEN(NPV)                                                                               \
     case NPV:                                                                                  \

@@ -33,6 +33,11 @@ constexpr int SPC4 = 8;          // packed u16 entries per uint4
 constexpr unsigned SYM_MASK = 0x7ffu;
 constexpr int SYM_BITS = 11;
 constexpr int BW4_MAX_M = 512;   // warp-private count copies must fit in shared memory
+// CTA work items of the N = 4 path are sized for ONE fat backward CTA per SM (up to BWD4_MAX_WARPS warps sharing one
+// copy of the word's B^T); the forward kernel keeps its 4-warp CTAs and splits every work item over FWD4_SPLIT CTAs.
+constexpr int BWD4_MAX_WARPS = 16;
+constexpr int FWD4_SPLIT = 4;
+constexpr int BWD4_REP = 8;      // replicas of B^T in the backward kernel when they fit (M <= 256), see fwd4_run
 
 // ---------------------------------------------------------------- repack
 // One warp per (block, chunk of 8 steps), lane = sequence.  The conflict rank of a lane at a step
@@ -458,12 +463,19 @@ __global__ void __launch_bounds__(BW_THREADS, FWD4_MIN_CTAS)
 k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
           const int32_t *__restrict__ len_sorted, const double *__restrict__ pi, const double *__restrict__ A,
           const double *__restrict__ Bt, int M, double2 *__restrict__ spill, double *__restrict__ ll_seq,
-          const int32_t *__restrict__ active, uint8_t *__restrict__ flag, uint8_t *__restrict__ allfull) {
+          const int32_t *__restrict__ active, uint8_t *__restrict__ flag, uint8_t *__restrict__ allfull, int split) {
     extern __shared__ double sB[];  // [M][4] B^T, [M] per-codeword max, [M] support masks (u8)
     double *sBmax = sB + (size_t)M * 4;
     unsigned char *sBmask = reinterpret_cast<unsigned char *>(sBmax + M);
-    const CtaWork cw = work[blockIdx.x];
+    CtaWork cw = work[blockIdx.x / split];
     if (!active[cw.word]) return;
+    {   // this CTA's share of the work item's blocks (the item is sized for one fat backward CTA)
+        const int nb = cw.blk_end - cw.blk_begin, part = blockIdx.x % split;
+        const int lo = cw.blk_begin + (int)((int64_t)nb * part / split);
+        cw.blk_end = cw.blk_begin + (int)((int64_t)nb * (part + 1) / split);
+        cw.blk_begin = lo;
+        if (cw.blk_begin >= cw.blk_end) return;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double a[BIDIAG ? 7 : 16], p[4], rmax;
     Masks4 mk;
@@ -671,18 +683,22 @@ __device__ __noinline__ void bwd4_step_slow(Bwd4State<BIDIAG> &st, const double 
 // exact kernel) and -inf (impossible sequences) drop out.  Called by all BW_THREADS threads; out[0..1].
 __device__ __forceinline__ void cta_ll_stat(const Blk *__restrict__ blks, const CtaWork &cw, const double *__restrict__ ll_seq,
                                             double (*sRed)[20], double *__restrict__ out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
     const int r0 = blks[cw.blk_begin].first, r1 = blks[cw.blk_end - 1].first + blks[cw.blk_end - 1].nseq;
+    // The sums are taken by the first 128 threads whatever the CTA's size, so that the pair does not depend on the
+    // kernel that takes it (k_bw_bwd4's fat CTA or k_bw_llstat_fix's small one): same order, same bits.
+    constexpr int NT = 128;
     double m = neg_inf();
-    for (int r = r0 + tid; r < r1; r += BW_THREADS) m = fmax(m, ll_seq[r]);
+    if (tid < NT)
+        for (int r = r0 + tid; r < r1; r += NT) m = fmax(m, ll_seq[r]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) sRed[warp][0] = m;
     __syncthreads();
     m = fmax(fmax(sRed[0][0], sRed[1][0]), fmax(sRed[2][0], sRed[3][0]));
     double sum = 0.0;
-    if (m > neg_inf())
-        for (int r = r0 + tid; r < r1; r += BW_THREADS) {
+    if (tid < NT && m > neg_inf())
+        for (int r = r0 + tid; r < r1; r += NT) {
             const double l = ll_seq[r];
             if (l > neg_inf()) sum += exp(l - m);
         }
@@ -694,6 +710,7 @@ __device__ __forceinline__ void cta_ll_stat(const Blk *__restrict__ blks, const 
         out[0] = m;
         out[1] = ((sRed[0][1] + sRed[1][1]) + sRed[2][1]) + sRed[3][1];
     }
+    (void)nwarps;
 }
 
 // Pipelined first E-step only: there the exact kernel runs AFTER the staged backward passes, so a sequence the
@@ -717,8 +734,16 @@ k_bw_llstat_fix(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, 
 // alpha-hat prefetch (P0 / P1) needs no register-to-register copies.
 // MT = 256 (the reference's codebook size, CodeVector/main.py) makes every shared-memory offset a literal;
 // MT = 0 takes M at run time.
-template <bool BIDIAG, int MT>
-__global__ void __launch_bounds__(BW_THREADS, BIDIAG ? 4 : 3)
+//
+// One fat CTA per SM: blockDim.x / 32 warps (16 for the left-to-right kernel, 12 for the dense one, fewer when the
+// count tables of a large alphabet need the room) share ONE copy of the word's B^T, which leaves room to store it
+// REP = 8 times: lane l gathers from replica l & 7, so the eight lanes of a quarter-warp always hit eight different
+// 16-byte bank slots.  ncu on the 4-warp version: 19.5 of the 69.5 shared-memory wavefronts per warp-step were this
+// gather (ideal 8), and that pipe — 72 % busy — is what the kernel waits for.  The count tables stay warp-private.
+// Shared memory: [M * REP] double2 (b0, b1), [M * REP] double2 (b2, b3), nwarps x [M] x 2 double2 counts,
+// [nwarps][4] gamma_0 sums.
+template <bool BIDIAG, int MT, int REP>
+__global__ void __launch_bounds__(BIDIAG ? BWD4_MAX_WARPS * 32 : 384, 1)
 k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
           const int32_t *__restrict__ len_sorted, const double *__restrict__ A, const double *__restrict__ Bt, int M_rt,
           const double2 *__restrict__ spill, const double *__restrict__ ll_seq, const int32_t *__restrict__ active,
@@ -726,13 +751,14 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
           int64_t pstride, uint8_t *__restrict__ flag, int32_t *__restrict__ new_flags) {
     using S16 = Sym<uint16_t>;
     const int M = MT ? MT : M_rt;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     extern __shared__ double smem[];
-    double *sB = smem;                              // B^T: [M] double2 (b0,b1) then [M] double2 (b2,b3)
-    double *sCnt = smem + (size_t)M * 4;            // [4 warps] x { [M] double2 (j=0,1), [M] double2 (j=2,3) }
-    double *sPi = sCnt + (size_t)M * 4 * BW_WARPS;  // [128 threads][4] gamma_0 sums
-    __shared__ double sRed[BW_WARPS][20];
+    double *sB = smem;                                    // B^T replicated: [M * REP] (b0,b1) then [M * REP] (b2,b3)
+    double *sCnt = smem + (size_t)M * REP * 4;            // [nwarps] x { [M] double2 (j=0,1), [M] double2 (j=2,3) }
+    double *sPi = sCnt + (size_t)M * 4 * nwarps;          // [nwarps][4] gamma_0 sums
+    __shared__ double sRed[BWD4_MAX_WARPS][20];
     __shared__ unsigned sSeen;
-    __shared__ uint4 sW[2][BW_THREADS];  // codeword chunks in flight (cp.async), double-buffered per thread
+    __shared__ uint4 sW[2][BWD4_MAX_WARPS * 32];  // codeword chunks in flight (cp.async), double-buffered per thread
 
     const CtaWork cw = work[blockIdx.x];
     double *part = partials + (size_t)blockIdx.x * pstride;
@@ -740,9 +766,13 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     if (!active[cw.word]) return;
     {
         const double2 *src = reinterpret_cast<const double2 *>(Bt + (size_t)cw.word * M * 4);
-        double2 *dst = reinterpret_cast<double2 *>(sB);
-        for (int e = tid; e < M * 2; e += BW_THREADS) dst[(e & 1) * M + (e >> 1)] = __ldg(src + e);
-        for (int e = tid; e < M * 4 * BW_WARPS + BW_THREADS * 4; e += BW_THREADS) sCnt[e] = 0.0;  // counts + sPi
+        double2 *dst01 = reinterpret_cast<double2 *>(sB), *dst23 = dst01 + (size_t)M * REP;
+        for (int e = tid; e < M * REP; e += nthreads) {
+            const int sym = e / REP;
+            dst01[e] = __ldg(src + 2 * sym);
+            dst23[e] = __ldg(src + 2 * sym + 1);
+        }
+        for (int e = tid; e < M * 4 * nwarps + nwarps * 4; e += nthreads) sCnt[e] = 0.0;  // counts + sPi
         if (tid == 0) sSeen = 0u;
     }
     double a[BIDIAG ? 7 : 16];
@@ -756,14 +786,15 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     __syncthreads();
 
     double2 *cntw01 = reinterpret_cast<double2 *>(sCnt + (size_t)warp * M * 4);  // (j = 2, 3) rows M entries further
-    const double2 *sB01 = reinterpret_cast<const double2 *>(sB), *sB23 = sB01 + M;
-    double *mypi = sPi + (size_t)tid * 4;
+    // this lane's replica column of B^T: the row of codeword sym is at [sym * REP]
+    const double2 *sB01 = reinterpret_cast<const double2 *>(sB) + (lane & (REP - 1)), *sB23 = sB01 + (size_t)M * REP;
+    double *mypi = sPi + (size_t)warp * 4;
     Bwd4State<BIDIAG> st;
 #pragma unroll
     for (int q = 0; q < (BIDIAG ? 7 : 16); ++q) st.X[q] = 0.0;
     st.seenX = 0u;
 
-    for (int b = cw.blk_begin + warp; b < cw.blk_end; b += BW_WARPS) {
+    for (int b = cw.blk_begin + warp; b < cw.blk_end; b += nwarps) {
         const Blk bk = blks[b];
         int T = 0;
         bool apos = false;
@@ -824,7 +855,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                     st.rref = r0;                                                                                   \
                     g0 = fma(al0, r0, pos_to_tiny(al0)); g1 = fma(al1, r0, pos_to_tiny(al1));                       \
                     g2 = fma(al2, r0, pos_to_tiny(al2)); g3 = fma(al3, r0, pos_to_tiny(al3));                       \
-                    const double2 b01 = sB01[sym], b23 = sB23[sym];                                                 \
+                    const double2 b01 = sB01[sym * REP], b23 = sB23[sym * REP];                                     \
                     st.v0 = b01.x; st.v1 = b01.y; st.v2 = b23.x; st.v3 = b23.y;                                     \
                     st.vpos = all_pos4(b01.x, b01.y, b23.x, b23.y);                                                 \
                     done = true;                                                                                    \
@@ -851,7 +882,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                     const double r = recip_from_ref(norm, st.rref); /* 1 / norm without a division */              \
                     const double sc = pow2_rescale_noacc(qs);                                                       \
                     const double h0 = q0 * sc, h1 = q1 * sc, h2 = q2 * sc, h3 = q3 * sc; /* beta-hat_t */          \
-                    const double2 b01 = sB01[sym], b23 = sB23[sym];                                                 \
+                    const double2 b01 = sB01[sym * REP], b23 = sB23[sym * REP];                                     \
                     const double nv0 = fma(b01.x, h0, tiny), nv1 = fma(b01.y, h1, tiny);                            \
                     const double nv2 = fma(b23.x, h2, tiny), nv3 = fma(b23.y, h3, tiny);                            \
                     const double vs = (nv0 + nv1) + (nv2 + nv3);                                                    \
@@ -886,13 +917,18 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                     /* taken and stays in registers on the lean path                                     */         \
                     Bwd4State<BIDIAG> tmp = st;                                                                     \
                     double g[4];                                                                                    \
-                    bwd4_step_slow<BIDIAG>(tmp, a, sB01, sB23, sym, false, al0, al1, al2, al3, g);                  \
+                    bwd4_step_slow<BIDIAG>(tmp, a, sB01, sB23, sym * REP, false, al0, al1, al2, al3, g);            \
                     st = tmp;                                                                                       \
                     g0 = g[0]; g1 = g[1]; g2 = g[2]; g3 = g[3];                                                     \
                 }                                                                                                   \
-                if (t == 0) { /* (:415-426) */                                                                      \
-                    mypi[0] += g0; mypi[1] += g1; mypi[2] += g2; mypi[3] += g3;                                     \
+            }                                                                                                       \
+            if (t == 0) { /* gamma_0 sums (:415-426): once per block, fixed-order warp tree (inactive lanes add 0) */ \
+                double p0 = g0, p1 = g1, p2 = g2, p3 = g3;                                                          \
+                _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) {                                                \
+                    p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o);           \
+                    p2 += __shfl_xor_sync(0xffffffffu, p2, o); p3 += __shfl_xor_sync(0xffffffffu, p3, o);           \
                 }                                                                                                   \
+                if (lane == 0) { mypi[0] += p0; mypi[1] += p1; mypi[2] += p2; mypi[3] += p3; }                      \
             }                                                                                                       \
             /* emission-count numerators (:460-500): warp-private rows, conflict-free rank order */                \
             cnt_update4(cntw01, M, act, sym, (int)(packed >> SYM_BITS), g0, g1, g2, g3);                            \
@@ -940,18 +976,16 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) sRed[warp][4 + q] = v;
     }
+    if (lane == 0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        double v = mypi[q];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) sRed[warp][q] = v;
+        for (int q = 0; q < 4; ++q) sRed[warp][q] = mypi[q];  // (already summed over the warp's lanes)
     }
     const unsigned seenW = __reduce_or_sync(0xffffffffu, st.seenX);
     if (lane == 0) atomicOr(&sSeen, seenW);
     __syncthreads();
     if (tid < 20) {
-        double v = ((sRed[0][tid] + sRed[1][tid]) + sRed[2][tid]) + sRed[3][tid];
+        double v = 0.0;
+        for (int w = 0; w < nwarps; ++w) v += sRed[w][tid];  // fixed order
         if (tid >= 4) {
             const int q = tid - 4;
             const double aij = __ldg(A + (size_t)cw.word * 16 + q);
@@ -961,11 +995,12 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         }
         part[tid] = v;
     }
-    for (int e = tid; e < M * 4; e += BW_THREADS)
-    {
+    for (int e = tid; e < M * 4; e += nthreads) {
         const int sym = e >> 2, j = e & 3;
         const size_t o = (size_t)(j >> 1) * 2 * M + (size_t)sym * 2 + (j & 1);  // split (j=0,1) / (j=2,3) arrays
-        part[20 + e] = ((sCnt[o] + sCnt[(size_t)M * 4 + o]) + sCnt[(size_t)M * 8 + o]) + sCnt[(size_t)M * 12 + o];
+        double v = 0.0;
+        for (int w = 0; w < nwarps; ++w) v += sCnt[(size_t)w * M * 4 + o];  // the warps' tables, in fixed order
+        part[20 + e] = v;
     }
     // ---- this CTA's share of the convergence statistic log_sum_exp_r log P_r (:503)
     __syncthreads();  // sRed is free again

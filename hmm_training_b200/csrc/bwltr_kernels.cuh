@@ -134,7 +134,13 @@ __device__ __noinline__ int exact_productsN(const double *nn, const double *bb, 
 // returns log P(O|lambda) (:376-377), -inf if structurally impossible, NaN = hand over to the
 // exact log-space kernel.  allfull = every step had all NS states alive and a scale >= 1, i.e.
 // every spilled alpha-hat is strictly positive (the backward pass then skips that test).
-template <int NS, bool SPILL>
+// PERSTATE = false (first pass): the scalar error bound of fwd4_run, ~5 instructions per step; rigorous but loose — it
+// assumes the error sits in the most probable state, so over a few thousand frames of peaked emissions it drifts
+// up to the limit although nothing is wrong.  A lane that trips it is simply run again with PERSTATE = true: per-state
+// bounds e_j following the exact linear recursion of the values, kept in local memory (volatile: no registers in the
+// common path), born only where a zero / denormal value is actually produced.  Only what that pass marks goes to the
+// exact log-space kernel.
+template <int NS, bool SPILL, bool PERSTATE = false>
 __device__ __forceinline__ double fwdL_run(int T, int tmax, const uint4 *__restrict__ op,
                                            const double2 *__restrict__ sB, const double *__restrict__ sBmax,
                                            const unsigned short *__restrict__ sBmask, const double (&as)[NS],
@@ -146,7 +152,9 @@ __device__ __forceinline__ double fwdL_run(int T, int tmax, const uint4 *__restr
     double al[NS];
 #pragma unroll
     for (int j = 0; j < NS; ++j) al[j] = 0.0;
-    double E = 0.0;  // error bound, units of 2^-1000
+    double E = 0.0;          // !PERSTATE: scalar error bound, units of 2^-1000
+    volatile double ev[NS];  // PERSTATE: per-state bounds, only touched once a denormal was born (`tainted`)
+    bool tainted = false;
     long long esum = 0;
     unsigned m = 0u;
     bool stop = false, allf = true;
@@ -172,11 +180,16 @@ __device__ __forceinline__ double fwdL_run(int T, int tmax, const uint4 *__restr
                 const unsigned r = (t == 0) ? pmask : (((m & selfm) | ((m & nextm) << 1)) & L::FULL);
                 m = r & (unsigned)sBmask[sym];
                 double at[NS];
+                unsigned subm = 0u;  // alive states whose value came out zero / denormal: an absolute error is born here
                 if (m == L::FULL && t > 0) {
                     // ---- every state alive (the usual case)
                     at[0] = fma(fma(al[0], as[0], tiny), b[0], tiny);
 #pragma unroll
                     for (int j = 1; j < NS; ++j) at[j] = fma(fma(al[j], as[j], fma(al[j - 1], an[j - 1], tiny)), b[j], tiny);
+                    if (PERSTATE) {
+#pragma unroll
+                        for (int j = 0; j < NS; ++j) subm |= is_sub(at[j]) ? (1u << j) : 0u;
+                    }
                 } else if (m == 0u) {
                     stop = true;  // no state can emit o_t: log P = -inf (:155-160)
                     allf = false;
@@ -192,6 +205,7 @@ __device__ __forceinline__ double fwdL_run(int T, int tmax, const uint4 *__restr
                         else if (j == 0) n = fma(al[0], as[0], tiny_if(r, 0));
                         else n = fma(al[j], as[j], fma(al[j - 1], an[j - 1], tiny_if(r, j)));
                         at[j] = fma(n, b[j], tiny_if(m, j));
+                        if (PERSTATE && t > 0 && ((m >> j) & 1u) && is_sub(at[j])) subm |= 1u << j;  // (pi * b at t = 0 is one exact product)
                     }
                 }
                 double ssum = tree_sum<NS>(at);
@@ -210,7 +224,7 @@ __device__ __forceinline__ double fwdL_run(int T, int tmax, const uint4 *__restr
                     const int code = exact_productsN<NS>(tn, tb, to, &Ex);
                     if (code == 0) {
                         stop = true;
-                    } else if ((code == 2 && t > 0) || E > 0.0) {
+                    } else if ((code == 2 && t > 0) || tainted || E > 0.0) {
                         stop = true;  // the surviving states had lost their bits: exact path
                         ll = nan_mark();
                     } else {
@@ -226,10 +240,38 @@ __device__ __forceinline__ double fwdL_run(int T, int tmax, const uint4 *__restr
                     allf = allf && (__double2hiint(sc) >= 0x3ff00000);  // scale >= 1: a denormal alpha cannot be flushed
 #pragma unroll
                     for (int j = 0; j < NS; ++j) al[j] = at[j] * sc;
-                    E = fma(E, rmax * sBmax[sym], (double)NS * ERR_UNIT) * sc;
-                    if (!(E <= ERR_LIMIT)) {
-                        stop = true;
-                        ll = nan_mark();
+                    if (!PERSTATE) {
+                        E = fma(E, rmax * sBmax[sym], (double)NS * ERR_UNIT) * sc;
+                        if (!(E <= ERR_LIMIT)) {
+                            stop = true;
+                            ll = nan_mark();
+                        }
+                    } else if (subm != 0u || tainted) {
+                        // e'_j = (b_j(o_t) * (e_j a_jj + e_j-1 a_j-1,j) + seed_j) * scale, seed_j = 2^-1074 where a denormal was born
+                        if (!tainted) {
+#pragma unroll
+                            for (int j = 0; j < NS; ++j) ev[j] = 0.0;
+                            tainted = true;
+                        }
+                        double etot = 0.0, eprev = 0.0;
+#pragma unroll
+                        for (int q = 0; q < L::CPR; ++q) {
+                            const double2 x = sB[L::swz(sym, q)];  // (re-read: b[] is not kept alive for this rare path)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int j = 2 * q + h;
+                                const double ej = ev[j];
+                                const double f = fma(ej, as[j], j > 0 ? eprev * an[j > 0 ? j - 1 : 0] : 0.0);
+                                eprev = ej;
+                                const double en = fma(f, h ? x.y : x.x, ((subm >> j) & 1u) ? ERR_UNIT : 0.0) * sc;
+                                ev[j] = en;
+                                etot += en;
+                            }
+                        }
+                        if (!(etot <= ERR_LIMIT)) {
+                            stop = true;
+                            ll = nan_mark();
+                        }
                     }
                     if (t == T - 1 && !stop) ll = log(tree_sum<NS>(al)) + (double)esum * LN2;
                 }
@@ -322,8 +364,15 @@ k_bw_fwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
         if (T > 0 && flag[bk.first + lane]) T = 0;  // handled by the exact log-space kernel
         bool af = false;
-        const double ll = fwdL_run<NS, true>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, sBmask, as, an, piw, rmax,
-                                             selfm, nextm, pmask, spill + (size_t)bk.spill_base * L::CPR * 32 + lane, af);
+        double ll = fwdL_run<NS, true>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, sBmask, as, an, piw, rmax,
+                                       selfm, nextm, pmask, spill + (size_t)bk.spill_base * L::CPR * 32 + lane, af);
+        if (__any_sync(0xffffffffu, T > 0 && ll != ll)) {  // (rare) the marked lanes again, with per-state bounds
+            bool af2 = false;
+            const double ll2 = fwdL_run<NS, true, true>((T > 0 && ll != ll) ? T : 0, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax,
+                                                        sBmask, as, an, piw, rmax, selfm, nextm, pmask,
+                                                        spill + (size_t)bk.spill_base * L::CPR * 32 + lane, af2);
+            if (T > 0 && ll != ll) { ll = ll2; af = af2; }
+        }
         if (T > 0) {
             ll_seq[bk.first + lane] = ll;
             allfull[bk.first + lane] = af ? 1 : 0;
@@ -360,8 +409,13 @@ k_scoreL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const u
         const Blk bk = blks[b];
         const int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
         bool af;
-        const double ll = fwdL_run<NS, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, sBmask, as, an, piw, rmax,
-                                              selfm, nextm, pmask, nullptr, af);
+        double ll = fwdL_run<NS, false>(T, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax, sBmask, as, an, piw, rmax,
+                                        selfm, nextm, pmask, nullptr, af);
+        if (__any_sync(0xffffffffu, T > 0 && ll != ll)) {  // (rare) the marked lanes again, with per-state bounds
+            const double ll2 = fwdL_run<NS, false, true>((T > 0 && ll != ll) ? T : 0, bk.tmax, obs_blk + bk.obs_base + lane, sB, sBmax,
+                                                         sBmask, as, an, piw, rmax, selfm, nextm, pmask, nullptr, af);
+            if (T > 0 && ll != ll) ll = ll2;
+        }
         if (lane < bk.nseq) {
             ll_out[(size_t)order[bk.first + lane] * W + w] = ll;
             if (ll != ll) *any_nan = 1;  // precision guard marked this pair: k_score_exact has work to do

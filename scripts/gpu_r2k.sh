@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/pytest_gpu.log | tail -30
+timeout 300 python bench.py --steps 6 --warmup 3 --no-extras --workload bw_c4 > gpurun_out/r2k_c4.json 2> gpurun_out/r2k_c4.err
+python - <<'PY'
+import json
+for n in ("c4",):
+    try:
+        d=json.load(open(f"gpurun_out/r2k_{n}.json"))
+        ph=d["roofline"]["phases"]
+        print(n, "ms/iter %.4f"%d["ms_per_step"], {k:round(v["ms_per_launch"],4) for k,v in ph.items()}, "frac %.3f"%d["roofline"]["frac"], "e2e ms", round(d["e2e"].get("ms_per_step",0),3))
+    except Exception as e: print(n, "ERR", e)
+PY

@@ -112,6 +112,8 @@ def test_baum_welch_matches_oracle_seeded(N, M, T):
 
 @pytest.mark.parametrize("N,M,T,S,family", [
     (4, 256, 6000, 3, "n4_left_to_right"),   # long horizons: thousands of rescales, per-state error bound
+    (16, 1024, 6000, 3, "left_to_right"),    # the same horizon on the N = 16 kernels (config 4's shape): the scalar error
+    (8, 512, 6000, 3, "left_to_right"),      # bound is seeded only where a denormal is born, so nothing is handed over
     (4, 512, 40, 40, "n4_left_to_right"),    # the largest alphabet the warp-private count tables hold
     (4, 513, 40, 40, "generic"),             # one more codeword: lanes-per-state kernels, u16 symbols
     (5, 4096, 60, 20, "generic"),            # wide alphabet, odd state count

@@ -431,7 +431,7 @@ def block_config4(env: Env, args, hbm_peak, peak_src):
     500 sequences per word PER GPU (weak scaling), one 133 MB fp64 all-reduce per iteration."""
     cfg = dict(WORKLOADS["bw_c4"])
     cfg["S"] = max(1, int(round(cfg["S"] * args.scale)))
-    bw, (obs, offsets, wos), _ = make_bw(env, cfg, 3000 + env.rank)
+    bw, (obs, offsets, wos), init = make_bw(env, cfg, 3000 + env.rank)
     frames_rank = int(offsets[-1])
     steps = max(3, min(args.steps, 6))
     ms, launches, phases = time_baum_welch(env, bw, steps, 3)
@@ -440,13 +440,42 @@ def block_config4(env: Env, args, hbm_peak, peak_src):
     bw.close()
     W, N, M = cfg["W"], cfg["N"], cfg["M"]
     accum_doubles = W * (((N + N * N + M * N) + 1 + 15) // 16 * 16) + env.world * W * 2
+    # end to end through engine.bw_fit, one EM iteration per call; codewords, the 131 MB of initial parameters and the
+    # 133 MB of results all in pinned host memory, so that every copy is one direct DMA
+    e2e = None
+    try:
+        torch = env.torch
+
+        def pin(a):  # copy into pinned host memory (torch has no uint16 tensors on every version: go through int16)
+            a = np.ascontiguousarray(a)
+            src = a.view(np.int16) if a.dtype == np.uint16 else a
+            return torch.from_numpy(src).pin_memory().numpy().view(a.dtype)
+
+        obs_h, off_h, wos_h = pin(obs), pin(offsets), pin(wos)
+        init_h = tuple(pin(x) for x in init)
+        out_h = tuple(pin(np.zeros_like(x)) for x in init)
+        ar = env.allreduce_hook("native")
+        call = lambda: env.engine.bw_fit(obs_h, off_h, wos_h, W, N, M, *init_h, -1.0, 1, allreduce=ar, rank=env.rank,
+                                         world=env.world, out=out_h)
+        call()
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            res = call()
+        env.barrier()
+        dt = env.max_over_ranks((time.perf_counter() - t0) / 2)
+        e2e = {"value": frames_rank * env.world / dt, "unit": "frames/s/iter", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(obs_h.nbytes + off_h.nbytes + wos_h.nbytes + sum(x.nbytes for x in init_h)),
+               "d2h_bytes_per_step": int(sum(x.nbytes for x in res)), "buffers": "pinned (inputs and outputs)"}
+    except Exception as exc:  # pragma: no cover
+        e2e = {"error": repr(exc)}
     out = {"workload": cfg["desc"], "scaling": "weak", "frames_per_gpu_per_iter": frames_rank, "ms_per_step": ms,
            "value": frames_rank * env.world / (ms * 1e-3), "unit": "frames/s/iter", "steps": steps,
            "kernel_family": family, "gpu_launches": launches,
            "allreduce_bytes": accum_doubles * 8,
            "allreduce_ms": phases.get("bw_allreduce", {}).get("ms_per_launch"),
            "roofline": bw_roofline("bw_c4", family, phases, frames_rank, N, M, hbm_peak, peak_src),
-           "precision_guard": {"exact_sequence_passes": exact, "backward_handovers": handover}}
+           "e2e": e2e, "precision_guard": {"exact_sequence_passes": exact, "backward_handovers": handover}}
     return out
 
 

@@ -198,9 +198,17 @@ class BaumWelch:
     def iterate(self, n_iter: int, epsilon: float = 1e-6, max_iterations: int = 100, sync_each: bool = True) -> None:
         check(self._lib.hmmb_bw_iterate(self._h, int(n_iter), float(epsilon), int(max_iterations), int(sync_each)))
 
-    def params(self, finalize: bool = True):
+    def params(self, finalize: bool = True, out=None):
+        """(pi, A, B).  out = (pi, A, B) caller-provided C-contiguous float64 arrays of the right shapes (e.g. in
+        pinned host memory: the device-to-host copy is then one direct DMA instead of going through bounce buffers)."""
         W, N, M = self.W, self.N, self.M
-        pi, A, B = np.empty((W, N)), np.empty((W, N, N)), np.empty((W, N, M))
+        if out is None:
+            pi, A, B = np.empty((W, N)), np.empty((W, N, N)), np.empty((W, N, M))
+        else:
+            pi, A, B = out
+            for x, shp in ((pi, (W, N)), (A, (W, N, N)), (B, (W, N, M))):
+                if x.shape != shp or x.dtype != np.float64 or not x.flags.c_contiguous:
+                    raise ValueError(f"out arrays must be C-contiguous float64 of shapes ({W},{N}), ({W},{N},{N}), ({W},{N},{M})")
         check(self._lib.hmmb_bw_get_params(self._h, int(finalize), ptr(pi), ptr(A), ptr(B)))
         return pi, A, B
 
@@ -244,14 +252,14 @@ class BaumWelch:
 
 
 def bw_fit(obs, offsets, word_of_seq, W: int, N: int, M: int, pi0, A0, B0, epsilon: float = 1e-6,
-           max_iterations: int = 100, allreduce=None, rank: int = 0, world: int = 1):
+           max_iterations: int = 100, allreduce=None, rank: int = 0, world: int = 1, out=None):
     """Batched hmm_training (HMM/hmm_training.py:265-541) for W words at once.
-    Returns (pi [W,N], A [W,N,N], B [W,N,M], ll_hist [W,max_iterations], iters [W])."""
+    Returns (pi [W,N], A [W,N,N], B [W,N,M], ll_hist [W,max_iterations], iters [W]).  out: see BaumWelch.params."""
     with BaumWelch(obs, offsets, word_of_seq, W, N, M, pipeline_upload=True, init=(pi0, A0, B0)) as bw:
         if world > 1:
             bw.set_dist(rank, world, allreduce)
         bw.iterate(max_iterations, epsilon, max_iterations, sync_each=True)
-        pi, A, B = bw.params(finalize=True)
+        pi, A, B = bw.params(finalize=True, out=out)
         hist, iters = bw.history(max_iterations)
     return pi, A, B, hist, iters
 

@@ -702,7 +702,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     HMMB_TRY(dev_alloc_t(&s.d_bad, 1));
     int *d_bad = s.d_bad;
     HMMB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), c.stream));
-    if (defer && s.special4 && up.active() && !unsorted && s.nblk > 0) {
+    if (defer && s.blocked() && up.active() && !unsorted && s.nblk > 0) {
         // leave the repack to the first E-step (bw_estep): record which blocks / CTA work items each stage completes
         std::unique_ptr<PendingPrepare> p(new PendingPrepare());
         p->idx_bytes = idx_bytes;
@@ -764,6 +764,13 @@ struct hmmb_bw {
     bool check_bad = false;       // pipelined prepare: the codeword-range flag has not been read back yet
     std::unique_ptr<PendingPrepare> pend_release;  // consumed by the E-step; freed after the next stream sync
     void *d_raw = nullptr;        // raw codewords uploaded once when both layouts are built
+    // Pipelined create with left-to-right initial parameters: only `sl` is built (its repack is left to the first
+    // E-step, stage by stage behind the upload); `s` carries the sizes alone.  The raw codewords and the sequence
+    // table are kept so that the generic layout can still be built should dense parameters arrive later.
+    bool ltr_only = false;
+    int raw_idx_bytes = 0;
+    std::vector<int64_t> keep_offsets;
+    std::vector<int32_t> keep_words;
     SeqSet &cur() { return use_ltr ? sl : s; }
     int W = 0, N = 0, M = 0;
     double *d_pi = nullptr, *d_A = nullptr, *d_Bt = nullptr;
@@ -815,6 +822,7 @@ static int bw_alloc_accum(hmmb_bw *h) {
 }
 
 static int bw_set_params_impl(hmmb_bw *h, const double *pi0, const double *A0, const double *B0, bool sync);
+static int bw_after_sync(hmmb_bw *h);
 
 // Buffers sized by the sequence set, accumulator layout, the small per-word uploads (second half of hmmb_bw_create).
 static int bw_finish_create(hmmb_bw *h, int64_t R) {
@@ -900,44 +908,79 @@ int hmmb_bw_create_ex(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_o
     auto fail = [&](int code) { bw_release(h); delete h; return code; };
     int rc;
     h->has_ltr = ltr_shape_ok(N, M);
-    if (h->has_ltr && !obs_on_device && R > 0 && offsets && obs && offsets[R] > offsets[0]) {
+    const bool have_params = pi0 && A0 && B0;
+    // Pipelined create for the left-to-right kernels (N = 8 / 16): pinned host codewords, initial parameters given
+    // and every A upper-bidiagonal.  Only the blocked layout is built, and its repack is left to the first E-step.
+    bool ltr_pipe = false;
+    if (h->has_ltr && (flags & HMMB_BW_PIPELINE_UPLOAD) && have_params && !obs_on_device && R > 0 && offsets && obs &&
+        offsets[R] > offsets[0] && !getenv("HMMB_FORCE_DENSE_A") && !getenv("HMMB_NO_LTR_PIPELINE") &&
+        host_is_pinned((const char *)obs + (size_t)offsets[0] * idx_bytes)) {
+        ltr_pipe = true;
+        const size_t nA = (size_t)W * N * N;
+        for (size_t e = 0; e < nA && ltr_pipe; ++e) {
+            const int ij = (int)(e % (size_t)(N * N)), i = ij / N, j = ij % N;
+            if (j != i && j != i + 1 && A0[e] > 0.0) ltr_pipe = false;
+        }
+    }
+    if (h->has_ltr && !ltr_pipe && !obs_on_device && R > 0 && offsets && obs && offsets[R] > offsets[0]) {
         // both layouts are built from the codewords: upload them once
         const size_t in_bytes = (size_t)(offsets[R] - offsets[0]) * idx_bytes;
         rc = dev_alloc(&h->d_raw, in_bytes);
         if (rc != HMMB_OK) return fail(rc);
-        cudaError_t e = cudaMemcpyAsync(h->d_raw, (const char *)obs + (size_t)offsets[0] * idx_bytes, in_bytes,
-                                        cudaMemcpyHostToDevice, c.stream);
-        if (e != cudaSuccess) return fail(cuda_fail(e, "codeword upload", __FILE__, __LINE__));
+        rc = h2d_big(h->d_raw, (const char *)obs + (size_t)offsets[0] * idx_bytes, in_bytes, c.stream);
+        if (rc != HMMB_OK) return fail(rc);
         // seqset_build indexes a device stream from offsets[0]
         obs = (const char *)h->d_raw - (size_t)offsets[0] * idx_bytes;
         obs_on_device = 1;
     }
-    const bool have_params = pi0 && A0 && B0;
     // everything that follows the sequence set (buffers sized by it, the small uploads, optionally the
     // initial parameters).  In a pipelined create it runs INSIDE seqset_build, between the metadata and the
     // rest of the codeword upload, so that none of it waits behind that upload.
     bool finished = false;
     std::function<int()> finish = [&]() -> int {
         finished = true;
+        if (ltr_pipe) {  // the generic set only carries the sizes (see hmmb_bw.ltr_only)
+            h->s.R = h->sl.R; h->s.frames = h->sl.frames; h->s.N = N; h->s.M = M; h->s.NP = pick_np(N);
+            h->s.sym_bytes = M <= 256 ? 1 : 2;
+            h->s.seq_begin = h->sl.seq_begin;
+            h->s.tmax_all = h->sl.tmax_all;
+        }
         HMMB_TRY(bw_finish_create(h, R));
         if (have_params) HMMB_TRY(bw_set_params_impl(h, pi0, A0, B0, false));
         return HMMB_OK;
     };
-    const bool pipeline = (flags & HMMB_BW_PIPELINE_UPLOAD) != 0 && !h->has_ltr;
-    rc = seqset_build(h->s, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_AUTO, pipeline,
-                      pipeline ? &finish : nullptr, pipeline_stages());
-    if (rc != HMMB_OK) return fail(rc);
-    if (h->has_ltr) {
-        rc = seqset_build(h->sl, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_LTR);
+    if (ltr_pipe) {
+        h->ltr_only = true;
+        h->raw_idx_bytes = idx_bytes;
+        rc = seqset_build(h->sl, obs, idx_bytes, 0, offsets, word_of_seq, R, W, N, M, LAYOUT_LTR, true, &finish, pipeline_stages());
         if (rc != HMMB_OK) return fail(rc);
-        dev_free(h->d_raw);
-        h->d_raw = nullptr;
+        if (!h->sl.pend) {
+            // input not in (word, length descending) order: the build did the repack itself and its raw buffer is
+            // gone, so the generic layout is built now, from the host codewords, as in a plain create
+            h->ltr_only = false;
+            rc = seqset_build(h->s, obs, idx_bytes, 0, offsets, word_of_seq, R, W, N, M, LAYOUT_AUTO);
+            if (rc != HMMB_OK) return fail(rc);
+        } else {
+            h->keep_offsets.assign(offsets, offsets + R + 1);
+            h->keep_words.assign(word_of_seq, word_of_seq + R);
+        }
+    } else {
+        const bool pipeline = (flags & HMMB_BW_PIPELINE_UPLOAD) != 0 && !h->has_ltr;
+        rc = seqset_build(h->s, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_AUTO, pipeline,
+                          pipeline ? &finish : nullptr, pipeline_stages());
+        if (rc != HMMB_OK) return fail(rc);
+        if (h->has_ltr) {
+            rc = seqset_build(h->sl, obs, idx_bytes, obs_on_device, offsets, word_of_seq, R, W, N, M, LAYOUT_LTR);
+            if (rc != HMMB_OK) return fail(rc);
+            dev_free(h->d_raw);
+            h->d_raw = nullptr;
+        }
     }
     if (!finished) {
         rc = finish();
         if (rc != HMMB_OK) return fail(rc);
     }
-    if (!h->s.pend) {
+    if (!h->s.pend && !h->sl.pend) {
         // (a pipelined create returns with its uploads in flight; otherwise everything is on the device now)
         cudaError_t e = cudaStreamSynchronize(c.stream);
         if (e != cudaSuccess) return fail(cuda_fail(e, "create sync", __FILE__, __LINE__));
@@ -963,6 +1006,36 @@ const char *hmmb_bw_kernel_family(hmmb_bw_t *h) {
     return "generic";
 }
 
+// hmmb_bw.ltr_only and parameters with a dense A: build the generic layout now, from the raw codewords the handle kept.
+static int bw_build_generic_lazily(hmmb_bw *h) {
+    Ctx &c = ctx();
+    if (h->sl.pend) {
+        // no E-step has run yet: finish the deferred repack here, then take the raw buffer over
+        PendingPrepare &p = *h->sl.pend;
+        HMMB_CUDA(cudaStreamSynchronize(c.copy_stream));
+        HMMB_TRY(launch_repack_range(h->sl, p.up->d_raw, p.idx_bytes, 0, h->sl.nblk, h->sl.d_bad));
+        HMMB_CUDA(cudaStreamSynchronize(c.stream));
+        h->d_raw = p.up->d_raw;
+        p.up->d_raw = nullptr;
+        h->sl.pend.reset();
+        h->check_bad = true;
+    } else if (h->pend_release) {
+        HMMB_CUDA(cudaStreamSynchronize(c.stream));
+        HMMB_TRY(bw_after_sync(h));
+    }
+    if (!h->d_raw) { set_error("dense transition matrices: the trainer no longer holds the raw codewords"); return HMMB_ERR_UNSUPPORTED; }
+    const int64_t R = h->sl.R;
+    HMMB_TRY(seqset_build(h->s, (const char *)h->d_raw - (size_t)h->keep_offsets[0] * h->raw_idx_bytes, h->raw_idx_bytes, 1,
+                          h->keep_offsets.data(), h->keep_words.data(), R, h->W, h->N, h->M, LAYOUT_AUTO));
+    // (bw_finish_create sized the alpha spill for both layouts already)
+    h->ltr_only = false;
+    dev_free(h->d_raw);
+    h->d_raw = nullptr;
+    h->keep_offsets.clear(); h->keep_offsets.shrink_to_fit();
+    h->keep_words.clear(); h->keep_words.shrink_to_fit();
+    return HMMB_OK;
+}
+
 // sync == false (pipelined create): the parameters go through a pinned staging buffer so that the call
 // neither blocks nor waits behind the codeword upload; everything stays ordered on the compute stream.
 static int bw_set_params_impl(hmmb_bw *h, const double *pi0, const double *A0, const double *B0, bool sync) {
@@ -976,7 +1049,11 @@ static int bw_set_params_impl(hmmb_bw *h, const double *pi0, const double *A0, c
         HMMB_CUDA(cudaMemcpyAsync(tmp + nB, A0, nA * sizeof(double), cudaMemcpyHostToDevice, c.stream));
         HMMB_CUDA(cudaMemcpyAsync(tmp + nB + nA, pi0, nP * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     } else {
-        const size_t bytes = (nB + nA + nP) * sizeof(double);
+        // Parts the caller holds in pinned memory go up straight from there (they must stay valid until the first
+        // hmmb_bw_iterate returns, like the codewords of a pipelined create); the rest is staged.
+        const bool pinB = nB * sizeof(double) >= (size_t(1) << 20) && host_is_pinned(B0);
+        const bool pinA = pinB && host_is_pinned(A0), pinP = pinB && host_is_pinned(pi0);
+        const size_t bytes = ((pinB ? 0 : nB) + (pinA ? 0 : nA) + (pinP ? 0 : nP)) * sizeof(double);
         if (c.pstage_busy) {
             cudaEventSynchronize(c.pstage_busy);
             event_put(c.pstage_busy);
@@ -995,12 +1072,21 @@ static int bw_set_params_impl(hmmb_bw *h, const double *pi0, const double *A0, c
             c.pstage_bytes = bytes;
         }
         double *ps = static_cast<double *>(c.pstage);
-        par_memcpy(ps, B0, nB * sizeof(double));
-        memcpy(ps + nB, A0, nA * sizeof(double));
-        memcpy(ps + nB + nA, pi0, nP * sizeof(double));
-        HMMB_TRY(h2d_small(tmp, ps, bytes));
-        c.pstage_busy = event_get();
-        HMMB_CUDA(cudaEventRecord(c.pstage_busy, c.h2d_on_copy ? c.copy_stream : c.stream));
+        auto put = [&](double *dst, const double *src, size_t n, bool pinned) -> int {
+            if (pinned) return h2d_small(dst, src, n * sizeof(double));
+            if (n * sizeof(double) >= (size_t(1) << 20)) par_memcpy(ps, src, n * sizeof(double));
+            else memcpy(ps, src, n * sizeof(double));
+            const int rc = h2d_small(dst, ps, n * sizeof(double));
+            ps += n;
+            return rc;
+        };
+        HMMB_TRY(put(tmp, B0, nB, pinB));
+        HMMB_TRY(put(tmp + nB, A0, nA, pinA));
+        HMMB_TRY(put(tmp + nB + nA, pi0, nP, pinP));
+        if (bytes) {
+            c.pstage_busy = event_get();
+            HMMB_CUDA(cudaEventRecord(c.pstage_busy, c.h2d_on_copy ? c.copy_stream : c.stream));
+        }
         HMMB_TRY(h2d_join());  // the kernels below read tmp
     }
     dim3 gb((unsigned)std::min((N * M + 255) / 256, 64), (unsigned)W);
@@ -1022,6 +1108,7 @@ static int bw_set_params_impl(hmmb_bw *h, const double *pi0, const double *A0, c
         }
         if (getenv("HMMB_FORCE_DENSE_A")) h->use_ltr = false;
     }
+    if (h->ltr_only && !h->use_ltr) HMMB_TRY(bw_build_generic_lazily(h));
     HMMB_LAUNCH("bw_load", k_load_clamped, (unsigned)std::min<size_t>((nA + 255) / 256, 1024), 256, 0, tmp + nB, (int64_t)nA, h->d_A);
     HMMB_LAUNCH("bw_load", k_load_clamped, (unsigned)std::min<size_t>((nP + 255) / 256, 1024), 256, 0, tmp + nB + nA, (int64_t)nP, h->d_pi);
     HMMB_LAUNCH("bw_load", k_fill, (unsigned)((W + 255) / 256), 256, 0, h->d_prev, (int64_t)W, -INFINITY);
@@ -1229,6 +1316,55 @@ static int launch_ltr_estep(hmmb_bw *h) {
                           (size_t)LTR_WARPS * 2 * NS * 8;
     HMMB_CUDA(cudaFuncSetAttribute(k_bw_fwdL<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
     HMMB_CUDA(cudaFuncSetAttribute(k_bw_bwdL<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    if (s.pend) {
+        // First E-step of a pipelined create (see launch_special_estep): stage j = the blocks whose codewords have
+        // landed, repacked and pushed through forward + backward on two alternating side streams while the later
+        // chunks are still on PCIe.  The accumulators take fp64 atomics from every stage, the exact kernel runs
+        // after the stages (its contributions do not depend on the backward pass), and the convergence statistic
+        // is taken from the per-sequence values by k_bw_reduce afterwards, so nothing has to be retaken.
+        Ctx &c = ctx();
+        PendingPrepare &p = *s.pend;
+        int bdone = 0, cdone = 0;
+        cudaStream_t main_stream = c.stream;
+        const bool side = p.nstage > 2 && !getenv("HMMB_PIPE_ONE_STREAM");
+        struct Restore { Ctx &c; cudaStream_t s; ~Restore() { c.stream = s; } } restore{c, main_stream};
+        if (side) {
+            cudaEvent_t fork = event_get();
+            HMMB_CUDA(cudaEventRecord(fork, main_stream));
+            for (auto st : c.stage_stream) HMMB_CUDA(cudaStreamWaitEvent(st, fork, 0));
+            event_put(fork);
+        }
+        for (int j = 0; j < p.nstage; ++j) {
+            if (side) c.stream = c.stage_stream[j & 1];
+            HMMB_CUDA(cudaStreamWaitEvent(c.stream, p.up->ev[p.ev_index[j]], 0));
+            HMMB_TRY(launch_repack_range(s, p.up->d_raw, p.idx_bytes, bdone, p.blk_end[j], s.d_bad));
+            const int c0 = cdone, c1 = p.cta_end[j];
+            if (c1 > c0) {
+                HMMB_LAUNCH("bw_forward", k_bw_fwdL<NS>, c1 - c0, LTR_THREADS, smem_f, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
+                            s.d_len, h->d_pi, h->d_A, h->d_Bt, M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag,
+                            h->d_allfull);
+                HMMB_LAUNCH("bw_backward", k_bw_bwdL<NS>, c1 - c0, LTR_THREADS, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
+                            s.d_len, h->d_A, h->d_Bt, M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero,
+                            h->d_allfull, h->d_accum, h->astride, h->d_flag, h->d_newflags);
+            }
+            bdone = p.blk_end[j];
+            cdone = p.cta_end[j];
+        }
+        c.stream = main_stream;
+        if (side) {
+            for (auto st : c.stage_stream) {
+                cudaEvent_t join = event_get();
+                HMMB_CUDA(cudaEventRecord(join, st));
+                HMMB_CUDA(cudaStreamWaitEvent(main_stream, join, 0));
+                event_put(join);
+            }
+        }
+        if (p.up->t0) { cudaEventDestroy(p.up->t0); p.up->t0 = nullptr; }
+        h->check_bad = true;
+        h->pend_release = std::move(s.pend);
+        HMMB_TRY((launch_exact<uint16_t, true>(h)));
+        return HMMB_OK;
+    }
     HMMB_LAUNCH("bw_forward", k_bw_fwdL<NS>, s.ncta, LTR_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs, s.d_len,
                 h->d_pi, h->d_A, h->d_Bt, M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag, h->d_allfull);
     HMMB_TRY((launch_exact<uint16_t, true>(h)));
@@ -1286,11 +1422,17 @@ static int bw_estep(hmmb_bw *h) {
 // state can go, and its codeword-range flag is read back (the check hmmb_bw_create makes itself when
 // it does the repack).
 static int bw_after_sync(hmmb_bw *h) {
+    if (h->pend_release && h->ltr_only && h->pend_release->up && !h->d_raw) {
+        // the raw codewords stay with the handle (lazy generic layout, see hmmb_bw.ltr_only)
+        cudaStreamSynchronize(ctx().copy_stream);
+        h->d_raw = h->pend_release->up->d_raw;
+        h->pend_release->up->d_raw = nullptr;
+    }
     h->pend_release.reset();
     if (h->check_bad) {
         h->check_bad = false;
         int bad = 0;
-        HMMB_CUDA(cudaMemcpy(&bad, h->s.d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+        HMMB_CUDA(cudaMemcpy(&bad, (h->ltr_only ? h->sl : h->s).d_bad, sizeof(int), cudaMemcpyDeviceToHost));
         if (bad) {
             set_error("codeword out of range: some observation is >= M=%d (reference: IndexError)", h->M);
             return HMMB_ERR_RANGE;

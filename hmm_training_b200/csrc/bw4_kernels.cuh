@@ -35,9 +35,15 @@ constexpr int SYM_BITS = 11;
 constexpr int BW4_MAX_M = 512;   // warp-private count copies must fit in shared memory
 // CTA work items of the N = 4 path are sized for ONE fat backward CTA per SM (up to BWD4_MAX_WARPS warps sharing one
 // copy of the word's B^T); the forward kernel keeps its 4-warp CTAs and splits every work item over FWD4_SPLIT CTAs.
-constexpr int BWD4_MAX_WARPS = 16;
+#ifndef BWD4_WARPS
+#define BWD4_WARPS 16
+#endif
+constexpr int BWD4_MAX_WARPS = BWD4_WARPS;
 constexpr int FWD4_SPLIT = 4;
-constexpr int BWD4_REP = 8;      // replicas of B^T in the backward kernel when they fit (M <= 256), see fwd4_run
+#ifndef BWD4_REPL
+#define BWD4_REPL 8
+#endif
+constexpr int BWD4_REP = BWD4_REPL;  // replicas of B^T in the backward kernel when they fit (M <= 256), see fwd4_run
 
 // ---------------------------------------------------------------- repack
 // One warp per (block, chunk of 8 steps), lane = sequence.  The conflict rank of a lane at a step
@@ -501,28 +507,104 @@ k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
 // Warp-private emission-count update in precomputed rank order (see k_repack_blocks4): one
 // conflict-free read-modify-write round per rank, rank 0 (distinct codewords) being the bulk.
 // Round 0 and round 1 (taken on ~93 % of the steps of the benchmark data) are written out; only ranks >= 2
-// loop.  row01 = this lane's (j = 0, 1) row of the warp's table, the (j = 2, 3) row sits M entries further.
-__device__ __forceinline__ void cnt_rmw4(double2 *__restrict__ row01, int M, double g0, double g1, double g2, double g3) {
-    double2 c01 = row01[0], c23 = row01[M];
-    c01.x += g0; c01.y += g1; c23.x += g2; c23.y += g3;
-    row01[0] = c01; row01[M] = c23;
+// loop.
+//
+// Shared-memory accesses of the backward kernel by 32-bit address.  The bases (B^T replica of the lane, count table of
+// the warp) are computed once and made opaque (hold32), so that they stay in two registers; written as C++ pointers
+// the compiler re-derives them from %tid and the shared window every step (~18 of 173 instructions per step).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned hold32(unsigned x) { return __shfl_sync(0xffffffffu, x, threadIdx.x & 31); }
+// read-only data (B^T): no memory clobber, free to move
+__device__ __forceinline__ double2 lds128_ro(unsigned addr) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
 }
-__device__ __forceinline__ void cnt_update4(double2 *__restrict__ cw01, int M, bool act, unsigned sym, int rank,
-                                            double g0, double g1, double g2, double g3) {
+__device__ __forceinline__ double2 lds128(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, double2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+// a double whose value is never used on the paths that do not assign it (no instruction, no zeroing)
+__device__ __forceinline__ double undef_f64() {
+    double x;
+    asm("" : "=d"(x));
+    return x;
+}
+// row = shared address of this lane's (j = 0, 1) count row; the (j = 2, 3) row sits `off23` bytes further
+__device__ __forceinline__ void cnt_rmw4(unsigned row, unsigned off23, double g0, double g1, double g2, double g3) {
+    double2 c01 = lds128(row), c23 = lds128(row + off23);
+    c01.x += g0; c01.y += g1; c23.x += g2; c23.y += g3;
+    sts128(row, c01); sts128(row + off23, c23);
+}
+// The rounds are straight-line predicated code behind a full-mask warp collective (the rank maximum), i.e. issued in
+// program order by a converged warp, and the shared-memory pipe serves one warp's accesses in issue order: a later
+// round (or the next step's round 0) reads what an earlier round stored without a __syncwarp() in between (each one
+// costs three instructions, nine per step).  The asm statements of lds128 / sts128 are volatile with a memory clobber, so
+// the compiler keeps their order as well.  -DBWD4_ROUND_SYNC=1 puts the barriers back.
+#ifndef BWD4_ROUND_SYNC
+#define BWD4_ROUND_SYNC 1
+#endif
+__device__ __forceinline__ void cnt_round_sync() {
+#if BWD4_ROUND_SYNC
+    __syncwarp();
+#endif
+}
+__device__ __forceinline__ void cnt_update4(unsigned row, unsigned off23, bool act, int rank, double g0, double g1,
+                                            double g2, double g3) {
     const int myrank = act ? rank : -1;
+#if defined(BWD4_ABLATE) && BWD4_ABLATE == 1  // timing experiment only (wrong counts): no count update at all
+    if (myrank == 77) cnt_rmw4(row, off23, g0, g1, g2, g3);
+    return;
+#endif
     const int maxrank = __reduce_max_sync(0xffffffffu, myrank);
-    double2 *row01 = cw01 + sym;
-    if (myrank == 0) cnt_rmw4(row01, M, g0, g1, g2, g3);
+    if (myrank == 0) cnt_rmw4(row, off23, g0, g1, g2, g3);
+#if defined(BWD4_ABLATE) && BWD4_ABLATE == 2  // timing experiment only (wrong counts): rank 0 only
+    cnt_round_sync();
+    return;
+#endif
     if (maxrank > 0) {  // warp-uniform
-        __syncwarp();
-        if (myrank == 1) cnt_rmw4(row01, M, g0, g1, g2, g3);
+        cnt_round_sync();
+        if (myrank == 1) cnt_rmw4(row, off23, g0, g1, g2, g3);
 #pragma unroll 1
         for (int r = 2; r <= maxrank; ++r) {
-            __syncwarp();
-            if (myrank == r) cnt_rmw4(row01, M, g0, g1, g2, g3);
+            cnt_round_sync();
+            if (myrank == r) cnt_rmw4(row, off23, g0, g1, g2, g3);
         }
     }
-    __syncwarp();
+    cnt_round_sync();
+}
+
+// (Experiment, off: -DBWD4_PRELOAD=1.  Measured 2.015 ms against 1.903 ms without it on config 3 — the eight registers
+// the rows occupy during the step's arithmetic cost more than the hidden LDS latency gains.)
+// The same with the rank-0 lanes' rows already in registers: the step loads them (cnt_preload4) as soon as it knows
+// its codeword, i.e. before its arithmetic, so that the round-0 read-modify-write does not wait for shared memory at
+// the end of the step (the DADDs behind the LDS were the hottest stall of the kernel).  The previous step's stores
+// precede the early loads in program order, and within a step no rank-0 row is written before round 0.
+__device__ __forceinline__ void cnt_preload4(unsigned row, unsigned off23, bool first, double2 &c01, double2 &c23) {
+    if (first) { c01 = lds128(row); c23 = lds128(row + off23); }
+}
+__device__ __forceinline__ void cnt_update4_pre(unsigned row, unsigned off23, bool act, int rank, double2 c01, double2 c23,
+                                                double g0, double g1, double g2, double g3) {
+    const int myrank = act ? rank : -1;
+    const int maxrank = __reduce_max_sync(0xffffffffu, myrank);
+    if (myrank == 0) {
+        c01.x += g0; c01.y += g1; c23.x += g2; c23.y += g3;
+        sts128(row, c01); sts128(row + off23, c23);
+    }
+    if (maxrank > 0) {  // warp-uniform
+        cnt_round_sync();
+        if (myrank == 1) cnt_rmw4(row, off23, g0, g1, g2, g3);
+#pragma unroll 1
+        for (int r = 2; r <= maxrank; ++r) {
+            cnt_round_sync();
+            if (myrank == r) cnt_rmw4(row, off23, g0, g1, g2, g3);
+        }
+    }
+    cnt_round_sync();
 }
 
 // all four non-negative doubles strictly positive? (integer pipe: x > 0 <=> hi|lo != 0)
@@ -550,7 +632,13 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 constexpr int BWD4_SPILL_PAD = 2;    // rows of padding in front of the alpha spill (see the step macro)
-constexpr int BWD_L2_PREFETCH = 12;  // steps ahead of use for prefetch.global.L2 of the alpha spill
+#ifndef BWD4_PRELOAD
+#define BWD4_PRELOAD 0
+#endif
+#ifndef BWD4_PF
+#define BWD4_PF 12
+#endif
+constexpr int BWD_L2_PREFETCH = BWD4_PF;  // steps ahead of use for prefetch.global.L2 of the alpha spill (even)
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr double LEAN_MIN = 0x1p-500;  // the lean backward step needs its three sums above this
 constexpr unsigned LEAN_MIN_HI = (1023u - 500u) << 20;  // high word of LEAN_MIN = 2^-500
@@ -571,7 +659,11 @@ __device__ __forceinline__ double recip_from_ref(double norm, double rref) {
 // (or any other loss in alpha-hat or beta-hat that matters for gamma) shows up here as a deviation of
 // sum_i alpha_t(i) beta_t(i) from P(O); beyond NORM_TOL the sequence is handed to the exact log-space kernel.
 constexpr double NORM_TOL = 1e-10;
-__device__ __forceinline__ bool norm_consistent(double norm, double r) { return fabs(fma(norm, r, -1.0)) <= NORM_TOL; }
+constexpr unsigned NORM_TOL_HI = 0x3DDB7CDFu;  // high word of 1e-10
+// (integer pipe: the high word of |x| orders like |x|; a NaN compares above every threshold)
+__device__ __forceinline__ bool norm_consistent(double norm, double r) {
+    return ((unsigned)__double2hiint(fma(norm, r, -1.0)) & 0x7fffffffu) < NORM_TOL_HI;
+}
 
 // State of one lane's backward recursion.
 template <bool BIDIAG>
@@ -676,6 +768,29 @@ __device__ __noinline__ void bwd4_step_slow(Bwd4State<BIDIAG> &st, const double 
     }
     st.v0 = v0; st.v1 = v1; st.v2 = v2; st.v3 = v3;
     st.vpos = (v0 > 0.0) & (v1 > 0.0) & (v2 > 0.0) & (v3 > 0.0);
+}
+
+// Careful version of the LAST part of a backward step only: v_j = b_j(o_t) beta-hat_t(j) when the lean step found
+// that sum tiny (its gamma / xi part had passed the magnitude tests and is already committed).  Same arithmetic
+// as the tail of bwd4_step_slow.  Returns true if the sequence has to be handed to the exact kernel.
+__device__ __noinline__ bool bwd4_v_slow(double h0, double h1, double h2, double h3, double b0, double b1, double b2,
+                                         double b3, double *v) {
+    bool imprecise = false;
+    double v0 = b0 * h0, v1 = b1 * h1, v2 = b2 * h2, v3 = b3 * h3;
+    const double vs = (v0 + v1) + (v2 + v3);
+    if (!(vs >= TINY_STEP)) {
+        double o[4];
+        int E;
+        if (exact_products4(h0, h1, h2, h3, b0, b1, b2, b3, o, &E) == 2) imprecise = true;
+        v0 = o[0]; v1 = o[1]; v2 = o[2]; v3 = o[3];
+    } else {
+        if (v0 == 0.0 && b0 > 0.0 && h0 > 0.0) v0 = tiny_pos();
+        if (v1 == 0.0 && b1 > 0.0 && h1 > 0.0) v1 = tiny_pos();
+        if (v2 == 0.0 && b2 > 0.0 && h2 > 0.0) v2 = tiny_pos();
+        if (v3 == 0.0 && b3 > 0.0 && h3 > 0.0) v3 = tiny_pos();
+    }
+    v[0] = v0; v[1] = v1; v[2] = v2; v[3] = v3;
+    return imprecise;
 }
 
 // (max, sum exp(. - max)) of log P_r over the sequences of one CTA work item, in a fixed order; the pairs of a
@@ -789,6 +904,9 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     // this lane's replica column of B^T: the row of codeword sym is at [sym * REP]
     const double2 *sB01 = reinterpret_cast<const double2 *>(sB) + (lane & (REP - 1)), *sB23 = sB01 + (size_t)M * REP;
     double *mypi = sPi + (size_t)warp * 4;
+    // 32-bit shared addresses of the lane's B^T replica column and of the warp's count table, held in registers
+    const unsigned bbase = hold32(smem_u32(sB01)), cbase = hold32(smem_u32(cntw01));
+    const unsigned B23_OFF = (unsigned)M * REP * 16u, CNT23_OFF = (unsigned)M * 16u;
     Bwd4State<BIDIAG> st;
 #pragma unroll
     for (int q = 0; q < (BIDIAG ? 7 : 16); ++q) st.X[q] = 0.0;
@@ -811,119 +929,136 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         const uint4 *op = obs_blk + bk.obs_base + lane;
         const double2 *sp = spill + bk.spill_base * 64 + lane;
         const int nch = (bk.tmax + SPC4 - 1) / SPC4;
-        // alpha-hat prefetch: P0 holds the next even time step, P1 the next odd one
+        // alpha-hat registers: P0 holds an even time step, P1 an odd one; every step loads its successor's row
         double2 P0_01 = make_double2(0.0, 0.0), P0_23 = P0_01, P1_01 = P0_01, P1_23 = P0_01;
         {
-            const int ta = bk.tmax - 1, tb = bk.tmax - 2;  // the first two steps of the block
-            double2 xa01 = P0_01, xa23 = P0_01, xb01 = P0_01, xb23 = P0_01;
-            if (ta < T) { xa01 = __ldcs(sp + (size_t)ta * 64); xa23 = __ldcs(sp + (size_t)ta * 64 + 32); }
-            if (tb >= 0 && tb < T) { xb01 = __ldcs(sp + (size_t)tb * 64); xb23 = __ldcs(sp + (size_t)tb * 64 + 32); }
-            if (ta & 1) { P1_01 = xa01; P1_23 = xa23; P0_01 = xb01; P0_23 = xb23; }
-            else        { P0_01 = xa01; P0_23 = xa23; P1_01 = xb01; P1_23 = xb23; }
+            // the rows of the block's first BWD_L2_PREFETCH steps are not covered by the prefetch inside the loop
+            const int r1 = nch * SPC4, r0 = max(r1 - BWD_L2_PREFETCH, 0);
+            const char *base = reinterpret_cast<const char *>(sp - lane) + (size_t)r0 * 1024;
+            for (int l = lane; l < (r1 - r0) * 8; l += 32) prefetch_l2(base + (size_t)l * 128);
+            const int ta = bk.tmax - 1;  // the first step of the block
+            if (ta < T) {
+                const double2 x01 = __ldcs(sp + (size_t)ta * 64), x23 = __ldcs(sp + (size_t)ta * 64 + 32);
+                if (ta & 1) { P1_01 = x01; P1_23 = x23; }
+                else        { P0_01 = x01; P0_23 = x23; }
+            }
         }
         int wbuf = 0;
         cp_async16(&sW[0][tid], op + (size_t)(nch - 1) * 32);
         cp_async_commit();
 
-// One backward step at time T_ (parity C_ = T_ & 1 is a literal; O_ = the other parity).
-#define HMMB_BWD_STEP(T_, C_, O_, SP_)                                                                              \
+// One backward step at time T_ (parity C_ = T_ & 1 is a literal; O_ = the other parity).  PACKED_ = the step's
+// codeword | rank << SYM_BITS.
+#define HMMB_BWD_STEP(T_, C_, O_, SP_, PACKED_)                                                                     \
     {                                                                                                               \
         const int t = (T_);                                                                                         \
         const double2 *spt = (SP_); /* = sp + t * 64: every address below is an immediate offset from it */         \
-        const unsigned packed = S16::pop_back(w);                                                                   \
+        const unsigned packed = (PACKED_);                                                                          \
         if (t < bk.tmax) { /* warp-uniform */                                                                       \
             const unsigned sym = packed & SYM_MASK;                                                                 \
             const bool act = t < T;                                                                                 \
             const double al0 = P##C_##_01.x, al1 = P##C_##_01.y, al2 = P##C_##_23.x, al3 = P##C_##_23.y;            \
-            /* unconditional, two steps ahead: a row at or beyond a lane's own T is never used, and for t < 2 */   \
-            /* the load lands in the previous block's tail / the front padding of the spill (BWD4_SPILL_PAD)  */   \
-            P##C_##_01 = __ldcs(spt - 2 * 64);                                                                      \
-            P##C_##_23 = __ldcs(spt - 2 * 64 + 32);                                                                 \
-            if (t >= BWD_L2_PREFETCH && t - BWD_L2_PREFETCH < T) { /* pull the spill towards L2 well ahead */      \
-                prefetch_l2(spt - BWD_L2_PREFETCH * 64);                                                            \
-                prefetch_l2(spt - BWD_L2_PREFETCH * 64 + 32);                                                       \
-            }                                                                                                       \
-            double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;                                                          \
+            /* alpha-hat of step t - 1 goes straight into the other parity's registers (free since the previous  */ \
+            /* step: no copies).  One step ahead is enough because the rows were pulled into L2 BWD_L2_PREFETCH   */ \
+            /* steps ago.  Unconditional: a row at or beyond a lane's own T is never used, and for t = 0 the     */ \
+            /* load lands in the previous block's tail / the front padding of the spill (BWD4_SPILL_PAD).        */ \
+            P##O_##_01 = __ldcs(spt - 64);                                                                          \
+            P##O_##_23 = __ldcs(spt - 64 + 32);                                                                     \
+            const unsigned brow = bbase + sym * (unsigned)(REP * 16);                                               \
+            const unsigned crow = cbase + sym * 16u;                                                                \
+            const int rank = (int)(packed >> SYM_BITS);                                                             \
+            double2 cn01 = make_double2(undef_f64(), undef_f64()), cn23 = cn01;                                     \
+            if (BWD4_PRELOAD) cnt_preload4(crow, CNT23_OFF, act && rank == 0, cn01, cn23);                          \
+            double g0 = undef_f64(), g1 = undef_f64(), g2 = undef_f64(), g3 = undef_f64();                          \
             if (act) {                                                                                              \
                 bool done = false;                                                                                  \
-                if (t == T - 1) {                                                                                   \
-                    /* first step of the sequence, inline: log beta_{T-1} = 0 (:363), so beta-hat = 1, gamma =  */  \
-                    /* alpha-hat / sum alpha-hat, no xi term, v = b(o_{T-1}).  The one true division of the      */  \
-                    /* sequence; every later step derives its 1 / norm from it (recip_from_ref).                */  \
-                    const double n0 = (al0 + al1) + (al2 + al3); /* in [1, 2): the forward pass rescaled it */     \
-                    const double r0 = 1.0 / n0;                                                                     \
-                    st.rref = r0;                                                                                   \
-                    g0 = fma(al0, r0, pos_to_tiny(al0)); g1 = fma(al1, r0, pos_to_tiny(al1));                       \
-                    g2 = fma(al2, r0, pos_to_tiny(al2)); g3 = fma(al3, r0, pos_to_tiny(al3));                       \
-                    const double2 b01 = sB01[sym * REP], b23 = sB23[sym * REP];                                     \
-                    st.v0 = b01.x; st.v1 = b01.y; st.v2 = b23.x; st.v3 = b23.y;                                     \
-                    st.vpos = all_pos4(b01.x, b01.y, b23.x, b23.y);                                                 \
-                    done = true;                                                                                    \
-                } else if (lean_ok && st.vpos) {                                                                    \
-                    /* lean path: beta_t(i) ~ q_i = sum_j a_ij v_j (:163-199); gamma_t(i) = al_i q_i / norm   */   \
+                if (lean_ok && st.vpos) { /* (vpos is false until the sequence's first step has run) */             \
+                    /* lean path: beta_t(i) ~ q_i = sum_j a_ij v_j (:163-199); gamma_t(i) = al_i q_i / norm   */    \
                     /* (:389-394); xi_t(i,j) = al_i a_ij v_j / norm (:397-410); norm = sum_i al_i q_i.  The    */   \
-                    /* denormal addends keep a finite-but-underflowed log value (barely) positive.            */   \
-                    const double v0 = st.v0, v1 = st.v1, v2 = st.v2, v3 = st.v3;                                    \
+                    /* denormal addends keep a finite-but-underflowed log value (barely) positive.            */    \
                     double q0, q1, q2, q3;                                                                          \
                     if (BIDIAG) {                                                                                   \
-                        q0 = fma(a[4], v1, fma(a[0], v0, tiny));                                                    \
-                        q1 = fma(a[5], v2, fma(a[1], v1, tiny));                                                    \
-                        q2 = fma(a[6], v3, fma(a[2], v2, tiny));                                                    \
-                        q3 = fma(a[3], v3, tiny);                                                                   \
+                        q0 = fma(a[4], st.v1, fma(a[0], st.v0, tiny));                                              \
+                        q1 = fma(a[5], st.v2, fma(a[1], st.v1, tiny));                                              \
+                        q2 = fma(a[6], st.v3, fma(a[2], st.v2, tiny));                                              \
+                        q3 = fma(a[3], st.v3, tiny);                                                                \
                     } else {                                                                                        \
-                        q0 = fma(a[3], v3, fma(a[2], v2, fma(a[1], v1, fma(a[0], v0, tiny))));                      \
-                        q1 = fma(a[7], v3, fma(a[6], v2, fma(a[5], v1, fma(a[4], v0, tiny))));                      \
-                        q2 = fma(a[11], v3, fma(a[10], v2, fma(a[9], v1, fma(a[8], v0, tiny))));                    \
-                        q3 = fma(a[15], v3, fma(a[14], v2, fma(a[13], v1, fma(a[12], v0, tiny))));                  \
+                        q0 = fma(a[3], st.v3, fma(a[2], st.v2, fma(a[1], st.v1, fma(a[0], st.v0, tiny))));          \
+                        q1 = fma(a[7], st.v3, fma(a[6], st.v2, fma(a[5], st.v1, fma(a[4], st.v0, tiny))));          \
+                        q2 = fma(a[11], st.v3, fma(a[10], st.v2, fma(a[9], st.v1, fma(a[8], st.v0, tiny))));        \
+                        q3 = fma(a[15], st.v3, fma(a[14], st.v2, fma(a[13], st.v1, fma(a[12], st.v0, tiny))));      \
                     }                                                                                               \
                     const double qs = (q0 + q1) + (q2 + q3);                                                        \
                     const double c0 = al0 * q0, c1 = al1 * q1, c2 = al2 * q2, c3 = al3 * q3;                        \
                     const double norm = (c0 + c1) + (c2 + c3);                                                      \
-                    const double r = recip_from_ref(norm, st.rref); /* 1 / norm without a division */              \
-                    const double sc = pow2_rescale_noacc(qs);                                                       \
-                    const double h0 = q0 * sc, h1 = q1 * sc, h2 = q2 * sc, h3 = q3 * sc; /* beta-hat_t */          \
-                    const double2 b01 = sB01[sym * REP], b23 = sB23[sym * REP];                                     \
-                    const double nv0 = fma(b01.x, h0, tiny), nv1 = fma(b01.y, h1, tiny);                            \
-                    const double nv2 = fma(b23.x, h2, tiny), nv3 = fma(b23.y, h3, tiny);                            \
-                    const double vs = (nv0 + nv1) + (nv2 + nv3);                                                    \
-                    /* the three sums are positive doubles: compare their high words on the integer pipe */        \
-                    const unsigned lo3 = min(min((unsigned)__double2hiint(norm), (unsigned)__double2hiint(qs)),     \
-                                             (unsigned)__double2hiint(vs));                                         \
-                    if ((lo3 >= LEAN_MIN_HI) & norm_consistent(norm, r) && (apos || all_pos4(al0, al1, al2, al3))) { \
+                    const double r = recip_from_ref(norm, st.rref); /* 1 / norm without a division */               \
+                    /* the sums are positive doubles: compare their high words on the integer pipe */               \
+                    const unsigned lo2 = min((unsigned)__double2hiint(norm), (unsigned)__double2hiint(qs));         \
+                    if ((lo2 >= LEAN_MIN_HI) & norm_consistent(norm, r) && (apos || all_pos4(al0, al1, al2, al3))) {\
+                        /* gamma and xi are committed here; what is left of the step is v for step t - 1 */         \
                         g0 = fma(c0, r, tiny); g1 = fma(c1, r, tiny); g2 = fma(c2, r, tiny); g3 = fma(c3, r, tiny); \
                         const double u0 = al0 * r, u1 = al1 * r, u2 = al2 * r, u3 = al3 * r;                        \
                         if (BIDIAG) {                                                                               \
-                            st.X[0] = fma(u0, v0, st.X[0]); st.X[1] = fma(u1, v1, st.X[1]);                         \
-                            st.X[2] = fma(u2, v2, st.X[2]); st.X[3] = fma(u3, v3, st.X[3]);                         \
-                            st.X[4] = fma(u0, v1, st.X[4]); st.X[5] = fma(u1, v2, st.X[5]);                         \
-                            st.X[6] = fma(u2, v3, st.X[6]);                                                         \
+                            st.X[0] = fma(u0, st.v0, st.X[0]); st.X[1] = fma(u1, st.v1, st.X[1]);                   \
+                            st.X[2] = fma(u2, st.v2, st.X[2]); st.X[3] = fma(u3, st.v3, st.X[3]);                   \
+                            st.X[4] = fma(u0, st.v1, st.X[4]); st.X[5] = fma(u1, st.v2, st.X[5]);                   \
+                            st.X[6] = fma(u2, st.v3, st.X[6]);                                                      \
                         } else {                                                                                    \
-                            st.X[0] = fma(u0, v0, st.X[0]);   st.X[1] = fma(u0, v1, st.X[1]);                       \
-                            st.X[2] = fma(u0, v2, st.X[2]);   st.X[3] = fma(u0, v3, st.X[3]);                       \
-                            st.X[4] = fma(u1, v0, st.X[4]);   st.X[5] = fma(u1, v1, st.X[5]);                       \
-                            st.X[6] = fma(u1, v2, st.X[6]);   st.X[7] = fma(u1, v3, st.X[7]);                       \
-                            st.X[8] = fma(u2, v0, st.X[8]);   st.X[9] = fma(u2, v1, st.X[9]);                       \
-                            st.X[10] = fma(u2, v2, st.X[10]); st.X[11] = fma(u2, v3, st.X[11]);                     \
-                            st.X[12] = fma(u3, v0, st.X[12]); st.X[13] = fma(u3, v1, st.X[13]);                     \
-                            st.X[14] = fma(u3, v2, st.X[14]); st.X[15] = fma(u3, v3, st.X[15]);                     \
+                            st.X[0] = fma(u0, st.v0, st.X[0]);   st.X[1] = fma(u0, st.v1, st.X[1]);                 \
+                            st.X[2] = fma(u0, st.v2, st.X[2]);   st.X[3] = fma(u0, st.v3, st.X[3]);                 \
+                            st.X[4] = fma(u1, st.v0, st.X[4]);   st.X[5] = fma(u1, st.v1, st.X[5]);                 \
+                            st.X[6] = fma(u1, st.v2, st.X[6]);   st.X[7] = fma(u1, st.v3, st.X[7]);                 \
+                            st.X[8] = fma(u2, st.v0, st.X[8]);   st.X[9] = fma(u2, st.v1, st.X[9]);                 \
+                            st.X[10] = fma(u2, st.v2, st.X[10]); st.X[11] = fma(u2, st.v3, st.X[11]);               \
+                            st.X[12] = fma(u3, st.v0, st.X[12]); st.X[13] = fma(u3, st.v1, st.X[13]);               \
+                            st.X[14] = fma(u3, st.v2, st.X[14]); st.X[15] = fma(u3, st.v3, st.X[15]);               \
                         }                                                                                           \
                         st.seenX = 0xffffu; /* every alpha_i > 0 and every v_j > 0 */                               \
-                        st.v0 = nv0; st.v1 = nv1; st.v2 = nv2; st.v3 = nv3;                                         \
+                        const double sc = pow2_rescale_noacc(qs);                                                   \
+                        const double h0 = q0 * sc, h1 = q1 * sc, h2 = q2 * sc, h3 = q3 * sc; /* beta-hat_t */       \
+                        const double2 b01 = lds128_ro(brow), b23 = lds128_ro(brow + B23_OFF);                       \
+                        st.v0 = fma(b01.x, h0, tiny); st.v1 = fma(b01.y, h1, tiny);                                 \
+                        st.v2 = fma(b23.x, h2, tiny); st.v3 = fma(b23.y, h3, tiny);                                 \
+                        const double vs = (st.v0 + st.v1) + (st.v2 + st.v3);                                        \
+                        if ((unsigned)__double2hiint(vs) < LEAN_MIN_HI) { /* tiny emission column: careful v */     \
+                            double vv[4];                                                                           \
+                            if (bwd4_v_slow(h0, h1, h2, h3, b01.x, b01.y, b23.x, b23.y, vv)) st.imprecise = true;   \
+                            st.v0 = vv[0]; st.v1 = vv[1]; st.v2 = vv[2]; st.v3 = vv[3];                             \
+                            st.vpos = all_pos4(vv[0], vv[1], vv[2], vv[3]);                                         \
+                        }                                                                                           \
                         done = true;                                                                                \
                     }                                                                                               \
                 }                                                                                                   \
                 if (!done) {                                                                                        \
-                    /* the careful step works on a stack copy so that `st` itself never has its address */         \
-                    /* taken and stays in registers on the lean path                                     */         \
-                    Bwd4State<BIDIAG> tmp = st;                                                                     \
-                    double g[4];                                                                                    \
-                    bwd4_step_slow<BIDIAG>(tmp, a, sB01, sB23, sym * REP, false, al0, al1, al2, al3, g);            \
-                    st = tmp;                                                                                       \
-                    g0 = g[0]; g1 = g[1]; g2 = g[2]; g3 = g[3];                                                     \
+                    if (t == T - 1) {                                                                               \
+                        /* first step of the sequence, inline: log beta_{T-1} = 0 (:363), so beta-hat = 1, gamma = */\
+                        /* alpha-hat / sum alpha-hat, no xi term, v = b(o_{T-1}).  The one true division of the     */\
+                        /* sequence; every later step derives its 1 / norm from it (recip_from_ref).               */\
+                        const double n0 = (al0 + al1) + (al2 + al3); /* in [1, 2): the forward pass rescaled it */  \
+                        const double r0 = 1.0 / n0;                                                                 \
+                        st.rref = r0;                                                                               \
+                        g0 = fma(al0, r0, pos_to_tiny(al0)); g1 = fma(al1, r0, pos_to_tiny(al1));                   \
+                        g2 = fma(al2, r0, pos_to_tiny(al2)); g3 = fma(al3, r0, pos_to_tiny(al3));                   \
+                        const double2 b01 = lds128_ro(brow), b23 = lds128_ro(brow + B23_OFF);                       \
+                        st.v0 = b01.x; st.v1 = b01.y; st.v2 = b23.x; st.v3 = b23.y;                                 \
+                        st.vpos = all_pos4(b01.x, b01.y, b23.x, b23.y);                                             \
+                    } else {                                                                                        \
+                        /* the careful step works on a stack copy so that `st` itself never has its address */      \
+                        /* taken and stays in registers on the lean path                                     */     \
+                        Bwd4State<BIDIAG> tmp = st;                                                                 \
+                        double g[4];                                                                                \
+                        bwd4_step_slow<BIDIAG>(tmp, a, sB01, sB23, sym * REP, false, al0, al1, al2, al3, g);        \
+                        st = tmp;                                                                                   \
+                        g0 = g[0]; g1 = g[1]; g2 = g[2]; g3 = g[3];                                                 \
+                    }                                                                                               \
                 }                                                                                                   \
             }                                                                                                       \
             if (t == 0) { /* gamma_0 sums (:415-426): once per block, fixed-order warp tree (inactive lanes add 0) */ \
-                double p0 = g0, p1 = g1, p2 = g2, p3 = g3;                                                          \
+                const int am = act ? -1 : 0; /* (bit masks: g is not defined for a lane without a frame) */         \
+                double p0 = __hiloint2double(__double2hiint(g0) & am, __double2loint(g0) & am);                     \
+                double p1 = __hiloint2double(__double2hiint(g1) & am, __double2loint(g1) & am);                     \
+                double p2 = __hiloint2double(__double2hiint(g2) & am, __double2loint(g2) & am);                     \
+                double p3 = __hiloint2double(__double2hiint(g3) & am, __double2loint(g3) & am);                     \
                 _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) {                                                \
                     p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o);           \
                     p2 += __shfl_xor_sync(0xffffffffu, p2, o); p3 += __shfl_xor_sync(0xffffffffu, p3, o);           \
@@ -931,7 +1066,8 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                 if (lane == 0) { mypi[0] += p0; mypi[1] += p1; mypi[2] += p2; mypi[3] += p3; }                      \
             }                                                                                                       \
             /* emission-count numerators (:460-500): warp-private rows, conflict-free rank order */                \
-            cnt_update4(cntw01, M, act, sym, (int)(packed >> SYM_BITS), g0, g1, g2, g3);                            \
+            if (BWD4_PRELOAD) cnt_update4_pre(crow, CNT23_OFF, act, rank, cn01, cn23, g0, g1, g2, g3);              \
+            else cnt_update4(crow, CNT23_OFF, act, rank, g0, g1, g2, g3);                                           \
         }                                                                                                           \
     }
 
@@ -946,8 +1082,14 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
             }
 #pragma unroll 1
             for (int pr = SPC4 / 2 - 1; pr >= 0; --pr) {
-                HMMB_BWD_STEP(c * SPC4 + 2 * pr + 1, 1, 0, spp + 64)
-                HMMB_BWD_STEP(c * SPC4 + 2 * pr, 0, 1, spp)
+                // pull the two alpha-hat rows that will be needed BWD_L2_PREFETCH steps from now (2 KB, contiguous)
+                // towards L2: lanes 0..15 take one 128-byte line each
+                if (c * SPC4 + 2 * pr >= BWD_L2_PREFETCH && lane < 16)
+                    prefetch_l2(reinterpret_cast<const char *>(spp) - BWD_L2_PREFETCH * 1024 + lane * (128 - 16));
+                const unsigned p1 = S16::pop_back(w);
+                HMMB_BWD_STEP(c * SPC4 + 2 * pr + 1, 1, 0, spp + 64, p1)
+                const unsigned p0 = S16::pop_back(w);
+                HMMB_BWD_STEP(c * SPC4 + 2 * pr, 0, 1, spp, p0)
                 spp -= 2 * 64;
             }
         }

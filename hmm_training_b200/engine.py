@@ -174,7 +174,7 @@ class BaumWelch:
                                     self.N, self.M, 1 if pipeline_upload else 0, ptr(p0), ptr(a0), ptr(b0)))
         self._h = h
         self._keep = None
-        self._obs_keepalive = obs if pipeline_upload else None
+        self._obs_keepalive = (obs, p0, a0, b0) if pipeline_upload else None  # (pinned parameters go up asynchronously too)
         self.frames = int(lib.hmmb_bw_total_frames(h))
 
     def set_params(self, pi0, A0, B0) -> None:

@@ -133,11 +133,13 @@ int hmmb_bw_create(hmmb_bw_t **out, const void *obs, int idx_bytes, int obs_on_d
                    const int64_t *offsets, const int32_t *word_of_seq, int64_t R, int W, int N,
                    int M);
 /* flags for hmmb_bw_create_ex.  HMMB_BW_PIPELINE_UPLOAD: when the codewords come from PINNED host
- * memory in (word, length-descending) order and N = 4, the call returns while they are still
+ * memory in (word, length-descending) order and either N = 4, or N = 8 / 16 with initial parameters
+ * whose A are all upper-bidiagonal (left-to-right kernels), the call returns while they are still
  * being uploaded (copy stream, a few chunks) and the first hmmb_bw_iterate runs its E-step stage
  * by stage behind the upload (repack -> forward -> backward of the blocks that have landed).
- * The caller must keep `obs` valid and unchanged until that first hmmb_bw_iterate has returned;
- * a codeword >= M is then reported by that call (HMMB_ERR_RANGE) instead of by the create.
+ * The caller must keep `obs` — and pi0 / A0 / B0 where they are pinned too: those then go up
+ * straight from the caller's memory — valid and unchanged until that first hmmb_bw_iterate has
+ * returned; a codeword >= M is then reported by that call (HMMB_ERR_RANGE) instead of by the create.
  * Results are those of the unpipelined path (the CTA partition is finer, so sums may differ in
  * the last bits).                                                                            */
 #define HMMB_BW_PIPELINE_UPLOAD 1

@@ -256,6 +256,72 @@ def test_pipelined_upload_matches_plain_create(S, ragged):
         _lib.load().hmmb_host_free(handle)
 
 
+@pytest.mark.parametrize("N,M,S,ragged", [(16, 1024, 600, False), (8, 300, 900, True)])
+def test_pipelined_upload_left_to_right_kernels(N, M, S, ragged):
+    """Config 4's shape through the pipelined create: pinned codewords + left-to-right initial parameters (pinned or
+    pageable) build ONLY the blocked layout, whose repack and first E-step run in stages behind the upload.  The
+    accumulators of these kernels take fp64 atomics, so the comparison with the plain path is 1e-12, not bit-exact.
+    A later set_params with a dense A must still work (the generic layout is then built from the kept codewords),
+    and a codeword >= M must still surface as IndexError."""
+    from hmm_training_b200 import _lib, engine
+    W, T = 40, 150
+    obs, offsets, wos = synthetic.fixed_length_codewords(5, W, S, T, N, M)
+    if ragged:
+        rng = np.random.default_rng(12)
+        lens = np.concatenate([np.sort(rng.integers(100, 2 * T + 1, size=S))[::-1] for _ in range(W)]).astype(np.int64)
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        obs = rng.integers(0, M, size=int(offsets[-1])).astype(np.uint16)
+    assert obs.nbytes >= 4 << 20  # large enough for the chunked upload
+    pi0, A0, B0 = engine.default_init(N, M)
+    pi0, A0, B0 = np.tile(pi0, (W, 1)), np.tile(A0, (W, 1, 1)), np.tile(B0, (W, 1, 1))
+    pinned, handle = _pinned_copy(obs)
+    pB, hB = _pinned_copy(B0)
+    pA, hA = _pinned_copy(A0)
+    pP, hP = _pinned_copy(pi0)
+    lib = _lib.load()
+    try:
+        with engine.BaumWelch(obs, offsets, wos, W, N, M) as bw:  # pageable input: plain path, both layouts
+            bw.set_params(pi0, A0, B0)
+            assert bw.kernel_family() == "left_to_right"
+            bw.iterate(3, 1e-6, 3)
+            ref = bw.params() + bw.history(3)
+        for params in ((pi0, A0, B0), (pP, pA, pB)):
+            got = engine.bw_fit(pinned, offsets, wos, W, N, M, *params, max_iterations=3)
+            for x, y in zip(got[:4], ref[:4]):
+                np.testing.assert_allclose(x, y, rtol=1e-12, atol=1e-300)
+            assert np.array_equal(got[4], ref[4])
+        # dense parameters after a pipelined left-to-right create
+        rng = np.random.default_rng(4)
+        Ad = rng.random((W, N, N)) + 0.1
+        Ad /= Ad.sum(axis=2, keepdims=True)
+        with engine.BaumWelch(obs, offsets, wos, W, N, M) as bw:
+            bw.set_params(pi0, Ad, B0)
+            assert bw.kernel_family() == "generic"
+            bw.iterate(2, 1e-6, 2)
+            refd = bw.params() + bw.history(2)
+        for first_iterate in (False, True):
+            with engine.BaumWelch(pinned, offsets, wos, W, N, M, pipeline_upload=True, init=(pi0, A0, B0)) as bw:
+                assert bw.kernel_family() == "left_to_right"
+                if first_iterate:
+                    bw.iterate(1, 1e-6, 3)
+                bw.set_params(pi0, Ad, B0)
+                assert bw.kernel_family() == "generic"
+                bw.iterate(2, 1e-6, 2)
+                gotd = bw.params() + bw.history(2)
+            for x, y in zip(gotd[:4], refd[:4]):
+                np.testing.assert_allclose(x, y, rtol=1e-12, atol=1e-300)
+        bad, hb = _pinned_copy(obs.astype(np.uint16))
+        try:
+            bad[len(bad) // 2 + 7] = M + 5  # >= M, in the second half of the upload
+            with pytest.raises(IndexError):
+                engine.bw_fit(bad, offsets, wos, W, N, M, pi0, A0, B0, max_iterations=2)
+        finally:
+            lib.hmmb_host_free(hb)
+    finally:
+        for hnd in (handle, hB, hA, hP):
+            lib.hmmb_host_free(hnd)
+
+
 def test_pipelined_upload_with_forward_handover():
     """in the pipelined first E-step the exact kernel runs after the staged backward passes, so
     the per-CTA convergence statistic taken inside k_bw_bwd4 missed every sequence the forward precision guard had

@@ -593,6 +593,19 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         const char *sp_line = reinterpret_cast<const char *>(spill + (size_t)bk.spill_base * L::CPR * 32) + (size_t)lane * 128;
         const int nch = (bk.tmax + SPC4 - 1) / SPC4;
         uint4 wnext = __ldg(op + (size_t)(nch - 1) * 32);
+        // alpha-hat of the step to come.  Every step loads its successor's row into these registers right after its
+        // own last use of them, so that the load (an L2 hit thanks to the prefetch below) is in flight during the
+        // count flush and the next step's q = A v, instead of being waited for at the first product with q (that
+        // wait was 14 % of the kernel's stall samples).  Unconditional: a row at or beyond a lane's own T lies
+        // inside the block's spill and is never used.
+        double al[NS];
+        double rref = 1.0;  // 1 / sum_i alpha-hat_{T-1}(i): reference of the division-free normalisation (bw4_kernels.cuh)
+#pragma unroll
+        for (int q = 0; q < L::CPR; ++q) {
+            const double2 x = __ldcs(sp + ((size_t)(bk.tmax - 1) * L::CPR + q) * 32);
+            al[2 * q] = x.x;
+            al[2 * q + 1] = x.y;
+        }
         for (int c = nch - 1; c >= 0; --c) {
             uint4 w = wnext;
             if (c > 0) wnext = __ldg(op + (size_t)(c - 1) * 32);
@@ -613,13 +626,6 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                 if (t >= BWDL_L2_PREFETCH && lane * 128 < NS * 8 * 32)  // pull the spill towards L2 well ahead
                     prefetch_l2(sp_line + (size_t)(t - BWDL_L2_PREFETCH) * (NS * 8 * 32));
                 if (act) {
-                    double al[NS];
-#pragma unroll
-                    for (int q = 0; q < L::CPR; ++q) {
-                        const double2 x = __ldcs(sp + ((size_t)t * L::CPR + q) * 32);
-                        al[2 * q] = x.x;
-                        al[2 * q + 1] = x.y;
-                    }
                     bool done = false;
                     if (lean_ok && (apos || all_posN<NS>(al))) {
                         double2 *sg = reinterpret_cast<double2 *>(stage);
@@ -633,7 +639,8 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                                 nv[2 * p + 1] = x.y;
                             }
                             if (max_hiN<NS>(nv) >= LEAN_MIN_HI) {
-                                const double r = 1.0 / tree_sum<NS>(al);
+                                const double r = 1.0 / tree_sum<NS>(al);  // the one true division of the sequence
+                                rref = r;
 #pragma unroll
                                 for (int p = 0; p < L::CPR; ++p)
                                     sg[p] = make_double2(fma(al[2 * p], r, tiny), fma(al[2 * p + 1], r, tiny));
@@ -661,8 +668,10 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                                 n3 = fma(al[i + 3], q[i + 3], n3);
                             }
                             const double norm = (n0 + n1) + (n2 + n3);
-                            if ((norm >= LEAN_MIN) & (qs >= LEAN_MIN)) {
-                                const double r = 1.0 / norm;
+                            // 1 / norm from the reference by exponent arithmetic; the same identity (sum_i alpha_t(i)
+                            // beta_t(i) = P(O) at every t) is the backward pass's precision check
+                            const double r = recip_from_ref(norm, rref);
+                            if ((norm >= LEAN_MIN) & (qs >= LEAN_MIN) & norm_consistent(norm, r)) {
                                 const double sc = pow2_rescale_noacc(qs);
 #pragma unroll
                                 for (int p = 0; p < L::CPR; ++p)  // gamma_t, staged (not yet issued)
@@ -697,6 +706,7 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                         for (int i = 0; i < NS; ++i) { tmp.v[i] = v[i]; tmp.Xs[i] = Xs[i]; tmp.Xn[i] = Xn[i]; alc[i] = al[i]; }
                         tmp.seenS = seenS; tmp.seenN = seenN; tmp.imprecise = imprecise; tmp.vpos = vpos;
                         bwdL_step_slow<NS>(tmp, sA, sB, sym, t == T - 1, alc, g);
+                        if (t == T - 1) rref = 1.0 / tree_sum<NS>(al);
 #pragma unroll
                         for (int i = 0; i < NS; ++i) { v[i] = tmp.v[i]; Xs[i] = tmp.Xs[i]; Xn[i] = tmp.Xn[i]; }
                         seenS = tmp.seenS; seenN = tmp.seenN; imprecise = tmp.imprecise; vpos = tmp.vpos;
@@ -711,6 +721,14 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                     bulk_reduce_add_f64(acc_cnt + (size_t)sym * NS, smem_addr(stage), NS * 8);
                     if (t == 0) bulk_reduce_add_f64(accw, smem_addr(stage), NS * 8);
 #endif
+                }
+                if (t > 0) {  // (warp-uniform) alpha-hat of step t - 1
+#pragma unroll
+                    for (int q = 0; q < L::CPR; ++q) {
+                        const double2 x = __ldcs(sp + ((size_t)(t - 1) * L::CPR + q) * 32);
+                        al[2 * q] = x.x;
+                        al[2 * q + 1] = x.y;
+                    }
                 }
 #if HMMB_LTR_TMA
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <cmath>
+#include <functional>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -53,6 +54,7 @@ struct Ctx {
     cudaStream_t d2h_stream = nullptr;   // results leaving while later stages still compute (pipelined scorer)
     cudaStream_t stage_stream[2] = {nullptr, nullptr};  // pipelined first E-step: stages alternate between these
     bool h2d_on_copy = false;            // small H2D copies of the running build go through copy_stream too
+    std::function<int(int, int)> after_chunk;  // (chunk, nchunk): called after a codeword chunk has been queued on copy_stream
     int64_t launches = 0;
     bool profiling = false;
     std::vector<std::string> phase_names;

@@ -328,6 +328,8 @@ struct SeqSet {
     int N = 0, M = 0, NP = 0, sym_bytes = 1;
     bool special4 = false;            // blocked layout (32 same-word sequences per block), N = 4 kernels
     int ltr_ns = 0;                   // blocked layout for the left-to-right kernels with NS = ltr_ns states
+    bool peer_enc = false;            // packed entries carry the peer lane (trainer's N = 4 layout, M <= 256; bw4_kernels.cuh)
+    unsigned symmask() const { return peer_enc ? PEER_SYM_MASK : SYM_MASK; }
     bool blocked() const { return special4 || ltr_ns != 0; }
     std::vector<int32_t> order;       // sorted -> original
     std::vector<int64_t> seq_begin;   // per word [W+1] (sorted order)
@@ -375,15 +377,22 @@ static int h2d_join() {
 static int pick_np(int N) { return N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : 32)); }
 
 // repack blocks [b0, b1) of the blocked layouts from the raw codewords (any input width)
+template <typename InT>
+static int launch_repack_typed(SeqSet &s, const InT *d_in, int b0, int b1, int *d_bad) {
+    if (s.peer_enc)
+        HMMB_LAUNCH("prepare", (k_repack_blocks4<InT, true>), b1 - b0, REPACK_WARPS * 32, 0, d_in, s.d_off, s.d_len, s.d_blks, b0, s.nblk, (uint4 *)s.d_obs, s.M, d_bad);
+    else
+        HMMB_LAUNCH("prepare", (k_repack_blocks4<InT, false>), b1 - b0, REPACK_WARPS * 32, 0, d_in, s.d_off, s.d_len, s.d_blks, b0, s.nblk, (uint4 *)s.d_obs, s.M, d_bad);
+    return HMMB_OK;
+}
 static int launch_repack_range(SeqSet &s, const void *d_in, int idx_bytes, int b0, int b1, int *d_bad) {
     if (b1 <= b0) return HMMB_OK;
     switch (idx_bytes) {
-        case 1: HMMB_LAUNCH("prepare", k_repack_blocks4<uint8_t>, b1 - b0, REPACK_WARPS * 32, 0, (const uint8_t *)d_in, s.d_off, s.d_len, s.d_blks, b0, s.nblk, (uint4 *)s.d_obs, s.M, d_bad); break;
-        case 2: HMMB_LAUNCH("prepare", k_repack_blocks4<uint16_t>, b1 - b0, REPACK_WARPS * 32, 0, (const uint16_t *)d_in, s.d_off, s.d_len, s.d_blks, b0, s.nblk, (uint4 *)s.d_obs, s.M, d_bad); break;
-        case 4: HMMB_LAUNCH("prepare", k_repack_blocks4<uint32_t>, b1 - b0, REPACK_WARPS * 32, 0, (const uint32_t *)d_in, s.d_off, s.d_len, s.d_blks, b0, s.nblk, (uint4 *)s.d_obs, s.M, d_bad); break;
-        default: HMMB_LAUNCH("prepare", k_repack_blocks4<unsigned long long>, b1 - b0, REPACK_WARPS * 32, 0, (const unsigned long long *)d_in, s.d_off, s.d_len, s.d_blks, b0, s.nblk, (uint4 *)s.d_obs, s.M, d_bad); break;
+        case 1: return launch_repack_typed(s, (const uint8_t *)d_in, b0, b1, d_bad);
+        case 2: return launch_repack_typed(s, (const uint16_t *)d_in, b0, b1, d_bad);
+        case 4: return launch_repack_typed(s, (const uint32_t *)d_in, b0, b1, d_bad);
+        default: return launch_repack_typed(s, (const unsigned long long *)d_in, b0, b1, d_bad);
     }
-    return HMMB_OK;
 }
 
 // first block whose codewords are not completely inside the first `hi_bytes` bytes of the raw stream
@@ -410,15 +419,12 @@ static int launch_prepare(SeqSet &s, const InT *d_in, int64_t nsym, int *d_bad, 
             for (int k = 0; k < up.nchunk; ++k) {
                 const int end = k == up.nchunk - 1 ? s.nblk : blocks_within(blks, done, off_s, len_s, (int)sizeof(InT), up.hi[k]);
                 HMMB_CUDA(cudaStreamWaitEvent(c.stream, up.ev[k], 0));
-                if (end > done)
-                    HMMB_LAUNCH("prepare", k_repack_blocks4<InT>, end - done, 256, 0, d_in, s.d_off, s.d_len, s.d_blks, done,
-                                s.nblk, (uint4 *)s.d_obs, s.M, d_bad);
+                if (end > done) HMMB_TRY(launch_repack_typed(s, d_in, done, end, d_bad));
                 done = end;
             }
         } else {
             if (up.active()) HMMB_CUDA(cudaStreamWaitEvent(c.stream, up.ev[up.nchunk - 1], 0));
-            HMMB_LAUNCH("prepare", k_repack_blocks4<InT>, s.nblk, 256, 0, d_in, s.d_off, s.d_len, s.d_blks, 0, s.nblk,
-                        (uint4 *)s.d_obs, s.M, d_bad);
+            if (s.nblk > 0) HMMB_TRY(launch_repack_typed(s, d_in, 0, s.nblk, d_bad));
         }
     } else {
         if (up.active()) HMMB_CUDA(cudaStreamWaitEvent(c.stream, up.ev[up.nchunk - 1], 0));
@@ -464,6 +470,8 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     s.sym_bytes = M <= 256 ? 1 : 2;
     s.special4 = layout == LAYOUT_AUTO && N == 4 && M <= BW4_MAX_M && !getenv("HMMB_FORCE_GENERIC");
     s.ltr_ns = (layout == LAYOUT_LTR) ? N : 0;
+    // (the scorer builds its sets with word_of_seq == nullptr and keeps the plain codeword | rank entries)
+    s.peer_enc = BWD4_PEER_ENC && s.special4 && word_of_seq != nullptr && M <= PEER_MAX_M;
 
     std::unique_ptr<EarlyUpload> up_owner(new EarlyUpload());
     EarlyUpload &up = *up_owner;
@@ -1261,7 +1269,7 @@ static int launch_exact(hmmb_bw *h) {
     SeqSet &s = h->cur();
     HMMB_LAUNCH("bw_exact", (k_bw_exact<SymT, BLOCKED>), h->exact_grid, BW_THREADS, 0, s.d_obs, BLOCKED ? s.d_foff : s.d_off,
                 s.d_len, s.d_word, s.R, h->N, h->M, h->d_pi, h->d_A, h->d_Bt, h->d_llseq, h->d_active, h->d_flag,
-                h->d_exact_scratch, h->exact_stride, h->d_accum, h->astride, h->d_nexact);
+                h->d_exact_scratch, h->exact_stride, h->d_accum, h->astride, h->d_nexact, s.symmask());
     return HMMB_OK;
 }
 
@@ -1310,7 +1318,7 @@ static int launch_special_estep(hmmb_bw *h) {
         if (c1 <= c0) return HMMB_OK;
         HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, (c1 - c0) * FWD4_SPLIT, BW_THREADS, smem_f, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
                     s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_flag,
-                    h->d_allfull, FWD4_SPLIT);
+                    h->d_allfull, FWD4_SPLIT, s.symmask());
         HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT, REP>), c1 - c0, bwd_threads, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
                     s.d_len, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_bzero,
                     h->d_allfull, h->d_partials + (size_t)c0 * h->pstride, h->pstride, h->d_flag, h->d_newflags);
@@ -1384,7 +1392,7 @@ static int launch_special_estep(hmmb_bw *h) {
     }
     HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta * FWD4_SPLIT, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
                 s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_flag,
-                h->d_allfull, FWD4_SPLIT);
+                h->d_allfull, FWD4_SPLIT, s.symmask());
     HMMB_TRY((launch_exact<uint16_t, true>(h)));
     HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT, REP>), s.ncta, bwd_threads, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
                 s.d_len, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_bzero,

@@ -33,6 +33,18 @@ constexpr int SPC4 = 8;          // packed u16 entries per uint4
 constexpr unsigned SYM_MASK = 0x7ffu;
 constexpr int SYM_BITS = 11;
 constexpr int BW4_MAX_M = 512;   // warp-private count copies must fit in shared memory
+// Peer encoding of the trainer's N = 4 layout for alphabets of at most 256 codewords (the reference's 256, CodeVector/main.py):
+// entry = codeword (8 bits) | peer lane (5 bits) << 8 | min(rank, 7) << 13.  The peer of a rank-0 lane is the rank-1
+// lane that sees the same codeword at that step (itself if there is none): k_bw_bwd4 lets the rank-0 lane pull that
+// lane's gamma through a shuffle and add both in ONE read-modify-write, which removes the second round that ~93 %
+// of the steps of uniform data needed (two shared-memory loads, two stores and a warp barrier for ~8 lanes).
+// EXPERIMENT, OFF by default: parity-green (all GPU tests pass with it), but the eight SHFL.IDX per step cost more
+// than the round they replace — k_bw_bwd4 1.985 ms against 1.900 ms without it on config 3, same gpurun call.
+#ifndef BWD4_PEER_ENC
+#define BWD4_PEER_ENC 0
+#endif
+constexpr unsigned PEER_SYM_MASK = 0xffu;
+constexpr int PEER_MAX_M = 256;
 // CTA work items of the N = 4 path are sized for ONE fat backward CTA per SM (up to BWD4_MAX_WARPS warps sharing one
 // copy of the word's B^T); the forward kernel keeps its 4-warp CTAs and splits every work item over FWD4_SPLIT CTAs.
 #ifndef BWD4_WARPS
@@ -51,7 +63,7 @@ constexpr int BWD4_REP = BWD4_REPL;  // replicas of B^T in the backward kernel w
 // lanes that agree with me on every bit are my peers.  No shared memory, no barriers; the output
 // row of the chunk is one coalesced 512-byte store.
 constexpr int REPACK_WARPS = 8;
-template <typename InT>
+template <typename InT, bool PEER = false>
 __global__ void __launch_bounds__(REPACK_WARPS * 32)
 k_repack_blocks4(const InT *__restrict__ obs, const int64_t *__restrict__ off_sorted,
                  const int32_t *__restrict__ len_sorted, const Blk *__restrict__ blks, int blk_base, int nblk,
@@ -87,7 +99,14 @@ k_repack_blocks4(const InT *__restrict__ obs, const int64_t *__restrict__ off_so
                 peers &= ((sym >> bit) & 1u) ? set : ~set;
             }
             const unsigned rank = __popc(peers & lt);
-            const unsigned packed = have ? (sym | (rank << SYM_BITS)) : 0u;
+            unsigned packed;
+            if (PEER) {
+                const unsigned rest = peers & (peers - 1u);  // without the rank-0 lane
+                const unsigned peer = (have && rank == 0u && rest) ? (unsigned)(__ffs(rest) - 1) : (unsigned)lane;
+                packed = (have ? (sym | (min(rank, 7u) << 13)) : 0u) | (peer << 8);
+            } else {
+                packed = have ? (sym | (rank << SYM_BITS)) : 0u;
+            }
             r[s >> 1] |= packed << ((s & 1) * 16);
         }
         obs_blk[bk.obs_base + (size_t)c * 32 + lane] = make_uint4(r[0], r[1], r[2], r[3]);
@@ -201,7 +220,8 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
                                            const double *__restrict__ sBmax,
                                            const unsigned char *__restrict__ sBmask, const double *a,
                                            const double (&p)[4], double rmax, const Masks4 &mk,
-                                           double2 *__restrict__ sp, bool &allfull, int slot = 0) {
+                                           double2 *__restrict__ sp, bool &allfull, int slot = 0,
+                                           unsigned symmask = SYM_MASK) {
     using S16 = Sym<uint16_t>;
     double al0 = 0.0, al1 = 0.0, al2 = 0.0, al3 = 0.0;
     double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;  // error bounds, units of 2^-1000: per state (VECB) or e0 = their sum
@@ -219,7 +239,7 @@ __device__ __forceinline__ double fwd4_run(int T, int tmax, const uint4 *__restr
 #pragma unroll 2
         for (int s = 0; s < SPC4; ++s) {
             const int t = c * SPC4 + s;
-            const unsigned sym = S16::pop_front(w) & SYM_MASK;
+            const unsigned sym = S16::pop_front(w) & symmask;
             if (t < T && !stop) {
                 const double2 b01 = sB01[sym * REP + slot], b23 = sB23[sym * REP + slot];
                 const unsigned r = (t == 0) ? mk.pmask : lut4(mk.lutF, m);  // reachable before emission
@@ -469,7 +489,8 @@ __global__ void __launch_bounds__(BW_THREADS, FWD4_MIN_CTAS)
 k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const uint4 *__restrict__ obs_blk,
           const int32_t *__restrict__ len_sorted, const double *__restrict__ pi, const double *__restrict__ A,
           const double *__restrict__ Bt, int M, double2 *__restrict__ spill, double *__restrict__ ll_seq,
-          const int32_t *__restrict__ active, uint8_t *__restrict__ flag, uint8_t *__restrict__ allfull, int split) {
+          const int32_t *__restrict__ active, uint8_t *__restrict__ flag, uint8_t *__restrict__ allfull, int split,
+          unsigned symmask) {
     extern __shared__ double sB[];  // [M][4] B^T, [M] per-codeword max, [M] support masks (u8)
     double *sBmax = sB + (size_t)M * 4;
     unsigned char *sBmask = reinterpret_cast<unsigned char *>(sBmax + M);
@@ -494,7 +515,7 @@ k_bw_fwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         bool af = false;
         const double ll = fwd4_run<BIDIAG, true>(T, bk.tmax, obs_blk + bk.obs_base + lane, reinterpret_cast<const double2 *>(sB),
                                                  reinterpret_cast<const double2 *>(sB) + M, sBmax, sBmask, a, p, rmax,
-                                                 mk, spill + bk.spill_base * 64 + lane, af);
+                                                 mk, spill + bk.spill_base * 64 + lane, af, 0, symmask);
         if (T > 0) {
             ll_seq[bk.first + lane] = ll;
             allfull[bk.first + lane] = af ? 1 : 0;
@@ -598,6 +619,47 @@ __device__ __forceinline__ void cnt_update4_pre(unsigned row, unsigned off23, bo
     if (maxrank > 0) {  // warp-uniform
         cnt_round_sync();
         if (myrank == 1) cnt_rmw4(row, off23, g0, g1, g2, g3);
+#pragma unroll 1
+        for (int r = 2; r <= maxrank; ++r) {
+            cnt_round_sync();
+            if (myrank == r) cnt_rmw4(row, off23, g0, g1, g2, g3);
+        }
+    }
+    cnt_round_sync();
+}
+
+// Count update with the peer encoding (see BWD4_PEER_ENC): the rank-0 lane of a codeword adds its own gamma and, pulled
+// through a shuffle, that of the codeword's rank-1 lane in one read-modify-write; only ranks >= 2 (about a quarter of
+// the steps of uniform data) still take rounds of their own.  Lanes that are switched off at run time (sequence handed
+// to the exact kernel, impossible sequence, or no frame at this step) are handled through the ballot of `act`: a rank-0
+// lane still does the update for an active peer, an inactive peer contributes nothing.  Rank codes are capped at 7; a
+// step in which some lane reaches the cap (eight or more lanes on one codeword) falls back to exact ranks from
+// MATCH.ANY and plain rounds.
+__device__ __forceinline__ void cnt_update4_peer(unsigned row, unsigned off23, bool act, int rankcode, unsigned peer,
+                                                 unsigned sym, int lane, double g0, double g1, double g2, double g3) {
+    const int myrank = act ? rankcode : -1;
+    const int maxrank = __reduce_max_sync(0xffffffffu, myrank);
+    if (maxrank >= 7) {  // warp-uniform, rare
+        const unsigned same = __match_any_sync(0xffffffffu, act ? sym : 0x10000u + (unsigned)lane);
+        const int exact = act ? __popc(same & ((1u << lane) - 1u)) : -1;
+        const int maxexact = __reduce_max_sync(0xffffffffu, exact);
+        for (int r = 0; r <= maxexact; ++r) {
+            if (exact == r) cnt_rmw4(row, off23, g0, g1, g2, g3);
+            __syncwarp();
+        }
+        return;
+    }
+    const unsigned actmask = __ballot_sync(0xffffffffu, act);
+    const double q0 = __shfl_sync(0xffffffffu, g0, peer), q1 = __shfl_sync(0xffffffffu, g1, peer);
+    const double q2 = __shfl_sync(0xffffffffu, g2, peer), q3 = __shfl_sync(0xffffffffu, g3, peer);
+    const bool pact = peer != (unsigned)lane && ((actmask >> peer) & 1u);
+    if (rankcode == 0 && (act || pact)) {
+        double2 c01 = lds128(row), c23 = lds128(row + off23);
+        if (act) { c01.x += g0; c01.y += g1; c23.x += g2; c23.y += g3; }
+        if (pact) { c01.x += q0; c01.y += q1; c23.x += q2; c23.y += q3; }
+        sts128(row, c01); sts128(row + off23, c23);
+    }
+    if (maxrank >= 2) {  // warp-uniform
 #pragma unroll 1
         for (int r = 2; r <= maxrank; ++r) {
             cnt_round_sync();
@@ -865,6 +927,8 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
           const int32_t *__restrict__ b_has_zero, const uint8_t *__restrict__ allfull, double *__restrict__ partials,
           int64_t pstride, uint8_t *__restrict__ flag, int32_t *__restrict__ new_flags) {
     using S16 = Sym<uint16_t>;
+    // (the B^T replicas exist exactly for the alphabets the peer encoding covers: M <= 256, see bw_estep)
+    constexpr bool PEER = BWD4_PEER_ENC && REP > 1;
     const int M = MT ? MT : M_rt;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     extern __shared__ double smem[];
@@ -955,7 +1019,7 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         const double2 *spt = (SP_); /* = sp + t * 64: every address below is an immediate offset from it */         \
         const unsigned packed = (PACKED_);                                                                          \
         if (t < bk.tmax) { /* warp-uniform */                                                                       \
-            const unsigned sym = packed & SYM_MASK;                                                                 \
+            const unsigned sym = packed & (PEER ? PEER_SYM_MASK : SYM_MASK);                                        \
             const bool act = t < T;                                                                                 \
             const double al0 = P##C_##_01.x, al1 = P##C_##_01.y, al2 = P##C_##_23.x, al3 = P##C_##_23.y;            \
             /* alpha-hat of step t - 1 goes straight into the other parity's registers (free since the previous  */ \
@@ -966,9 +1030,9 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
             P##O_##_23 = __ldcs(spt - 64 + 32);                                                                     \
             const unsigned brow = bbase + sym * (unsigned)(REP * 16);                                               \
             const unsigned crow = cbase + sym * 16u;                                                                \
-            const int rank = (int)(packed >> SYM_BITS);                                                             \
+            const int rank = (int)(packed >> (PEER ? 13 : SYM_BITS));                                               \
             double2 cn01 = make_double2(undef_f64(), undef_f64()), cn23 = cn01;                                     \
-            if (BWD4_PRELOAD) cnt_preload4(crow, CNT23_OFF, act && rank == 0, cn01, cn23);                          \
+            if (BWD4_PRELOAD && !PEER) cnt_preload4(crow, CNT23_OFF, act && rank == 0, cn01, cn23);                 \
             double g0 = undef_f64(), g1 = undef_f64(), g2 = undef_f64(), g3 = undef_f64();                          \
             if (act) {                                                                                              \
                 bool done = false;                                                                                  \
@@ -1066,7 +1130,8 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                 if (lane == 0) { mypi[0] += p0; mypi[1] += p1; mypi[2] += p2; mypi[3] += p3; }                      \
             }                                                                                                       \
             /* emission-count numerators (:460-500): warp-private rows, conflict-free rank order */                \
-            if (BWD4_PRELOAD) cnt_update4_pre(crow, CNT23_OFF, act, rank, cn01, cn23, g0, g1, g2, g3);              \
+            if (PEER) cnt_update4_peer(crow, CNT23_OFF, act, rank, (packed >> 8) & 31u, sym, lane, g0, g1, g2, g3); \
+            else if (BWD4_PRELOAD) cnt_update4_pre(crow, CNT23_OFF, act, rank, cn01, cn23, g0, g1, g2, g3);         \
             else cnt_update4(crow, CNT23_OFF, act, rank, g0, g1, g2, g3);                                           \
         }                                                                                                           \
     }

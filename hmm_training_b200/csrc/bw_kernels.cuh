@@ -228,7 +228,8 @@ k_bw_exact(const void *__restrict__ obs, const int64_t *__restrict__ base_sorted
            const int32_t *__restrict__ word_sorted, int64_t R, int N, int M, const double *__restrict__ pi,
            const double *__restrict__ A, const double *__restrict__ Bt, double *__restrict__ ll_seq,
            const int32_t *__restrict__ active, const uint8_t *__restrict__ flag, double *__restrict__ scratch,
-           int64_t scratch_stride, double *__restrict__ accum, int64_t astride, int64_t *__restrict__ n_exact) {
+           int64_t scratch_stride, double *__restrict__ accum, int64_t astride, int64_t *__restrict__ n_exact,
+           unsigned symmask) {
     if (!any_flag_raised(flag)) return;  // nothing was ever handed over: no scan of the R flags
     const int lane = threadIdx.x & 31;
     const int64_t gw = (int64_t)blockIdx.x * BW_WARPS + (threadIdx.x >> 5);
@@ -246,7 +247,7 @@ k_bw_exact(const void *__restrict__ obs, const int64_t *__restrict__ base_sorted
             const double *piw = pi + (size_t)w * N, *Aw = A + (size_t)w * N * N, *Btw = Bt + (size_t)w * M * N;
             double logP;
             if (BLOCKED) {
-                BlkObs<SymT> o{reinterpret_cast<const uint4 *>(obs) + base_sorted[rr]};
+                BlkObs<SymT> o{reinterpret_cast<const uint4 *>(obs) + base_sorted[rr], symmask};
                 logP = exact_forward(T, N, lane, o, piw, Aw, Btw, sc);
                 __syncwarp();
                 if (logP > neg_inf()) exact_backward_accumulate(T, N, lane, o, Aw, Btw, sc, logP, accum + (size_t)w * astride);

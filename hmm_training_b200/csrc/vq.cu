@@ -116,6 +116,20 @@ __device__ __forceinline__ double exact_d2(const double (&x)[13], const double *
 //     reports the contract's near-ties, (d2 - d1) / d1 < 1e-12.
 // Indices are therefore those of the exact scan for EVERY frame; only the amount of fp64 work differs.
 constexpr int VQ_FPT = 2;            // frames per thread in the prefilter (each shared-memory centroid row feeds both)
+static_assert(VQ_FPT == 2, "the prefilter packs its two frames into one f32x2 chain");
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 constexpr double VQ_TOL_REL = 2.05e-6;
 constexpr double VQ_TOL_ABS = 1e-37;
 
@@ -197,6 +211,9 @@ k_vq_assign(const double *__restrict__ X, int64_t F, const double *__restrict__ 
             m1[u] = m2[u] = __int_as_float(0x7f800000);
             k1[u] = 0;
         }
+        unsigned long long x2[VQ_D];  // (-2 x-hat of frame 0, of frame 1) per dimension
+#pragma unroll
+        for (int d = 0; d < VQ_D; ++d) x2[d] = pack2(xm2[0][d], xm2[1][d]);
         for (int tile = 0; tile < ntiles; ++tile) {
             const int k0 = tile * VQ_TILE;
             const int kt = min(VQ_TILE, K - k0);
@@ -233,13 +250,18 @@ k_vq_assign(const double *__restrict__ X, int64_t F, const double *__restrict__ 
                 for (int j = 0; j < 4; ++j) {
                     // padding rows (k + j >= kt) are zeros starting from +inf: never the smallest or second smallest
                     const float4 ca = c4[(k + j) * 3], cb = c4[(k + j) * 3 + 1], cc = c4[(k + j) * 3 + 2];
+                    // Both frames of the thread in one packed chain: FFMA2 with the centroid coordinate as the
+                    // broadcast scalar operand (sm_100a: `FFMA2 Rd, Ra.F32x2, Rb.F32, Rc.F32x2`), 12 instructions
+                    // instead of 24 for the pair; each half is the same IEEE fused multiply-add as fmaf.
+                    const float cv[VQ_D] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w, cc.x, cc.y, cc.z, cc.w};
+                    unsigned long long s2 = pack2(nv[j], nv[j]);
+#pragma unroll
+                    for (int d = 0; d < VQ_D; ++d) s2 = ffma2(x2[d], pack2(cv[d], cv[d]), s2);
+                    float sv[VQ_FPT];
+                    unpack2(s2, sv[0], sv[1]);
 #pragma unroll
                     for (int u = 0; u < VQ_FPT; ++u) {
-                        float s = nv[j];
-                        s = fmaf(xm2[u][0], ca.x, s); s = fmaf(xm2[u][1], ca.y, s); s = fmaf(xm2[u][2], ca.z, s);
-                        s = fmaf(xm2[u][3], ca.w, s); s = fmaf(xm2[u][4], cb.x, s); s = fmaf(xm2[u][5], cb.y, s);
-                        s = fmaf(xm2[u][6], cb.z, s); s = fmaf(xm2[u][7], cb.w, s); s = fmaf(xm2[u][8], cc.x, s);
-                        s = fmaf(xm2[u][9], cc.y, s); s = fmaf(xm2[u][10], cc.z, s); s = fmaf(xm2[u][11], cc.w, s);
+                        const float s = sv[u];
                         const float hi = fmaxf(s, m1[u]);
                         k1[u] = (s < m1[u]) ? (k0 + k + j) : k1[u];
                         m1[u] = fminf(s, m1[u]);
@@ -321,37 +343,57 @@ k_vq_exact_list(const double *__restrict__ X, const double *__restrict__ C, int 
                 int *__restrict__ n_near, int32_t near_base) {
     if (skip && *skip) return;
     const int n = *n_work;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    // One WARP per listed frame (a single thread's scan of K centroids is a serial chain of ~40 K dependent DP
+    // instructions: with a few hundred frames on the list that latency, 0.1 ms, was a third of the whole encode call).
+    // Lane l scans centroids l, l + 32, ... in index order with the reference's rule and keeps (smallest, its index,
+    // second smallest); the lanes' triples are merged with "smaller distance, then lower index" — the first centroid
+    // that attains the minimum in index order, and the second order statistic of all K distances, as the serial scan.
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
         const int64_t f = worklist[i];
         double x[13];
 #pragma unroll
         for (int d = 0; d < 13; ++d) x[d] = __ldg(X + f * 13 + d);
-        double best_d2 = pos_inf(), best_s = pos_inf(), second_s = pos_inf();
-        int best = 0;
-        for (int k = 0; k < K; ++k) {
+        double best_s = pos_inf(), second_s = pos_inf();
+        int best = lane;
+        for (int k = lane; k < K; k += 32) {
             double c[VQ_D];
 #pragma unroll
             for (int d = 0; d < VQ_D; ++d) c[d] = __ldg(C + (size_t)k * 13 + 1 + d);
-            const double a = exact_d2(x, c);
-            const double s = sqrt(a);
-            if (a < best_d2 && s < best_s) {
+            const double sk = sqrt(exact_d2(x, c));
+            if (sk < best_s) {
                 second_s = best_s;
-                best_s = s; best_d2 = a; best = k;
-            } else if (s < second_s) {
-                second_s = s;
+                best_s = sk; best = k;
+            } else if (sk < second_s) {
+                second_s = sk;
             }
         }
-        if (idx_out) idx_out[f] = best;
-        if (dist_out) dist_out[f] = best_s;
-        if (n_near && (second_s - best_s) <= VQ_NEAR_TIE_REL * best_s) {  // (also exact ties: twins, duplicates)
-            const int p = atomicAdd(n_near, 1);
-            if (p < near_cap) near[p] = (int32_t)f + near_base;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best_s, o), o2 = __shfl_xor_sync(0xffffffffu, second_s, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best, o);
+            const bool other_wins = ob < best_s || (ob == best_s && oi < best);
+            if (other_wins) {
+                second_s = fmin(best_s, o2);
+                best_s = ob; best = oi;
+            } else {
+                second_s = fmin(ob, second_s);
+            }
+        }
+        if (best >= K) best = 0;  // (K < 32 and nothing comparable: the serial scan's initial index)
+        if (lane == 0) {
+            if (idx_out) idx_out[f] = best;
+            if (dist_out) dist_out[f] = best_s;
+            if (n_near && (second_s - best_s) <= VQ_NEAR_TIE_REL * best_s) {  // (also exact ties: twins, duplicates)
+                const int p = atomicAdd(n_near, 1);
+                if (p < near_cap) near[p] = (int32_t)f + near_base;
+            }
         }
         if (MODE == 1) {
-#pragma unroll
-            for (int d = 0; d < 13; ++d) atomicAdd(accum + best * ACC_W + d, x[d]);
-            atomicAdd(accum + best * ACC_W + 13, 1.0);
-            atomicAdd(accum + (size_t)K * ACC_W, best_s);
+            if (lane < 13) atomicAdd(accum + best * ACC_W + lane, __ldg(X + f * 13 + lane));
+            if (lane == 13) atomicAdd(accum + best * ACC_W + 13, 1.0);
+            if (lane == 14) atomicAdd(accum + (size_t)K * ACC_W, best_s);
         }
     }
 }

@@ -171,3 +171,72 @@ def test_virtual_ranks_on_one_device_equal_single_rank(N, M, G):
     got = _one_iteration(engine, [seqs[i] for i in shards[0]], wos[shards[0]], W, N, M, init, 0, G, inject)
     for x, y, name in zip(got, want, ("pi", "A", "B", "statistic", "iterations")):
         assert_close(x, y, f"{G} virtual ranks: {name}", rtol=1e-12)
+
+
+# ---------------------------------------------------------------- VQ encode and recognition
+vq_shape = st.tuples(st.integers(1, 700), st.sampled_from([1, 2, 7, 31, 32, 33, 256, 300, 600]), st.sampled_from([0, 1, 2, 3]),
+                     st.integers(0, 2 ** 31 - 1))
+
+
+@pytest.mark.gpu
+@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@given(vq_shape)
+def test_gpu_vq_encode_properties(p):
+    """get_observations (HMM/hmm_training.py:95-118) for drawn frame / codebook shapes: bit-exact against the C oracle
+    (every frame, whether the fp32 prefilter decides it or the exact list kernel does), invariant under a permutation
+    of the frames, lowest index among duplicated centroids, and encoding a centroid returns the first copy of itself."""
+    from hmm_training_b200 import engine
+    from oracle import vq_oracle
+    F, K, kind, seed = p
+    rng = np.random.default_rng(seed)
+    C = rng.normal(size=(K, 13)) * 10.0
+    if kind == 1 and K > 1:    # duplicated and all-zero centroids
+        C[rng.integers(0, K, size=max(1, K // 4))] = C[0]
+        C[K // 2] = 0.0
+    if kind == 2:              # tightly clustered codebook: everything is a near-tie for the prefilter
+        C = C[:1] + rng.normal(size=(K, 13)) * 1e-7
+    X = C[rng.integers(0, K, size=F)] + rng.normal(size=(F, 13)) * (1e-9 if kind == 3 else 3.0)
+    X[:, 0] = rng.normal(size=F) * 1e3  # dimension 0 never takes part
+    idx = engine.vq_encode(X, C)
+    assert np.array_equal(idx, vq_oracle.encode(X, C))
+    perm = rng.permutation(F)
+    assert np.array_equal(engine.vq_encode(X[perm], C), idx[perm])
+    own = engine.vq_encode(C, C)
+    first = np.array([np.flatnonzero((C[:, 1:] == c[1:]).all(axis=1))[0] for c in C])
+    assert np.array_equal(own, first)
+
+
+score_shape = st.tuples(st.sampled_from([2, 4, 4, 5, 8, 16]), st.sampled_from([4, 16, 256, 300]), st.integers(1, 4),
+                        st.integers(1, 40), st.booleans(), st.sampled_from([0.0, 0.3]), st.integers(0, 2 ** 31 - 1))
+
+
+@pytest.mark.gpu
+@settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+@given(score_shape)
+def test_gpu_scoring_properties(p):
+    """calculate_log_likelihood / test_hmm (HMM/hmm_testing.py:49-104, 139-161): the [U, W] matrix equals the oracle's,
+    is invariant under a permutation of the utterances, the argmax is the first maximum (-1 = "unknown" when no model
+    can emit the utterance), and the scorer agrees with the trainer's own first-iteration statistic."""
+    from hmm_training_b200 import engine
+    N, M, W, U, ltr, zf, seed = p
+    rng = np.random.default_rng(seed)
+    pi, A, B = _random_model(rng, W, N, M, ltr, zf)
+    if zf > 0:
+        B[rng.random(B.shape) < 0.2] = 0.0  # structural zeros in the emissions: some utterances become impossible
+        B[:, :, 0] += 1e-3
+        B /= B.sum(axis=2, keepdims=True)
+    seqs, _ = _random_corpus(rng, 1, U, 1, 80, M)
+    obs, off = _pack(seqs)
+    ll, best = engine.score(obs, off, N, M, pi, A, B)
+    ref = O.score_batch(seqs, [(A[w], B[w], pi[w]) for w in range(W)])
+    assert_close(ll, ref, "log-likelihood matrix")
+    assert np.array_equal(best, O.argmax_first(ref))
+    perm = rng.permutation(U)
+    obs2, off2 = _pack([seqs[u] for u in perm])
+    ll2, best2 = engine.score(obs2, off2, N, M, pi, A, B)
+    assert np.array_equal(ll2, ll[perm]) and np.array_equal(best2, best[perm])
+    # the trainer's statistic of its first iteration is log_sum_exp over the same per-utterance values
+    w = int(rng.integers(0, W))
+    _, _, _, hist, _ = engine.bw_fit(obs, off, np.zeros(U, dtype=np.int32), 1, N, M, pi[w:w + 1], A[w:w + 1], B[w:w + 1],
+                                     epsilon=-1.0, max_iterations=1)
+    assert_close(hist[0, 0], O.log_sum_exp(ref[:, w]), "E-step statistic vs scorer")

@@ -601,6 +601,21 @@ def block_shards(env: Env):
     out["vq_encode_sharded"] = {"metric": "vq_encode_frames_per_s", "value": F * env.world / dt, "unit": "frames/s (host API per rank, pinned buffers)",
                                 "frames_total": F * env.world, "K": K, "ranks": env.world, "seconds": dt,
                                 "parallelism": "frame ranges per rank, no collective"}
+    # BASELINE config 2's codebook build with the frames split over the ranks: every Lloyd pass ends in one
+    # sum-all-reduce of the centroid sums, counts and the global distance (<= 28.7 KB)
+    try:
+        ar = env.allreduce_hook("native") if env.world > 1 else None
+        engine.lbg_fit(Xp, K, 100, 1e-3, allreduce=ar)
+        env.barrier()
+        t0 = time.perf_counter()
+        _, _, _, iters, _ = engine.lbg_fit(Xp, K, 100, 1e-3, allreduce=ar)
+        dt = env.max_over_ranks(time.perf_counter() - t0)
+        out["lbg_sharded"] = {"metric": "lbg_codebook_build_s", "value": dt, "unit": "s", "higher_is_better": False,
+                              "frames_total": F * env.world, "K": K, "ranks": env.world, "lloyd_passes": int(np.sum(iters)),
+                              "allreduce": "one per Lloyd pass (centroid sums + counts + distance)",
+                              "parallelism": "frame ranges per rank"}
+    except Exception as exc:  # pragma: no cover
+        out["lbg_sharded"] = {"error": repr(exc)}
     return out
 
 

@@ -111,9 +111,31 @@ k_bw_bwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
         stage[par * 32 + lane] = 0.0;
         __syncwarp();
         const unsigned gm = gmask << gbase;
+        // software pipeline of the step's loads (as in fwdG_run): alpha-hat and b(o_t) one step ahead, the codeword
+        // two steps ahead — the step used to wait for all three in turn (half of the kernel's stall samples)
+        unsigned sym_c = 0u, sym_n = 0u;
+        double al_c = 0.0, b_c = 0.0;
+        {
+            const int t0 = Tw - 1;
+            if (t0 < T) {
+                sym_c = (unsigned)o[t0];
+                if (i < N) {
+                    al_c = sp[(size_t)t0 * N + i];
+                    b_c = __ldg(Btw + (size_t)sym_c * N + i);
+                }
+            }
+            if (t0 >= 1 && t0 - 1 < T) sym_n = (unsigned)o[t0 - 1];
+        }
         for (int t = Tw - 1; t >= 0; --t) {
             const bool act = t < T;
             const bool last = (t == T - 1);
+            double al_n = 0.0, b_n = 0.0;
+            unsigned sym_nn = 0u;
+            if (t >= 1 && t - 1 < T && i < N) {
+                al_n = sp[(size_t)(t - 1) * N + i];
+                b_n = __ldg(Btw + (size_t)sym_n * N + i);
+            }
+            if (t >= 2 && t - 2 < T) sym_nn = (unsigned)o[t - 2];
             const unsigned vmask = (__ballot_sync(0xffffffffu, v > 0.0) >> gbase) & gmask;
             double q = 0.0;
             if (act) {
@@ -135,7 +157,7 @@ k_bw_bwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
             if (act) {
                 if (!last && qs > 0.0) sc = pow2_rescale_noacc(qs);
                 h = q * sc;  // beta-hat_t(i), group sum in [1,2)
-                al = i < N ? sp[(size_t)t * N + i] : 0.0;
+                al = al_c;
                 g = al * h;
             }
             double norm = group_sum<NP>(g);
@@ -155,7 +177,7 @@ k_bw_bwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
                 const double r1 = norm > 0.0 ? 1.0 / norm : 0.0;
                 g *= r1;  // gamma_t(i) (:389-394)
                 if (g == 0.0 && al > 0.0 && h > 0.0) g = tiny_pos();
-                sym = o[t];
+                sym = sym_c;
                 if (!last) {
                     u *= r1;
                     const double *sv = stage + par * 32 + gbase;
@@ -171,7 +193,7 @@ k_bw_bwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
             // v_i = b_i(o_t) beta-hat_t(i) for step t-1
             double b = 0.0;
             if (act) {
-                b = i < N ? __ldg(Btw + (size_t)sym * N + i) : 0.0;
+                b = b_c;
                 v = b * h;
                 if (v == 0.0 && b > 0.0 && h > 0.0) v = tiny_pos();
             }
@@ -194,6 +216,7 @@ k_bw_bwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
             par ^= 1;
             stage[par * 32 + lane] = v;
             __syncwarp();
+            al_c = al_n; b_c = b_n; sym_c = sym_n; sym_n = sym_nn;
         }
         if (T > 0 && i < N) {
 #pragma unroll

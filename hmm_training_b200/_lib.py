@@ -68,6 +68,7 @@ SYMBOLS = [
     ("hmmb_bw_total_frames", _c.c_int64, [_c.c_void_p]),
     ("hmmb_bw_kernel_family", _c.c_char_p, [_c.c_void_p]),
     ("hmmb_bw_diagnostics", _c.c_int, [_c.c_void_p, _lp, _lp]),
+    ("hmmb_bw_thin_states", _c.c_int, [_c.c_void_p, _lp]),
     ("hmmb_bw_fit", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int,
                                _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_double, _c.c_int, _c.c_void_p,
                                _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),

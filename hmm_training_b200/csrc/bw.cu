@@ -787,6 +787,16 @@ struct hmmb_bw {
     int raw_idx_bytes = 0;
     // ... and its initial B goes up in `bpieces` word ranges interleaved with the codeword chunks (B^T of piece p is
     // ready at bt_ready[p], recorded on the copy stream), so that the first stage does not wait for all of B
+    // thin-state rescue (hmm_device.cuh): sticky per-word state masks, slots behind the accumulators
+    uint32_t *d_thinmask = nullptr;   // [W]
+    int32_t *d_thin_new = nullptr;    // states flagged since the host last looked
+    int32_t *d_redo = nullptr;        // [W] words whose M-step was held back for a repeat of the iteration
+    int32_t *d_redo_in = nullptr;     // [W] copy of d_redo that the repeat runs on (the M-step rewrites d_redo)
+    int32_t *d_slot_of = nullptr;     // [W][N] slot of a flagged state, -1 = none
+    int32_t *act_cur = nullptr;       // the word mask the E-step launches use (d_active, or d_redo in a repeat)
+    int64_t slot_cap = 0, rstride = 0;
+    int n_slots = 0;
+    int64_t n_thin_total = 0;
     int bpieces = 0, bpieces_issued = 0;
     cudaEvent_t bt_ready[PendingPrepare::MAX_STAGES] = {};
     double *d_ptmp = nullptr;     // upload buffer of those parameters (released after the first E-step)
@@ -845,12 +855,13 @@ static void bw_release(hmmb_bw *h) {
     dev_free(h->d_accum); dev_free(h->d_partials); dev_free(h->d_prev); dev_free(h->d_hist); dev_free(h->d_active);
     dev_free(h->d_iters); dev_free(h->d_any); dev_free(h->d_cta_begin); dev_free(h->d_seq_begin);
     dev_free(h->d_bzero); dev_free(h->d_flag_base); dev_free(h->d_newflags); dev_free(h->d_nexact); dev_free(h->d_exact_scratch);
+    dev_free(h->d_thinmask); dev_free(h->d_thin_new); dev_free(h->d_redo); dev_free(h->d_redo_in); dev_free(h->d_slot_of);
 }
 
 static int bw_alloc_accum(hmmb_bw *h) {
     dev_free(h->d_accum);
     h->d_accum = nullptr;
-    h->accum_n = (int64_t)h->W * h->astride + (int64_t)h->world * h->W * 2;
+    h->accum_n = (int64_t)h->W * h->astride + (int64_t)h->world * h->W * 2 + (int64_t)h->world * h->slot_cap * h->rstride;
     return dev_alloc_t(&h->d_accum, (size_t)h->accum_n);
 }
 
@@ -876,9 +887,16 @@ static int bw_finish_create(hmmb_bw *h, int64_t R) {
     TRYF(bw_alloc_accum(h));
     TRYF(dev_alloc_t(&h->d_prev, (size_t)W));
     TRYF(dev_alloc_t(&h->d_active, (size_t)W));
+    h->act_cur = h->d_active;
     TRYF(dev_alloc_t(&h->d_iters, (size_t)W));
     TRYF(dev_alloc_t(&h->d_any, 1));
     TRYF(dev_alloc_t(&h->d_bzero, (size_t)W));
+    h->rstride = ((int64_t)N + M + 15) & ~int64_t(15);
+    TRYF(dev_alloc_t(&h->d_thinmask, (size_t)W));
+    TRYF(dev_alloc_t(&h->d_thin_new, 1));
+    TRYF(dev_alloc_t(&h->d_redo, (size_t)W));
+    TRYF(dev_alloc_t(&h->d_redo_in, (size_t)W));
+    TRYF(dev_alloc_t(&h->d_slot_of, (size_t)W * N));
     TRYF(dev_alloc_t(&h->d_flag_base, (size_t)std::max<int64_t>(R, 1) + FLAG_HDR));  // header: see raise_flag
     h->d_flag = h->d_flag_base + FLAG_HDR;
     TRYF(dev_alloc_t(&h->d_newflags, 1));
@@ -1212,6 +1230,13 @@ static int bw_set_params_impl(hmmb_bw *h, const double *pi0, const double *A0, c
     HMMB_CUDA(cudaMemsetAsync(h->d_newflags, 0, sizeof(int32_t), c.stream));
     HMMB_CUDA(cudaMemsetAsync(h->d_nexact, 0, sizeof(int64_t), c.stream));
     h->n_backward_handover = 0;
+    // (new parameters: the thin-state flags of the old model go; the slot region keeps its allocation)
+    HMMB_CUDA(cudaMemsetAsync(h->d_thinmask, 0, (size_t)W * sizeof(uint32_t), c.stream));
+    HMMB_CUDA(cudaMemsetAsync(h->d_thin_new, 0, sizeof(int32_t), c.stream));
+    HMMB_CUDA(cudaMemsetAsync(h->d_redo, 0, (size_t)W * sizeof(int32_t), c.stream));
+    HMMB_CUDA(cudaMemsetAsync(h->d_slot_of, 0xff, (size_t)W * N * sizeof(int32_t), c.stream));
+    h->n_slots = 0;
+    h->n_thin_total = 0;
     if (sync) HMMB_CUDA(cudaStreamSynchronize(c.stream));
     if (pieces) h->d_ptmp = tmp;  // still the target of copies to come: released after the first E-step
     else dev_free(tmp);           // stream-ordered reuse: later users of the block are queued behind the kernels above
@@ -1268,7 +1293,7 @@ template <typename SymT, bool BLOCKED>
 static int launch_exact(hmmb_bw *h) {
     SeqSet &s = h->cur();
     HMMB_LAUNCH("bw_exact", (k_bw_exact<SymT, BLOCKED>), h->exact_grid, BW_THREADS, 0, s.d_obs, BLOCKED ? s.d_foff : s.d_off,
-                s.d_len, s.d_word, s.R, h->N, h->M, h->d_pi, h->d_A, h->d_Bt, h->d_llseq, h->d_active, h->d_flag,
+                s.d_len, s.d_word, s.R, h->N, h->M, h->d_pi, h->d_A, h->d_Bt, h->d_llseq, h->act_cur, h->d_flag,
                 h->d_exact_scratch, h->exact_stride, h->d_accum, h->astride, h->d_nexact, s.symmask());
     return HMMB_OK;
 }
@@ -1285,10 +1310,10 @@ static int launch_generic_estep(hmmb_bw *h) {
     const int64_t per_group = (s.R + total_groups - 1) / total_groups;
     HMMB_LAUNCH("bw_forward", (k_bw_fwdG<NP, SymT>), (unsigned)grid, BW_THREADS, 0, (const SymT *)s.d_obs, s.d_off, s.d_len,
                 s.d_word, s.d_foff, s.R, per_group, h->N, h->M, h->d_pi, h->d_A, h->d_Bt, h->d_spill, h->d_llseq,
-                h->d_active, h->d_flag);
+                h->act_cur, h->d_flag);
     HMMB_TRY((launch_exact<SymT, false>(h)));
     HMMB_LAUNCH("bw_backward", (k_bw_bwdG<NP, SymT>), (unsigned)grid, BW_THREADS, 0, (const SymT *)s.d_obs, s.d_off, s.d_len,
-                s.d_word, s.d_foff, s.R, per_group, h->N, h->M, h->d_A, h->d_Bt, h->d_spill, h->d_llseq, h->d_active,
+                s.d_word, s.d_foff, s.R, per_group, h->N, h->M, h->d_A, h->d_Bt, h->d_spill, h->d_llseq, h->act_cur,
                 h->d_accum, h->astride, h->d_flag, h->d_newflags);
     return HMMB_OK;
 }
@@ -1317,10 +1342,10 @@ static int launch_special_estep(hmmb_bw *h) {
     auto launch_range = [&](int c0, int c1) -> int {
         if (c1 <= c0) return HMMB_OK;
         HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, (c1 - c0) * FWD4_SPLIT, BW_THREADS, smem_f, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
-                    s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_flag,
+                    s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->act_cur, h->d_flag,
                     h->d_allfull, FWD4_SPLIT, s.symmask());
         HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT, REP>), c1 - c0, bwd_threads, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
-                    s.d_len, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_bzero,
+                    s.d_len, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->act_cur, h->d_bzero,
                     h->d_allfull, h->d_partials + (size_t)c0 * h->pstride, h->pstride, h->d_flag, h->d_newflags);
         return HMMB_OK;
     };
@@ -1386,16 +1411,16 @@ static int launch_special_estep(hmmb_bw *h) {
         // accumulator contributions are independent of the backward pass); the per-CTA statistic, taken inside
         // k_bw_bwd4 while those sequences still carried their NaN mark, is then retaken
         HMMB_TRY((launch_exact<uint16_t, true>(h)));
-        HMMB_LAUNCH("bw_exact", k_bw_llstat_fix, s.ncta, BW_THREADS, 0, s.d_work, s.d_blks, h->d_llseq, h->d_active,
+        HMMB_LAUNCH("bw_exact", k_bw_llstat_fix, s.ncta, BW_THREADS, 0, s.d_work, s.d_blks, h->d_llseq, h->act_cur,
                     h->d_flag, h->d_partials, h->pstride, h->M);
         return HMMB_OK;
     }
     HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta * FWD4_SPLIT, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
-                s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_flag,
+                s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->act_cur, h->d_flag,
                 h->d_allfull, FWD4_SPLIT, s.symmask());
     HMMB_TRY((launch_exact<uint16_t, true>(h)));
     HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT, REP>), s.ncta, bwd_threads, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
-                s.d_len, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->d_active, h->d_bzero,
+                s.d_len, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->act_cur, h->d_bzero,
                 h->d_allfull, h->d_partials, h->pstride, h->d_flag, h->d_newflags);
     return HMMB_OK;
 }
@@ -1442,10 +1467,10 @@ static int launch_ltr_estep(hmmb_bw *h) {
             }
             if (c1 > c0) {
                 HMMB_LAUNCH("bw_forward", k_bw_fwdL<NS>, c1 - c0, LTR_THREADS, smem_f, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
-                            s.d_len, h->d_pi, h->d_A, h->d_Bt, M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag,
+                            s.d_len, h->d_pi, h->d_A, h->d_Bt, M, (double2 *)h->d_spill, h->d_llseq, h->act_cur, h->d_flag,
                             h->d_allfull);
                 HMMB_LAUNCH("bw_backward", k_bw_bwdL<NS>, c1 - c0, LTR_THREADS, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
-                            s.d_len, h->d_A, h->d_Bt, M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero,
+                            s.d_len, h->d_A, h->d_Bt, M, (const double2 *)h->d_spill, h->d_llseq, h->act_cur, h->d_bzero,
                             h->d_allfull, h->d_accum, h->astride, h->d_flag, h->d_newflags);
             }
             bdone = p.blk_end[j];
@@ -1467,12 +1492,12 @@ static int launch_ltr_estep(hmmb_bw *h) {
         return HMMB_OK;
     }
     HMMB_LAUNCH("bw_forward", k_bw_fwdL<NS>, s.ncta, LTR_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs, s.d_len,
-                h->d_pi, h->d_A, h->d_Bt, M, (double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_flag, h->d_allfull);
+                h->d_pi, h->d_A, h->d_Bt, M, (double2 *)h->d_spill, h->d_llseq, h->act_cur, h->d_flag, h->d_allfull);
     HMMB_TRY((launch_exact<uint16_t, true>(h)));
     const int groups = (h->allreduce && h->world > 1) ? std::min(h->overlap_groups, h->W) : 1;
     if (groups <= 1) {
         HMMB_LAUNCH("bw_backward", k_bw_bwdL<NS>, s.ncta, LTR_THREADS, smem_b, s.d_work, s.d_blks, (const uint4 *)s.d_obs, s.d_len,
-                    h->d_A, h->d_Bt, M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero, h->d_allfull,
+                    h->d_A, h->d_Bt, M, (const double2 *)h->d_spill, h->d_llseq, h->act_cur, h->d_bzero, h->d_allfull,
                     h->d_accum, h->astride, h->d_flag, h->d_newflags);
         return HMMB_OK;
     }
@@ -1483,13 +1508,13 @@ static int launch_ltr_estep(hmmb_bw *h) {
     // group's backward pass computes.  hook(NULL, 0) at the end joins the side stream.
     HMMB_LAUNCH("bw_reduce", k_bw_reduce, dim3((unsigned)h->W, 1u), RED_THREADS, 0, (const double *)nullptr, h->pstride,
                 h->d_cta_begin, h->d_llseq, h->d_seq_begin, h->d_accum, h->astride, h->nacc,
-                h->d_accum + (size_t)h->W * h->astride, h->rank, h->W, h->d_active);
+                h->d_accum + (size_t)h->W * h->astride, h->rank, h->W, h->act_cur);
     for (int g = 0; g < groups; ++g) {
         const int w0 = (int)((int64_t)h->W * g / groups), w1 = (int)((int64_t)h->W * (g + 1) / groups);
         const int c0 = s.cta_begin[w0], c1 = s.cta_begin[w1];
         if (c1 > c0)
             HMMB_LAUNCH("bw_backward", k_bw_bwdL<NS>, c1 - c0, LTR_THREADS, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
-                        s.d_len, h->d_A, h->d_Bt, M, (const double2 *)h->d_spill, h->d_llseq, h->d_active, h->d_bzero,
+                        s.d_len, h->d_A, h->d_Bt, M, (const double2 *)h->d_spill, h->d_llseq, h->act_cur, h->d_bzero,
                         h->d_allfull, h->d_accum, h->astride, h->d_flag, h->d_newflags);
         int rc = h->allreduce(h->d_accum + (size_t)w0 * h->astride, (int64_t)(w1 - w0) * h->astride, h->user);
         if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
@@ -1543,6 +1568,107 @@ static int bw_after_sync(hmmb_bw *h) {
     return HMMB_OK;
 }
 
+// ---- thin-state rescue, host side (device side: hmm_device.cuh / bw_kernels.cuh)
+static double *rescue_base(hmmb_bw *h) { return h->d_accum + (size_t)h->W * h->astride + (size_t)h->world * h->W * 2; }
+
+// log-space pass over the sequences of the words with flagged states (after the E-step, before the reduce)
+static int launch_rescue(hmmb_bw *h) {
+    if (h->n_slots == 0) return HMMB_OK;
+    SeqSet &s = h->cur();
+    double *own = rescue_base(h) + (size_t)h->rank * h->slot_cap * h->rstride;
+    const int64_t n = h->slot_cap * h->rstride;
+    HMMB_LAUNCH("bw_rescue", k_bw_rescue_init, (unsigned)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, own, n);
+#define RESCUE(SYMT, BLK, BASE)                                                                                       \
+    HMMB_LAUNCH("bw_rescue", (k_bw_rescue<SYMT, BLK>), h->exact_grid, BW_THREADS, 0, s.d_obs, BASE, s.d_len, s.d_word, s.R, \
+                h->N, h->M, h->d_pi, h->d_A, h->d_Bt, h->act_cur, h->d_exact_scratch, h->exact_stride, h->d_thinmask, \
+                h->d_slot_of, own, h->rstride, s.symmask())
+    if (s.blocked()) {
+        RESCUE(uint16_t, true, s.d_foff);
+    } else if (s.sym_bytes == 1) {
+        RESCUE(uint8_t, false, s.d_off);
+    } else {
+        RESCUE(uint16_t, false, s.d_off);
+    }
+#undef RESCUE
+    return HMMB_OK;
+}
+
+// Called after a stream synchronisation with the number of states the M-step has newly flagged: gives every flagged
+// state a slot — numbered by (word, state), the same on every rank because the flags derive from the all-reduced
+// sums — and grows the slot region behind the accumulators if needed.
+static int bw_assign_slots(hmmb_bw *h) {
+    Ctx &c = ctx();
+    const int W = h->W, N = h->N;
+    std::vector<uint32_t> mask((size_t)W);
+    HMMB_CUDA(cudaMemcpy(mask.data(), h->d_thinmask, (size_t)W * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> slot_of((size_t)W * N, -1);
+    int n = 0;
+    for (int w = 0; w < W; ++w)
+        for (int i = 0; i < N; ++i)
+            if ((mask[w] >> i) & 1u) slot_of[(size_t)w * N + i] = n++;
+    h->n_slots = n;
+    h->n_thin_total = n;
+    if (n > h->slot_cap) {
+        h->slot_cap = ((int64_t)n + 15) & ~int64_t(15);
+        HMMB_CUDA(cudaStreamSynchronize(c.stream));
+        HMMB_TRY(bw_alloc_accum(h));
+    }
+    HMMB_CUDA(cudaMemcpy(h->d_slot_of, slot_of.data(), slot_of.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    HMMB_CUDA(cudaMemsetAsync(h->d_thin_new, 0, sizeof(int32_t), c.stream));
+    return HMMB_OK;
+}
+
+// E-step (+ rescue pass) + reduce + all-reduce + M-step over the words of `mask`
+static int bw_one_pass(hmmb_bw *h, int32_t *mask, double eps, int max_iter, int sync_each, int skip_new_thin) {
+    Ctx &c = ctx();
+    h->act_cur = mask;
+    struct Restore { hmmb_bw *h; ~Restore() { h->act_cur = h->d_active; } } restore{h};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        HMMB_CUDA(cudaMemsetAsync(h->d_accum, 0, (size_t)h->accum_n * sizeof(double), c.stream));
+        h->estep_reduced = false;
+        HMMB_TRY(bw_estep(h));
+        // (an E-step that already ran its collectives cannot be redone by one rank alone: backward-pass
+        // hand-overs then only take effect from the next iteration, as with sync_each == 0)
+        if (!sync_each || h->estep_reduced) break;
+        // backward-pass hand-overs are discovered after their sequence already contributed:
+        // redo this E-step once with them routed to the exact kernel (flags are sticky)
+        int32_t nf = 0;
+        HMMB_CUDA(cudaMemcpyAsync(&nf, h->d_newflags, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        HMMB_CUDA(cudaStreamSynchronize(c.stream));
+        HMMB_TRY(bw_after_sync(h));
+        if (nf == 0) break;
+        h->n_backward_handover += nf;
+        HMMB_CUDA(cudaMemsetAsync(h->d_newflags, 0, sizeof(int32_t), c.stream));
+    }
+    HMMB_TRY(launch_rescue(h));
+    if (!h->estep_reduced) {
+        const dim3 rgrid((unsigned)h->W, h->s.special4 ? (unsigned)((h->nacc + RED_EX - 1) / RED_EX) : 1u);
+        HMMB_LAUNCH("bw_reduce", k_bw_reduce, rgrid, RED_THREADS, 0, h->s.special4 ? h->d_partials : nullptr, h->pstride,
+                    h->d_cta_begin, h->d_llseq, h->d_seq_begin, h->d_accum, h->astride, h->nacc,
+                    h->d_accum + (size_t)h->W * h->astride, h->rank, h->W, mask);
+        if (h->allreduce && h->world > 1) {
+            static int pid_ar = -1;
+            if (pid_ar < 0) pid_ar = phase_id("bw_allreduce");
+            if (c.profiling) phase_begin(pid_ar);  // CUDA events around the collective on the launching stream
+            int rc = h->allreduce(h->d_accum, h->accum_n, h->user);
+            if (c.profiling) phase_end(pid_ar);
+            if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+        }
+    } else if (h->n_slots > 0 && h->allreduce && h->world > 1) {
+        // (the overlapping E-step has reduced the word slices and the statistics itself: the slot region is left)
+        int rc = h->allreduce(rescue_base(h), (int64_t)h->world * h->slot_cap * h->rstride, h->user);
+        if (rc == 0) rc = h->allreduce(nullptr, 0, h->user);
+        if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+    }
+    HMMB_CUDA(cudaMemsetAsync(h->d_redo, 0, (size_t)h->W * sizeof(int32_t), c.stream));
+    HMMB_LAUNCH("bw_mstep", k_bw_mstep, h->W, RED_THREADS, 0, h->d_accum, h->astride,
+                h->d_accum + (size_t)h->W * h->astride, h->world, h->W, h->N, h->M, h->d_pi, h->d_A, h->d_Bt,
+                mask, h->d_active, h->d_iters, h->d_prev, h->d_hist, h->hist_cap, eps, max_iter, h->d_any, h->d_bzero,
+                h->d_thinmask, h->d_thin_new, h->d_redo, skip_new_thin, h->d_slot_of, rescue_base(h), h->slot_cap, h->rstride,
+                getenv("HMMB_NO_THIN_RESCUE") ? 0.0 : THIN_LIMIT);
+    return HMMB_OK;
+}
+
 int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync_each) {
     HMMB_TRY(require_init());
     if (!h || !h->params_set) { set_error("hmmb_bw_iterate: parameters not set"); return HMMB_ERR_ARG; }
@@ -1550,55 +1676,44 @@ int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync
     HMMB_TRY(bw_ensure_hist(h, std::min(std::max(max_iter, 1), 1 << 16)));  // history keeps at most 65536 iterations
     for (int it = 0; it < n_iter; ++it) {
         if (!h->any_active) break;
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            HMMB_CUDA(cudaMemsetAsync(h->d_accum, 0, (size_t)h->accum_n * sizeof(double), c.stream));
-            h->estep_reduced = false;
-            HMMB_TRY(bw_estep(h));
-            // (an E-step that already ran its collectives cannot be redone by one rank alone: backward-pass
-            // hand-overs then only take effect from the next iteration, as with sync_each == 0)
-            if (!sync_each || h->estep_reduced) break;
-            // backward-pass hand-overs are discovered after their sequence already contributed:
-            // redo this E-step once with them routed to the exact kernel (flags are sticky)
-            int32_t nf = 0;
-            HMMB_CUDA(cudaMemcpyAsync(&nf, h->d_newflags, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        HMMB_CUDA(cudaMemsetAsync(h->d_any, 0, sizeof(int32_t), c.stream));
+        // with sync_each a word whose M-step finds a newly thin state is held back (its parameters, iteration count
+        // and history untouched) and the iteration is repeated for those words with the state's slot in place
+        HMMB_TRY(bw_one_pass(h, h->d_active, eps, max_iter, sync_each, sync_each ? 1 : 0));
+        if (sync_each) {
+            int32_t any = 0, nt = 0;
+            HMMB_CUDA(cudaMemcpyAsync(&any, h->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+            HMMB_CUDA(cudaMemcpyAsync(&nt, h->d_thin_new, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
             HMMB_CUDA(cudaStreamSynchronize(c.stream));
             HMMB_TRY(bw_after_sync(h));
-            if (nf == 0) break;
-            h->n_backward_handover += nf;
-            HMMB_CUDA(cudaMemsetAsync(h->d_newflags, 0, sizeof(int32_t), c.stream));
-        }
-        if (!h->estep_reduced) {
-            const dim3 rgrid((unsigned)h->W, h->s.special4 ? (unsigned)((h->nacc + RED_EX - 1) / RED_EX) : 1u);
-            HMMB_LAUNCH("bw_reduce", k_bw_reduce, rgrid, RED_THREADS, 0, h->s.special4 ? h->d_partials : nullptr, h->pstride,
-                        h->d_cta_begin, h->d_llseq, h->d_seq_begin, h->d_accum, h->astride, h->nacc,
-                        h->d_accum + (size_t)h->W * h->astride, h->rank, h->W, h->d_active);
-            if (h->allreduce && h->world > 1) {
-                static int pid_ar = -1;
-                if (pid_ar < 0) pid_ar = phase_id("bw_allreduce");
-                if (c.profiling) phase_begin(pid_ar);  // CUDA events around the collective on the launching stream
-                int rc = h->allreduce(h->d_accum, h->accum_n, h->user);
-                if (c.profiling) phase_end(pid_ar);
-                if (rc != 0) { set_error("allreduce hook failed (%d)", rc); return HMMB_ERR_CUDA; }
+            if (nt > 0) {
+                HMMB_TRY(bw_assign_slots(h));
+                HMMB_CUDA(cudaMemcpyAsync(h->d_redo_in, h->d_redo, (size_t)h->W * sizeof(int32_t), cudaMemcpyDeviceToDevice, c.stream));
+                HMMB_TRY(bw_one_pass(h, h->d_redo_in, eps, max_iter, sync_each, 0));
+                HMMB_CUDA(cudaMemcpyAsync(&any, h->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+                HMMB_CUDA(cudaStreamSynchronize(c.stream));
+                HMMB_TRY(bw_after_sync(h));
             }
-        }
-        HMMB_CUDA(cudaMemsetAsync(h->d_any, 0, sizeof(int32_t), c.stream));
-        HMMB_LAUNCH("bw_mstep", k_bw_mstep, h->W, RED_THREADS, 0, h->d_accum, h->astride,
-                    h->d_accum + (size_t)h->W * h->astride, h->world, h->W, h->N, h->M, h->d_pi, h->d_A, h->d_Bt,
-                    h->d_active, h->d_iters, h->d_prev, h->d_hist, h->hist_cap, eps, max_iter, h->d_any, h->d_bzero);
-        if (sync_each) {
-            int32_t any = 0;
-            HMMB_CUDA(cudaMemcpyAsync(&any, h->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
-            HMMB_CUDA(cudaStreamSynchronize(c.stream));
             h->any_active = any != 0;
         }
     }
     if (!sync_each && n_iter > 0) {
-        int32_t any = 0;
+        int32_t any = 0, nt = 0;
         HMMB_CUDA(cudaMemcpyAsync(&any, h->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+        HMMB_CUDA(cudaMemcpyAsync(&nt, h->d_thin_new, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
         HMMB_CUDA(cudaStreamSynchronize(c.stream));
         HMMB_TRY(bw_after_sync(h));
         h->any_active = any != 0;
+        // states flagged while the iterations were queued: their slots exist from the next call on
+        if (nt > 0) HMMB_TRY(bw_assign_slots(h));
     }
+    return HMMB_OK;
+}
+
+int hmmb_bw_thin_states(hmmb_bw_t *h, int64_t *n_states) {
+    HMMB_TRY(require_init());
+    if (!h || !n_states) { set_error("hmmb_bw_thin_states: null argument"); return HMMB_ERR_ARG; }
+    *n_states = h->n_thin_total;
     return HMMB_OK;
 }
 

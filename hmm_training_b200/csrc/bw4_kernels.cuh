@@ -763,6 +763,12 @@ __device__ __noinline__ void bwd4_step_slow(Bwd4State<BIDIAG> &st, const double 
         const double qs = (q[0] + q[1]) + (q[2] + q[3]);
         const double sc = qs > 0.0 ? pow2_rescale_noacc(qs) : 1.0;
         h0 = q[0] * sc; h1 = q[1] * sc; h2 = q[2] * sc; h3 = q[3] * sc;
+        // (sum q can reach N * 2, i.e. sc < 1: a denormal marker must not be flushed by the rescale — beta_t(i) is
+        // finite in the reference, and gamma_t(i) / v_i below only stay positive if h_i does)
+        if (h0 == 0.0 && q[0] > 0.0) h0 = tiny_pos();
+        if (h1 == 0.0 && q[1] > 0.0) h1 = tiny_pos();
+        if (h2 == 0.0 && q[2] > 0.0) h2 = tiny_pos();
+        if (h3 == 0.0 && q[3] > 0.0) h3 = tiny_pos();
         w0 = v0 * sc; w1 = v1 * sc; w2 = v2 * sc; w3 = v3 * sc;
     }
     // gamma_t(i) = alpha_t(i) beta_t(i) / sum_i alpha_t(i) beta_t(i)   (:389-394)
@@ -1086,7 +1092,9 @@ k_bw_bwd4(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                         const double vs = (st.v0 + st.v1) + (st.v2 + st.v3);                                        \
                         if ((unsigned)__double2hiint(vs) < LEAN_MIN_HI) { /* tiny emission column: careful v */     \
                             double vv[4];                                                                           \
-                            if (bwd4_v_slow(h0, h1, h2, h3, b01.x, b01.y, b23.x, b23.y, vv)) st.imprecise = true;   \
+                            /* (q > 0 on this path: a beta-hat the rescale flushed is still a finite log value) */ \
+                            if (bwd4_v_slow(zero_to_tiny(h0), zero_to_tiny(h1), zero_to_tiny(h2), zero_to_tiny(h3), b01.x, b01.y,       \
+                                            b23.x, b23.y, vv)) st.imprecise = true;   \
                             st.v0 = vv[0]; st.v1 = vv[1]; st.v2 = vv[2]; st.v3 = vv[3];                             \
                             st.vpos = all_pos4(vv[0], vv[1], vv[2], vv[3]);                                         \
                         }                                                                                           \

@@ -157,6 +157,7 @@ k_bw_bwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
             if (act) {
                 if (!last && qs > 0.0) sc = pow2_rescale_noacc(qs);
                 h = q * sc;  // beta-hat_t(i), group sum in [1,2)
+                if (h == 0.0 && q > 0.0) h = tiny_pos();  // (sc < 1 must not flush a denormal marker: bw4_kernels.cuh)
                 al = al_c;
                 g = al * h;
             }
@@ -295,6 +296,54 @@ k_bw_exact(const void *__restrict__ obs, const int64_t *__restrict__ base_sorted
 // per-sequence log-likelihoods, the two halves of log_sum_exp (:503), into
 // llstats[rank][w][2].
 constexpr int RED_THREADS = 256;
+// ---------------------------------------------------------------- thin-state rescue (hmm_device.cuh)
+// own-rank slot region -> -inf ("no finite term yet"); the other ranks' regions keep the zeros of the accumulator memset
+__global__ void k_bw_rescue_init(double *__restrict__ slots, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        slots[e] = neg_inf();
+}
+// One warp per sequence of a word that has flagged states: the reference's log-space forward / backward pass, rows of
+// the flagged states accumulated in log space.  Same argument conventions as k_bw_exact; every sequence of the word
+// takes part (also those the fast kernels or the exact kernel have just handled: the slots replace their rows).
+template <typename SymT, bool BLOCKED>
+__global__ void __launch_bounds__(BW_THREADS)
+k_bw_rescue(const void *__restrict__ obs, const int64_t *__restrict__ base_sorted, const int32_t *__restrict__ len_sorted,
+            const int32_t *__restrict__ word_sorted, int64_t R, int N, int M, const double *__restrict__ pi,
+            const double *__restrict__ A, const double *__restrict__ Bt, const int32_t *__restrict__ active,
+            double *__restrict__ scratch, int64_t scratch_stride, const uint32_t *__restrict__ thinmask,
+            const int32_t *__restrict__ slot_of, double *__restrict__ slots, int64_t rstride, unsigned symmask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * BW_WARPS + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * BW_WARPS;
+    double *sc = scratch + gw * scratch_stride;
+    for (int64_t base = gw * 32; base < R; base += nw * 32) {
+        const int64_t r = base + lane;
+        const bool f = r < R && active[word_sorted[r]] && thinmask[word_sorted[r]] != 0u;
+        unsigned m = __ballot_sync(0xffffffffu, f);
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const int64_t rr = base + l;
+            const int w = word_sorted[rr], T = len_sorted[rr];
+            const double *piw = pi + (size_t)w * N, *Aw = A + (size_t)w * N * N, *Btw = Bt + (size_t)w * M * N;
+            if (BLOCKED) {
+                BlkObs<SymT> o{reinterpret_cast<const uint4 *>(obs) + base_sorted[rr], symmask};
+                const double logP = exact_forward(T, N, lane, o, piw, Aw, Btw, sc);
+                __syncwarp();
+                if (logP > neg_inf())
+                    exact_backward_rescue(T, N, M, lane, o, Aw, Btw, sc, logP, thinmask[w], slot_of + (size_t)w * N, slots, rstride);
+            } else {
+                LinObs<SymT> o{reinterpret_cast<const SymT *>(obs) + base_sorted[rr]};
+                const double logP = exact_forward(T, N, lane, o, piw, Aw, Btw, sc);
+                __syncwarp();
+                if (logP > neg_inf())
+                    exact_backward_rescue(T, N, M, lane, o, Aw, Btw, sc, logP, thinmask[w], slot_of + (size_t)w * N, slots, rstride);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 constexpr int RED_EX = 32;  // accumulator entries per CTA of k_bw_reduce
 constexpr int RED_CY = RED_THREADS / RED_EX;
 
@@ -365,13 +414,17 @@ k_bw_reduce(const double *__restrict__ partials, int64_t pstride, const int32_t 
 __global__ void __launch_bounds__(RED_THREADS)
 k_bw_mstep(const double *__restrict__ accum, int64_t astride, const double *__restrict__ llstats, int world, int W,
            int N, int M, double *__restrict__ pi, double *__restrict__ A, double *__restrict__ Bt,
-           int32_t *__restrict__ active, int32_t *__restrict__ iters, double *__restrict__ prev_ll,
-           double *__restrict__ ll_hist, int hist_cap, double eps, int max_iter, int32_t *__restrict__ any_active,
-           int32_t *__restrict__ b_has_zero) {
+           const int32_t *__restrict__ active_in, int32_t *__restrict__ active, int32_t *__restrict__ iters,
+           double *__restrict__ prev_ll, double *__restrict__ ll_hist, int hist_cap, double eps, int max_iter,
+           int32_t *__restrict__ any_active, int32_t *__restrict__ b_has_zero, uint32_t *__restrict__ thinmask,
+           int32_t *__restrict__ thin_new, int32_t *__restrict__ redo, int skip_new_thin,
+           const int32_t *__restrict__ slot_of, const double *__restrict__ slots, int64_t slot_cap, int64_t rstride,
+           double thin_limit) {
     __shared__ double sDen[HMMB_MAX_STATES];
     __shared__ double sPart[RED_THREADS / 32][HMMB_MAX_STATES];
+    __shared__ int sSkip;
     const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (!active[w]) return;
+    if (!active_in[w]) return;
     const double *acc = accum + (size_t)w * astride;
     const double *xi = acc + N;
     const double *cnt = acc + N + N * N;
@@ -407,6 +460,31 @@ k_bw_mstep(const double *__restrict__ accum, int64_t astride, const double *__re
         }
     }
     __syncthreads();
+    // Thin states (hmm_device.cuh, "thin-state rescue"): a positive denominator below THIN_LIMIT means the row's sums sit
+    // where the linear accumulators run out of range.  The state is flagged (sticky); with skip_new_thin the word leaves
+    // this iteration untouched and is marked in `redo`, so that the host can give the state a slot and repeat the
+    // iteration for the marked words — otherwise the flag takes effect from the next iteration on.
+    __shared__ unsigned sThinBits;
+    if (tid == 0) sThinBits = 0u;
+    __syncthreads();
+    if (tid < N) {
+        double denA = 0.0;
+        for (int j = 0; j < N; ++j) denA += xi[tid * N + j];
+        if ((denA > 0.0 && denA < thin_limit) || (sDen[tid] > 0.0 && sDen[tid] < thin_limit)) atomicOr(&sThinBits, 1u << tid);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned have = thinmask[w];
+        const unsigned fresh = sThinBits & ~have;
+        if (fresh) {
+            thinmask[w] = have | fresh;
+            atomicAdd(thin_new, __popc(fresh));
+        }
+        sSkip = (fresh && skip_new_thin) ? 1 : 0;
+        if (redo) redo[w] = sSkip;
+    }
+    __syncthreads();
+    if (sSkip) return;
     // B (:474-497): no finite term -> 1e-20 floor; empty denominator -> row stays -inf (0)
     for (int e = tid; e < M * N; e += RED_THREADS) {
         const int j = e % N;
@@ -445,6 +523,80 @@ k_bw_mstep(const double *__restrict__ accum, int64_t astride, const double *__re
             if (pv == 0.0) pv = tiny_pos();
         }
         pi[(size_t)w * N + i] = pv;
+    }
+    // Flagged states with a slot: rows of A and B from the log-space sums (the ranks' slots combined by log_sum_exp in
+    // rank order), as the reference forms them (:429-457, :460-497)
+    {
+        const unsigned tm = thinmask[w];
+        if (tm != 0u && slot_cap > 0) {
+            __syncthreads();  // the plain rows above are written
+            for (int i = 0; i < N; ++i) {
+                if (!((tm >> i) & 1u)) continue;
+                const int sl = slot_of[(size_t)w * N + i];
+                if (sl < 0) continue;
+                auto entry = [&](int e) {  // log sum over ranks of entry e of the state's slot
+                    double mx = neg_inf();
+                    for (int r = 0; r < world; ++r) mx = fmax(mx, slots[((size_t)r * slot_cap + sl) * rstride + e]);
+                    if (!(mx > neg_inf())) return neg_inf();
+                    double sm = 0.0;
+                    for (int r = 0; r < world; ++r) {
+                        const double v = slots[((size_t)r * slot_cap + sl) * rstride + e];
+                        if (v > neg_inf()) sm += exp(v - mx);
+                    }
+                    return mx + log(sm);
+                };
+                // block-wide log_sum_exp of entries [e0, e0 + n)
+                auto block_lse = [&](int e0, int n) {
+                    double mx = neg_inf();
+                    for (int e = tid; e < n; e += RED_THREADS) mx = fmax(mx, entry(e0 + e));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    if (lane == 0) sPart[warp][0] = mx;
+                    __syncthreads();
+                    mx = sPart[0][0];
+                    for (int q = 1; q < RED_THREADS / 32; ++q) mx = fmax(mx, sPart[q][0]);
+                    __syncthreads();
+                    double sm = 0.0;
+                    if (mx > neg_inf())
+                        for (int e = tid; e < n; e += RED_THREADS) {
+                            const double v = entry(e0 + e);
+                            if (v > neg_inf()) sm += exp(v - mx);
+                        }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                    if (lane == 0) sPart[warp][0] = sm;
+                    __syncthreads();
+                    double tot = 0.0;
+                    for (int q = 0; q < RED_THREADS / 32; ++q) tot += sPart[q][0];
+                    __syncthreads();
+                    return (mx > neg_inf()) ? mx + log(tot) : neg_inf();
+                };
+                const double denA = block_lse(0, N), denB = block_lse(N, M);
+                if (tid < N) {
+                    const double x = entry(tid);
+                    double v = 0.0;
+                    if (denA > neg_inf() && x > neg_inf()) {
+                        v = exp(x - denA);
+                        if (v == 0.0) v = tiny_pos();
+                    }
+                    A[((size_t)w * N + i) * N + tid] = v;
+                }
+                for (int k = tid; k < M; k += RED_THREADS) {
+                    const double c = entry(N + k);
+                    double b = 0.0;
+                    if (denB > neg_inf()) {
+                        if (c > neg_inf()) {
+                            b = exp(c - denB);
+                            if (b == 0.0) b = tiny_pos();
+                        } else {
+                            b = 1e-20;
+                        }
+                    }
+                    Bt[(size_t)w * M * N + (size_t)k * N + i] = b;
+                }
+            }
+            __syncthreads();
+        }
     }
     if (tid == 0) {
         // a state that was never visited keeps an all-zero (log: -inf) emission row (:471)

@@ -455,7 +455,11 @@ __device__ __noinline__ void bwdL_step_slow(BwdLState<NS> &st, const double *__r
             qs += x;
         }
         const double sc = qs > 0.0 ? pow2_rescale_noacc(qs) : 1.0;
-        for (int i = 0; i < NS; ++i) { h[i] = q[i] * sc; w[i] = st.v[i] * sc; }
+        for (int i = 0; i < NS; ++i) {
+            h[i] = q[i] * sc;
+            if (h[i] == 0.0 && q[i] > 0.0) h[i] = tiny_pos();  // (sc < 1 must not flush a denormal marker: bw4_kernels.cuh)
+            w[i] = st.v[i] * sc;
+        }
     }
     // gamma_t(i) = alpha_t(i) beta_t(i) / sum_i alpha_t(i) beta_t(i)   (:389-394)
     double u[NS], norm = 0.0;

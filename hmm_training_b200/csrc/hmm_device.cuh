@@ -420,4 +420,77 @@ __device__ __noinline__ void exact_backward_accumulate(int T, int N, int lane, c
     }
 }
 
+// ================================================================ thin-state rescue (log-space accumulators)
+// The linear-domain accumulators hold POSTERIORS (gamma, xi in [0, 1]); a state whose whole posterior mass over the
+// training set — over the steps that count for a row: t < T - 1 for A (HMM/hmm_training.py:429-457) — is below
+// ~1e-308 has no representable sums, while the reference, which keeps log sums, still forms the RATIOS that become
+// its A / B row (found by the property tests: a 16-state model on a 15-frame sequence, whose state 13 is only
+// entered before the last step with posterior 1e-340, keeps a_13,13 = 0.394 in the reference).  Rows whose linear
+// denominator falls below THIN_LIMIT are therefore re-accumulated in LOG space: the M-step flags the state (sticky),
+// and from then on k_bw_rescue runs the reference's log-space recursions over the word's sequences and keeps, per
+// flagged state i, log sum_t xi_t(i, j) and log sum_{t: o_t = k} gamma_t(i) in a slot of its own rank behind the
+// accumulators (slots of other ranks stay 0, so the sum-all-reduce gathers them); the M-step combines the ranks'
+// slots with log_sum_exp and overrides row i of A and B from them.
+constexpr double THIN_LIMIT = 0x1p-200;
+
+// *addr = log(exp(*addr) + exp(x)) atomically (x finite; *addr may be -inf)
+__device__ __forceinline__ void atomic_lse(double *addr, double x) {
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        const double cur = __longlong_as_double((long long)assumed);
+        double nv;
+        if (!(cur > neg_inf())) nv = x;
+        else nv = fmax(cur, x) + log1p(exp(-fabs(cur - x)));
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(nv));
+    } while (old != assumed);
+}
+
+// Backward pass in log space for ONE sequence (one warp, lane = state; scratch holds log alpha from exact_forward),
+// adding only the rows of the states in `mask` to their slots: slot_of[i] >= 0 indexes [N log-xi | M log-gamma]
+// rows of `rstride` doubles at `slots` (this rank's region).
+template <typename ObsT>
+__device__ __noinline__ void exact_backward_rescue(int T, int N, int M, int lane, const ObsT obs,
+                                                   const double *__restrict__ Aw, const double *__restrict__ Btw,
+                                                   const double *__restrict__ scratch, double logP, unsigned mask,
+                                                   const int32_t *__restrict__ slot_of, double *__restrict__ slots,
+                                                   int64_t rstride) {
+    const int i = lane;
+    const bool st = i < N;
+    const bool mine = st && ((mask >> i) & 1u) && slot_of[i] >= 0;
+    double *row = mine ? slots + (size_t)slot_of[i] * rstride : nullptr;
+    double lbeta = st ? 0.0 : neg_inf();  // log beta_{T-1} = 0
+    for (int t = T - 1; t >= 0; --t) {
+        const unsigned sym = obs[t];
+        const double la = st ? scratch[(size_t)t * N + i] : neg_inf();
+        if (t < T - 1) {
+            const unsigned sym1 = obs[t + 1];
+            const double lbj = st ? safe_log_d(__ldg(Btw + (size_t)sym1 * N + i)) : neg_inf();
+            const double term = (lbj > neg_inf() && lbeta > neg_inf()) ? lbj + lbeta : neg_inf();
+            double m = neg_inf();
+            for (int j = 0; j < N; ++j) {
+                const double tj = __shfl_sync(0xffffffffu, term, j);
+                const double laij = st ? safe_log_d(__ldg(Aw + (size_t)i * N + j)) : neg_inf();
+                const double x = (tj > neg_inf() && laij > neg_inf()) ? laij + tj : neg_inf();
+                m = fmax(m, x);
+                // log xi_t(i,j) = log alpha_t(i) + log a_ij + log b_j(o_{t+1}) + log beta_{t+1}(j) - log P   (:397-410)
+                if (mine && x > neg_inf() && la > neg_inf()) atomic_lse(row + j, la + x - logP);
+            }
+            double s = 0.0;
+            for (int j = 0; j < N; ++j) {
+                const double tj = __shfl_sync(0xffffffffu, term, j);
+                const double laij = st ? safe_log_d(__ldg(Aw + (size_t)i * N + j)) : neg_inf();
+                const double x = (tj > neg_inf() && laij > neg_inf()) ? laij + tj : neg_inf();
+                if (x > neg_inf()) s += exp(x - m);
+            }
+            lbeta = (m > neg_inf()) ? m + log(s) : neg_inf();
+            if (!st) lbeta = neg_inf();
+        }
+        // log gamma_t(i) (:389-394), by codeword
+        if (mine && la > neg_inf() && lbeta > neg_inf()) atomic_lse(row + N + sym, la + lbeta - logP);
+    }
+    (void)M;
+}
+
 }  // namespace hmmb

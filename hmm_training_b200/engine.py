@@ -228,6 +228,12 @@ class BaumWelch:
         check(self._lib.hmmb_bw_diagnostics(self._h, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
+    def thin_states(self) -> int:
+        """(word, state) pairs whose A / B rows come from log-space sums (posterior mass below 2^-200)."""
+        n = ctypes.c_int64(0)
+        check(self._lib.hmmb_bw_thin_states(self._h, ctypes.byref(n)))
+        return n.value
+
     def seq_ll(self) -> np.ndarray:
         out = np.empty(max(self.R, 1))
         check(self._lib.hmmb_bw_get_seq_ll(self._h, ptr(out)))

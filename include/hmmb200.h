@@ -182,6 +182,11 @@ const char *hmmb_bw_kernel_family(hmmb_bw_t *h);
  * redo when hmmb_bw_iterate runs with sync_each != 0; with sync_each == 0 they are only
  * counted and take effect from the next iteration).                                        */
 int hmmb_bw_diagnostics(hmmb_bw_t *h, int64_t *exact_sequence_passes, int64_t *backward_handovers);
+/* Number of (word, state) pairs whose A / B rows are currently formed from log-space sums because their posterior
+ * mass fell below 2^-200 ("thin states": the linear accumulators cannot hold sums below ~1e-308, the reference's
+ * log sums can — HMM/hmm_training.py:429-497).  With sync_each the iteration that finds such a state is repeated
+ * for its word; without, the state is rescued from the next hmmb_bw_iterate call on.                             */
+int hmmb_bw_thin_states(hmmb_bw_t *h, int64_t *n_states);
 
 /* one-shot convenience: create + set_params + iterate + get + destroy (host buffers)      */
 int hmmb_bw_fit(const void *obs, int idx_bytes, const int64_t *offsets, const int32_t *word_of_seq,

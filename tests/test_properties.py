@@ -21,6 +21,17 @@ from hypothesis import strategies as st
 from helpers import assert_close, assert_same_support
 from oracle import hmm_oracle as O
 
+# The committed runs are derandomised (the same examples every time: a round-end run must not depend on luck);
+# HMMB_HYP_RANDOM=1 explores fresh examples, HMMB_HYP_EXAMPLES=n sets how many.
+import os
+
+_RANDOM = bool(os.environ.get("HMMB_HYP_RANDOM"))
+_SCALE = int(os.environ.get("HMMB_HYP_EXAMPLES", "0"))
+
+
+def _settings(n):
+    return settings(max_examples=_SCALE or n, deadline=None, derandomize=not _RANDOM, suppress_health_check=list(HealthCheck))
+
 
 def _random_model(rng, W, N, M, left_to_right, zero_frac):
     pi = rng.random((W, N)) + 0.05
@@ -73,7 +84,7 @@ shape = st.tuples(st.sampled_from([2, 3, 4, 5, 8, 16]), st.integers(3, 40), st.i
                   st.booleans(), st.sampled_from([0.0, 0.3]), st.integers(0, 2 ** 31 - 1))
 
 
-@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@_settings(25)
 @given(shape)
 def test_oracle_reestimation_invariants(p):
     N, M, W, S, ltr, zf, seed = p
@@ -98,7 +109,7 @@ gpu_shape = st.tuples(st.sampled_from([2, 3, 4, 4, 6, 8, 16]), st.sampled_from([
 
 
 @pytest.mark.gpu
-@settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+@_settings(20)
 @given(gpu_shape)
 def test_gpu_reestimation_invariants_and_oracle(p):
     from hmm_training_b200 import engine
@@ -115,13 +126,15 @@ def test_gpu_reestimation_invariants_and_oracle(p):
                                             return_history=True)
         assert_close(A[w], Ao, "A"); assert_close(B[w], Bo, "B"); assert_close(pi[w], pio, "pi")
         assert_same_support(A[w], Ao, "A"); assert_same_support(pi[w], pio, "pi")
-        assert_close(hist[w, :4], np.array(ho), "statistic")
+        # (a log-likelihood that is 0 up to rounding — P(O) = 1 after re-estimation on one short sequence — has no
+        # meaningful relative error: absolute 1e-12 beside the relative 1e-9)
+        assert_close(hist[w, :4], np.array(ho), "statistic", atol=1e-12)
     # permutation of the sequences
     perm = rng.permutation(len(seqs))
     obs2, off2 = _pack([seqs[r] for r in perm])
     pi2, A2, B2, hist2, _ = engine.bw_fit(obs2, off2, wos[perm], W, N, M, pi0, A0, B0, epsilon=-1.0, max_iterations=4)
     assert_close(A2, A, "A under permutation", rtol=1e-12); assert_close(B2, B, "B under permutation", rtol=1e-12)
-    assert_close(pi2, pi, "pi under permutation", rtol=1e-12); assert_close(hist2, hist, "statistic under permutation", rtol=1e-12)
+    assert_close(pi2, pi, "pi under permutation", rtol=1e-12); assert_close(hist2, hist, "statistic under permutation", rtol=1e-12, atol=1e-12)
 
 
 def _one_iteration(engine, seqs, wos, W, N, M, init, rank=0, world=1, hook=None):
@@ -170,7 +183,7 @@ def test_virtual_ranks_on_one_device_equal_single_rank(N, M, G):
 
     got = _one_iteration(engine, [seqs[i] for i in shards[0]], wos[shards[0]], W, N, M, init, 0, G, inject)
     for x, y, name in zip(got, want, ("pi", "A", "B", "statistic", "iterations")):
-        assert_close(x, y, f"{G} virtual ranks: {name}", rtol=1e-12)
+        assert_close(x, y, f"{G} virtual ranks: {name}", rtol=1e-12, atol=1e-13)
 
 
 # ---------------------------------------------------------------- VQ encode and recognition
@@ -179,7 +192,7 @@ vq_shape = st.tuples(st.integers(1, 700), st.sampled_from([1, 2, 7, 31, 32, 33, 
 
 
 @pytest.mark.gpu
-@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@_settings(25)
 @given(vq_shape)
 def test_gpu_vq_encode_properties(p):
     """get_observations (HMM/hmm_training.py:95-118) for drawn frame / codebook shapes: bit-exact against the C oracle
@@ -211,7 +224,7 @@ score_shape = st.tuples(st.sampled_from([2, 4, 4, 5, 8, 16]), st.sampled_from([4
 
 
 @pytest.mark.gpu
-@settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+@_settings(20)
 @given(score_shape)
 def test_gpu_scoring_properties(p):
     """calculate_log_likelihood / test_hmm (HMM/hmm_testing.py:49-104, 139-161): the [U, W] matrix equals the oracle's,
@@ -229,7 +242,7 @@ def test_gpu_scoring_properties(p):
     obs, off = _pack(seqs)
     ll, best = engine.score(obs, off, N, M, pi, A, B)
     ref = O.score_batch(seqs, [(A[w], B[w], pi[w]) for w in range(W)])
-    assert_close(ll, ref, "log-likelihood matrix")
+    assert_close(ll, ref, "log-likelihood matrix", atol=1e-12)
     assert np.array_equal(best, O.argmax_first(ref))
     perm = rng.permutation(U)
     obs2, off2 = _pack([seqs[u] for u in perm])
@@ -239,4 +252,4 @@ def test_gpu_scoring_properties(p):
     w = int(rng.integers(0, W))
     _, _, _, hist, _ = engine.bw_fit(obs, off, np.zeros(U, dtype=np.int32), 1, N, M, pi[w:w + 1], A[w:w + 1], B[w:w + 1],
                                      epsilon=-1.0, max_iterations=1)
-    assert_close(hist[0, 0], O.log_sum_exp(ref[:, w]), "E-step statistic vs scorer")
+    assert_close(hist[0, 0], O.log_sum_exp(ref[:, w]), "E-step statistic vs scorer", atol=1e-12)

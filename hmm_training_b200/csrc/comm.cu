@@ -28,6 +28,7 @@ struct NcclApi {
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
+    int (*CommGetAsyncError)(ncclComm_t, int *) = nullptr;  // optional
 };
 
 NcclApi g_nccl;
@@ -52,6 +53,7 @@ int nccl_load() {
     a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
     a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    a.CommGetAsyncError = reinterpret_cast<decltype(a.CommGetAsyncError)>(dlsym(h, "ncclCommGetAsyncError"));
     if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy || !a.GetErrorString) {
         set_error("hmmb_comm: libnccl lacks an expected symbol");
         dlclose(h);
@@ -111,6 +113,14 @@ extern "C" int hmmb_comm_allreduce(void *dev_buf, int64_t n_doubles, void *user)
     if (!dev_buf || n_doubles <= 0) return HMMB_OK;
     const int rc = g_nccl.AllReduce(dev_buf, dev_buf, (size_t)n_doubles, NCCL_FLOAT64, NCCL_SUM, g_comm, ctx().stream);
     if (rc != 0) return nccl_fail(rc, "ncclAllReduce");
+    // failure detection: an asynchronous error of the communicator — a peer that died, a
+    // transport fault — surfaces here, at the next collective, instead of as a hang at the next synchronisation
+    if (g_nccl.CommGetAsyncError) {
+        int async_rc = 0;
+        const int q = g_nccl.CommGetAsyncError(g_comm, &async_rc);
+        if (q != 0) return nccl_fail(q, "ncclCommGetAsyncError");
+        if (async_rc != 0) return nccl_fail(async_rc, "ncclAllReduce (asynchronous error of the communicator)");
+    }
     return HMMB_OK;
 }
 

@@ -1686,11 +1686,14 @@ int hmmb_bw_iterate(hmmb_bw_t *h, int n_iter, double eps, int max_iter, int sync
             HMMB_CUDA(cudaMemcpyAsync(&nt, h->d_thin_new, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
             HMMB_CUDA(cudaStreamSynchronize(c.stream));
             HMMB_TRY(bw_after_sync(h));
-            if (nt > 0) {
+            // (a repeat can flag further states of the words it runs on — they are held back again; the flags only
+            // grow, at most N per word, so this ends)
+            for (int guard = 0; nt > 0 && guard <= HMMB_MAX_STATES; ++guard) {
                 HMMB_TRY(bw_assign_slots(h));
                 HMMB_CUDA(cudaMemcpyAsync(h->d_redo_in, h->d_redo, (size_t)h->W * sizeof(int32_t), cudaMemcpyDeviceToDevice, c.stream));
-                HMMB_TRY(bw_one_pass(h, h->d_redo_in, eps, max_iter, sync_each, 0));
+                HMMB_TRY(bw_one_pass(h, h->d_redo_in, eps, max_iter, sync_each, 1));
                 HMMB_CUDA(cudaMemcpyAsync(&any, h->d_any, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+                HMMB_CUDA(cudaMemcpyAsync(&nt, h->d_thin_new, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
                 HMMB_CUDA(cudaStreamSynchronize(c.stream));
                 HMMB_TRY(bw_after_sync(h));
             }

@@ -23,6 +23,9 @@
 namespace hmmb {
 
 constexpr int VQ_THREADS = 256;
+#ifndef VQ_MIN_CTAS
+#define VQ_MIN_CTAS 3           // resident CTAs per SM the assign kernel is compiled for: 80 registers, no spills; encode call 0.212 (2) / 0.199 (3) / 0.206 ms (4)
+#endif
 constexpr int VQ_TILE = 512;  // centroids per shared-memory tile: 512 * 12 * 8 B = 48 KB
 constexpr int VQ_D = 12;      // dims 1..12 take part in the distance
 #ifndef VQ_ILP
@@ -137,7 +140,7 @@ constexpr double VQ_TOL_ABS = 1e-37;
 // distances, reduced in shared memory and flushed once per CTA.
 // Shared memory: [tile][12] fp64 centroids, [tile][12] fp32 centroids, [tile] fp32 ||c||^2, accumulators.
 template <int MODE>
-__global__ void __launch_bounds__(VQ_THREADS, 2)
+__global__ void __launch_bounds__(VQ_THREADS, VQ_MIN_CTAS)
 k_vq_assign(const double *__restrict__ X, int64_t F, const double *__restrict__ C, int K,
             int32_t *__restrict__ idx_out, double *__restrict__ dist_out, double *__restrict__ accum,
             int smem_accum, const int *__restrict__ skip, int32_t *__restrict__ worklist, int *__restrict__ n_work) {
@@ -482,7 +485,7 @@ static int vq_launch(int mode, const double *dX, int64_t F, const double *dC, in
     int64_t nbatch = (F + FPB - 1) / FPB;
     if (nbatch == 0) return HMMB_OK;
     // persistent-style grid: a multiple of the SM count, each CTA strides over frame batches
-    int per_sm = smem > 100 * 1024 ? 1 : 2;
+    int per_sm = smem > 100 * 1024 ? 1 : (smem * VQ_MIN_CTAS <= 200 * 1024 ? VQ_MIN_CTAS : 2);
     int64_t grid = (int64_t)c.sm_count * per_sm * (mode == 1 ? 1 : 2);
     if (grid > nbatch) grid = nbatch;
     const unsigned egrid = (unsigned)std::min<int64_t>((int64_t)c.sm_count * 4, (F + 127) / 128);

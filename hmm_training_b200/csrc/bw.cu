@@ -99,10 +99,13 @@ k_score4(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4
 // (score4_lean_run) for models that allow it; 8 warps per CTA, one model per CTA, M <= SCORE4R_MAX_M.
 // Shared memory: [M * 8] double2 (b0, b1), [M * 8] double2 (b2, b3), [M] per-codeword max, [M] support masks.
 constexpr int SCORE4R_WARPS = 8;
+#ifndef SCORE4R_MIN_CTAS
+#define SCORE4R_MIN_CTAS 2
+#endif
 constexpr int SCORE4R_REP = 8;
 constexpr int SCORE4R_MAX_M = 256;  // 64 KB of replicated B^T: three CTAs per SM
 template <bool BIDIAG, bool VECB>
-__global__ void __launch_bounds__(SCORE4R_WARPS * 32, 2)
+__global__ void __launch_bounds__(SCORE4R_WARPS * 32, SCORE4R_MIN_CTAS)
 k_score4r(const Blk *__restrict__ blks, int nblk, int blocks_per_cta, const uint4 *__restrict__ obs_blk,
           const int32_t *__restrict__ len_sorted, const int32_t *__restrict__ order, const double *__restrict__ pi,
           const double *__restrict__ A, const double *__restrict__ Bt, int M, int W, double *__restrict__ ll_out,

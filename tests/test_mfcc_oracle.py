@@ -43,3 +43,31 @@ def test_framing_matches_reference_rule():
     assert [len(f) for f in MO.split_into_frames_with_overlap(np.arange(330))] == [320, 170]
     assert [len(f) for f in MO.split_into_frames_with_overlap(np.arange(10))] == []      # <= 12 samples: dropped
     assert [len(f) for f in MO.split_into_frames_with_overlap(np.arange(13))] == [13]
+
+
+def test_pipeline_matches_transformers_audio_utils():
+    """A third-party cross-check of the restatement (NOT a pin: still no librosa output).  transformers.audio_utils
+    re-implements librosa's conventions — `mel_filter_bank(norm="slaney", mel_scale="slaney")` = `librosa.filters.mel`,
+    `power_to_db` with amin 1e-10 and an 80 dB range, periodic Hann — and its own test-suite holds it to librosa.  The
+    whole per-frame pipeline of the reference's call (one un-centred 320-sample frame, 26 mel bands, ortho DCT-II, 13
+    coefficients; CodeVector/codevector_classes.py:226-250) agrees with it to 1e-7: the difference is librosa's
+    float32 filter weights, which the oracle keeps and transformers does not."""
+    au = pytest.importorskip("transformers.audio_utils")
+    from scipy.fft import dct
+    sr, n = 16000, 320
+    fb_t = au.mel_filter_bank(num_frequency_bins=n // 2 + 1, num_mel_filters=26, min_frequency=0.0, max_frequency=sr / 2,
+                              sampling_rate=sr, norm="slaney", mel_scale="slaney")
+    assert np.abs(MO.mel_filterbank(sr, n, 26) - fb_t.T).max() < 2e-9  # float32 rounding of weights <= 8.7e-3
+    win = au.window_function(n, "hann", periodic=True)
+    rng = np.random.default_rng(0)
+    for k in range(40):
+        y = rng.normal(size=n) * 10 ** rng.uniform(-3, 0)
+        if k == 0:
+            y[:] = 0.0  # silence: every band at the 1e-10 floor
+        if k == 1:
+            y = np.sin(2 * np.pi * 440.0 * np.arange(n) / sr)  # one loud band, the others at the 80 dB floor
+        S = au.spectrogram(y, win, frame_length=n, hop_length=n, fft_length=n, power=2.0, center=False, mel_filters=fb_t,
+                           log_mel="dB", mel_floor=1e-10, reference=1.0, min_value=1e-10, db_range=80.0, dtype=np.float64)
+        want = dct(S[:, 0], type=2, norm="ortho")[:13]
+        got = MO.mfcc_frame(y, sr)
+        assert np.abs(got - want).max() <= 1e-7 * max(1.0, np.abs(want).max())

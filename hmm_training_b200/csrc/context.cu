@@ -359,7 +359,7 @@ int hmmb_shutdown(void) {
 
 const char *hmmb_last_error(void) { return g_err; }
 
-const char *hmmb_version(void) { return "hmmb200 0.1 (sm_100a)"; }
+const char *hmmb_version(void) { return "hmmb200 0.2 (sm_100a)"; }
 
 int hmmb_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *global_mem_bytes) {
     HMMB_TRY(require_init());

@@ -10,6 +10,14 @@
 
 namespace hmmb {
 
+// resident CTAs per SM the generic E-step kernels are compiled for (1 = no register cap)
+#ifndef GEN_FWD_MIN_CTAS
+#define GEN_FWD_MIN_CTAS 1
+#endif
+#ifndef GEN_BWD_MIN_CTAS
+#define GEN_BWD_MIN_CTAS 1
+#endif
+
 // generic path: convert to the canonical symbol width, validate range
 template <typename InT, typename SymT>
 __global__ void k_convert_obs(const InT *__restrict__ obs, int64_t n, SymT *__restrict__ out, int M,
@@ -25,7 +33,7 @@ __global__ void k_convert_obs(const InT *__restrict__ obs, int64_t n, SymT *__re
 // Each group of NP lanes walks the contiguous range of sequences
 // [group * per_group, (group+1) * per_group) of the word-sorted order.
 template <int NP, typename SymT>
-__global__ void __launch_bounds__(BW_THREADS)
+__global__ void __launch_bounds__(BW_THREADS, GEN_FWD_MIN_CTAS)
 k_bw_fwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, const int32_t *__restrict__ len_sorted,
           const int32_t *__restrict__ word_sorted, const int64_t *__restrict__ foff_sorted, int64_t R,
           int64_t per_group, int N, int M, const double *__restrict__ pi, const double *__restrict__ A,
@@ -69,7 +77,7 @@ k_bw_fwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
 // Lane i = state i of its group's sequence; holds row i of A and row i of the xi accumulator.
 // Accumulator layout per word: [pi N][xi N*N][cnt M*N] (fp64 RED into `accum`).
 template <int NP, typename SymT>
-__global__ void __launch_bounds__(BW_THREADS)
+__global__ void __launch_bounds__(BW_THREADS, GEN_BWD_MIN_CTAS)
 k_bw_bwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, const int32_t *__restrict__ len_sorted,
           const int32_t *__restrict__ word_sorted, const int64_t *__restrict__ foff_sorted, int64_t R,
           int64_t per_group, int N, int M, const double *__restrict__ A, const double *__restrict__ Bt,

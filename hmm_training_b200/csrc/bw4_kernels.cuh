@@ -702,6 +702,11 @@ constexpr int BWD4_SPILL_PAD = 2;    // rows of padding in front of the alpha sp
 #endif
 constexpr int BWD_L2_PREFETCH = BWD4_PF;  // steps ahead of use for prefetch.global.L2 of the alpha spill (even)
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// the same under a predicate instead of a branch (ptxas drains the load scoreboards at the first branch of a loop body
+// that has a use of the loaded registers somewhere behind it: bwltr_kernels.cuh)
+__device__ __forceinline__ void prefetch_l2_if(const void *p, bool on) {
+    asm volatile("{\n\t.reg .pred pf;\n\tsetp.ne.u32 pf, %1, 0;\n\t@pf prefetch.global.L2 [%0];\n\t}" ::"l"(p), "r"((unsigned)on));
+}
 constexpr double LEAN_MIN = 0x1p-500;  // the lean backward step needs its three sums above this
 constexpr unsigned LEAN_MIN_HI = (1023u - 500u) << 20;  // high word of LEAN_MIN = 2^-500
 

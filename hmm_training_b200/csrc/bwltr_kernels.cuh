@@ -45,6 +45,9 @@ namespace hmmb {
 #endif
 constexpr int LTR_STAGE_BUFS = HMMB_LTR_TMA ? 2 : 1;
 constexpr int LTR_WARPS = 8;
+#ifndef LTR_SERPENTINE
+#define LTR_SERPENTINE 1
+#endif
 constexpr int LTR_THREADS = LTR_WARPS * 32;
 constexpr int LTR_MAX_SYM = 1 << SYM_BITS;   // codewords share the packed u16 layout of the N = 4 path
 // steps ahead of use for the alpha-hat L2 prefetch (3 / 6 / 12 and an extra L1 prefetch measured
@@ -359,7 +362,12 @@ k_bw_fwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     unsigned selfm, nextm, pmask;
     load_modelL<NS>(A + (size_t)cw.word * NS * NS, piw, as, an, rmax, selfm, nextm, pmask);
     __syncthreads();
-    for (int b = cw.blk_begin + warp; b < cw.blk_end; b += LTR_WARPS) {
+    // blocks are sorted by length: warps take them in serpentine order (0..7, 7..0, ...) so that every warp of the CTA
+    // gets about the same number of steps (plain striding gave warp 0 the longest block of every round: with four
+    // rounds per CTA the last warp idled for a tenth of the kernel at the CTA's final barrier)
+    for (int rb = cw.blk_begin, rnd = 0; rb < cw.blk_end; rb += LTR_WARPS, ++rnd) {
+        const int b = rb + (LTR_SERPENTINE && (rnd & 1) ? LTR_WARPS - 1 - warp : warp);
+        if (b >= cw.blk_end) continue;
         const Blk bk = blks[b];
         int T = lane < bk.nseq ? len_sorted[bk.first + lane] : 0;
         if (T > 0 && flag[bk.first + lane]) T = 0;  // handled by the exact log-space kernel
@@ -579,7 +587,9 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
     int step_parity = 0;
 #endif
 
-    for (int b = cw.blk_begin + warp; b < cw.blk_end; b += LTR_WARPS) {
+    for (int rb = cw.blk_begin, rnd = 0; rb < cw.blk_end; rb += LTR_WARPS, ++rnd) {
+        const int b = rb + (LTR_SERPENTINE && (rnd & 1) ? LTR_WARPS - 1 - warp : warp);
+        if (b >= cw.blk_end) continue;
         const Blk bk = blks[b];
         int T = 0;
         bool apos = false;
@@ -597,6 +607,14 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         const char *sp_line = reinterpret_cast<const char *>(spill + (size_t)bk.spill_base * L::CPR * 32) + (size_t)lane * 128;
         const int nch = (bk.tmax + SPC4 - 1) / SPC4;
         uint4 wnext = __ldg(op + (size_t)(nch - 1) * 32);
+#if !HMMB_LTR_TMA
+        if (T < bk.tmax) {  // this lane sits out the block's first steps (or all of them): its staged row reads as zero
+            double2 *sg = reinterpret_cast<double2 *>(stage_w);
+#pragma unroll
+            for (int p = 0; p < L::CPR; ++p) sg[p] = make_double2(0.0, 0.0);
+            *reinterpret_cast<unsigned *>(stage_w + NS * 8) = 0u;
+        }
+#endif
         // alpha-hat of the step to come.  Every step loads its successor's row into these registers right after its
         // own last use of them, so that the load (an L2 hit thanks to the prefetch below) is in flight during the
         // count flush and the next step's q = A v, instead of being waited for at the first product with q (that
@@ -613,11 +631,16 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
         for (int c = nch - 1; c >= 0; --c) {
             uint4 w = wnext;
             if (c > 0) wnext = __ldg(op + (size_t)(c - 1) * 32);
+            int s = SPC4 - 1;
+            // the top chunk's unused entries are dropped here, not skipped inside the step loop: a `continue` at the
+            // top of the step made ptxas wait for every outstanding scoreboard there (the alpha-hat loads of the
+            // step included: 8 % of the kernel's stall samples sat on that branch)
+            if (c == nch - 1)
+                for (const int s0 = bk.tmax - 1 - c * SPC4; s > s0; --s) S16::pop_back(w);
 #pragma unroll 1
-            for (int s = SPC4 - 1; s >= 0; --s) {
+            for (; s >= 0; --s) {
                 const int t = c * SPC4 + s;
                 const unsigned sym = S16::pop_back(w) & SYM_MASK;
-                if (t >= bk.tmax) continue;  // warp-uniform
                 const bool act = t < T;
 #if HMMB_LTR_TMA
                 // the staging buffer used two steps ago must have been read by the TMA unit
@@ -627,8 +650,17 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
 #else
                 unsigned char *stage = stage_w;
 #endif
-                if (t >= BWDL_L2_PREFETCH && lane * 128 < NS * 8 * 32)  // pull the spill towards L2 well ahead
-                    prefetch_l2(sp_line + (size_t)(t - BWDL_L2_PREFETCH) * (NS * 8 * 32));
+                // pull the spill towards L2 well ahead
+                prefetch_l2_if(sp_line + (size_t)(t - BWDL_L2_PREFETCH) * (NS * 8 * 32), t >= BWDL_L2_PREFETCH && lane * 128 < NS * 8 * 32);
+                // q = A v of the lean step, computed ahead of every branch of the step: ptxas waits for the alpha-hat
+                // loads at the first branch that has a use of them behind it, and that wait (8 % of the kernel's stall
+                // samples when it sat at the top of the step) now overlaps these 2 N products and the sum
+                double q[NS];
+#pragma unroll
+                for (int i = 0; i < NS - 1; ++i) q[i] = fma(sA[NS + i], v[i + 1], fma(sA[i], v[i], tiny));
+                q[NS - 1] = fma(sA[NS - 1], v[NS - 1], tiny);
+                const double qs = tree_sum<NS>(q);
+                asm volatile("" ::"d"(qs));  // keeps ptxas from sinking the products into the branch below
                 if (act) {
                     bool done = false;
                     if (lean_ok && (apos || all_posN<NS>(al))) {
@@ -658,11 +690,6 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                             // (:389-394); xi_t(i,j) = al_i a_ij v_j / norm (:397-410); norm = sum_i al_i q_i.  The denormal
                             // addends keep a finite-but-underflowed log value (barely) positive.  Nothing is committed
                             // (v, Xs, Xn, the TMA reduction) before the three magnitude tests have passed.
-                            double q[NS];
-#pragma unroll
-                            for (int i = 0; i < NS - 1; ++i) q[i] = fma(sA[NS + i], v[i + 1], fma(sA[i], v[i], tiny));
-                            q[NS - 1] = fma(sA[NS - 1], v[NS - 1], tiny);
-                            const double qs = tree_sum<NS>(q);
                             double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
 #pragma unroll
                             for (int i = 0; i < NS; i += 4) {
@@ -726,10 +753,11 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                     if (t == 0) bulk_reduce_add_f64(accw, smem_addr(stage), NS * 8);
 #endif
                 }
-                if (t > 0) {  // (warp-uniform) alpha-hat of step t - 1
+                {  // alpha-hat of step t - 1 (at t = 0: row 0 once more, unused)
+                    const int tp = t > 0 ? t - 1 : 0;
 #pragma unroll
                     for (int q = 0; q < L::CPR; ++q) {
-                        const double2 x = __ldcs(sp + ((size_t)(t - 1) * L::CPR + q) * 32);
+                        const double2 x = __ldcs(sp + ((size_t)tp * L::CPR + q) * 32);
                         al[2 * q] = x.x;
                         al[2 * q + 1] = x.y;
                     }
@@ -755,9 +783,13 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                             atomicAdd(flush_dst + (size_t)sf * NS, *reinterpret_cast<const double *>(row));
                         }
                     } else {
-#pragma unroll 2
+                        // rows of lanes that are not active (yet) hold zeros and codeword 0 (written at the top of the
+                        // block): an instruction is skipped when none of its rows is active — a warp-uniform test —
+                        // and adds + 0.0 for the others.  (Per-lane tests here made the last, partly filled block of a
+                        // word a quarter slower than a full one, and the CTA's other warps waited for it.)
+#pragma unroll
                         for (int k = 0; k < NS; ++k) {
-                            if ((actmask >> (k * FPI + flush_fo)) & 1u) {
+                            if ((actmask >> (k * FPI)) & ((1u << FPI) - 1u)) {
                                 const unsigned char *row = flush_src + (size_t)k * FPI * L::ROWB;
                                 const unsigned sf = *reinterpret_cast<const unsigned *>(row + flush_sym_off);
                                 atomicAdd(flush_dst + (size_t)sf * NS, *reinterpret_cast<const double *>(row));

@@ -632,9 +632,11 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
             uint4 w = wnext;
             if (c > 0) wnext = __ldg(op + (size_t)(c - 1) * 32);
             int s = SPC4 - 1;
-            // the top chunk's unused entries are dropped here, not skipped inside the step loop: a `continue` at the
-            // top of the step made ptxas wait for every outstanding scoreboard there (the alpha-hat loads of the
-            // step included: 8 % of the kernel's stall samples sat on that branch)
+            // the top chunk's unused entries are dropped here, so that the step loop has no skip branch.  (ptxas waits
+            // for the alpha-hat loads of the previous iteration at the first instruction group of the loop body whatever
+            // the first use is — 7-8 % of the kernel's stall samples sit there; moving the first use behind q = A v,
+            // taking the all-positive test from the forward pass, or sending the rows through cp.async staging did not
+            // shorten the step: DESIGN.md section 6.)
             if (c == nch - 1)
                 for (const int s0 = bk.tmax - 1 - c * SPC4; s > s0; --s) S16::pop_back(w);
 #pragma unroll 1
@@ -652,15 +654,6 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
 #endif
                 // pull the spill towards L2 well ahead
                 prefetch_l2_if(sp_line + (size_t)(t - BWDL_L2_PREFETCH) * (NS * 8 * 32), t >= BWDL_L2_PREFETCH && lane * 128 < NS * 8 * 32);
-                // q = A v of the lean step, computed ahead of every branch of the step: ptxas waits for the alpha-hat
-                // loads at the first branch that has a use of them behind it, and that wait (8 % of the kernel's stall
-                // samples when it sat at the top of the step) now overlaps these 2 N products and the sum
-                double q[NS];
-#pragma unroll
-                for (int i = 0; i < NS - 1; ++i) q[i] = fma(sA[NS + i], v[i + 1], fma(sA[i], v[i], tiny));
-                q[NS - 1] = fma(sA[NS - 1], v[NS - 1], tiny);
-                const double qs = tree_sum<NS>(q);
-                asm volatile("" ::"d"(qs));  // keeps ptxas from sinking the products into the branch below
                 if (act) {
                     bool done = false;
                     if (lean_ok && (apos || all_posN<NS>(al))) {
@@ -690,6 +683,11 @@ k_bw_bwdL(const CtaWork *__restrict__ work, const Blk *__restrict__ blks, const 
                             // (:389-394); xi_t(i,j) = al_i a_ij v_j / norm (:397-410); norm = sum_i al_i q_i.  The denormal
                             // addends keep a finite-but-underflowed log value (barely) positive.  Nothing is committed
                             // (v, Xs, Xn, the TMA reduction) before the three magnitude tests have passed.
+                            double q[NS];
+#pragma unroll
+                            for (int i = 0; i < NS - 1; ++i) q[i] = fma(sA[NS + i], v[i + 1], fma(sA[i], v[i], tiny));
+                            q[NS - 1] = fma(sA[NS - 1], v[NS - 1], tiny);
+                            const double qs = tree_sum<NS>(q);
                             double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
 #pragma unroll
                             for (int i = 0; i < NS; i += 4) {

@@ -131,6 +131,32 @@ def case_bw_warm(ref):
     _bw_case(ref, "bw_structural_zeros", corpus, N, M, 4, init=(pi0, A0, B0))
 
 
+def case_bw_ltr(ref):
+    """The left-to-right kernel family (N = 8 / 16, bidiagonal A: BASELINE config 4's model family) pinned to the reference
+    itself, through its warm-start route: pi entered in state 0 only (N = 16) or everywhere (N = 8), ragged lengths
+    including T = 1, more than 32 sequences per word (a full block and a partly filled one), 5 iterations."""
+    rng = np.random.default_rng(16)
+    for N, M, W, S_, tmin, tmax, iters, e0 in ((16, 64, 2, 40, 18, 45, 5, True), (8, 24, 2, 37, 6, 22, 5, False)):
+        corpus = []
+        for w in range(W):
+            seqs = S.clustered_sequences(rng, S_, N=N, M=M, tmin=tmin, tmax=tmax, shift=3 * w, spread=max(2, M // (2 * N)))
+            seqs[0] = seqs[0][:1]
+            corpus.append(seqs)
+        pi0 = np.zeros((W, N)); A0 = np.zeros((W, N, N)); B0 = np.zeros((W, N, M))
+        for w in range(W):
+            if e0:
+                pi0[w, 0] = 1.0
+            else:
+                pi0[w] = rng.dirichlet(np.ones(N))
+            for i in range(N):
+                stay = 0.4 + 0.4 * rng.random()
+                A0[w, i, i] = stay if i + 1 < N else 1.0
+                if i + 1 < N:
+                    A0[w, i, i + 1] = 1.0 - stay
+            B0[w] = rng.dirichlet(np.ones(M) * 2.0, size=N)
+        _bw_case(ref, f"bw_ltr_n{N}_m{M}", corpus, N, M, iters, init=(pi0, A0, B0))
+
+
 def case_vq(ref):
     Raw, Cen = ref.cvc.RawDataMFCC, ref.cvc.CentroidDataMFCC
     X = S.mfcc_mixture(0, 2000, K=64)
@@ -239,7 +265,7 @@ def case_pipeline(ref):
                         pi=np.stack([m.Pi for m in models]), true=np.array(true), pred=np.array(pred))
 
 
-CASES = {"bw_c1": case_bw_c1, "bw_small": case_bw_small, "bw_warm": case_bw_warm,
+CASES = {"bw_c1": case_bw_c1, "bw_small": case_bw_small, "bw_warm": case_bw_warm, "bw_ltr": case_bw_ltr,
          "vq": case_vq, "lbg": case_lbg, "frames": case_frames, "pipeline": case_pipeline}
 
 if __name__ == "__main__":

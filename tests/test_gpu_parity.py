@@ -16,7 +16,7 @@ from oracle import vq_oracle
 pytestmark = pytest.mark.gpu
 
 BW_CASES = ["bw_c1_clustered_s0_it10", "bw_uniform_s1_it3", "bw_clustered_s2_it1", "bw_converge_eps",
-            "bw_warm_n6_m32", "bw_structural_zeros"]
+            "bw_warm_n6_m32", "bw_structural_zeros", "bw_ltr_n16_m64", "bw_ltr_n8_m24"]
 
 
 @pytest.fixture(params=["special", "generic"])
@@ -59,6 +59,24 @@ def test_baum_welch_matches_reference_golden(name, kernel_family):
     pi0, A0, B0 = _init_for(g, W, N, M)
     pi, A, B, hist, iters = engine.bw_fit(g["obs"], g["offsets"], g["word_of_seq"], W, N, M, pi0, A0, B0,
                                           epsilon=float(g["epsilon"]), max_iterations=int(g["max_iterations"]))
+    _check_bw(name, g, pi, A, B, hist, iters, N, M)
+
+
+@pytest.mark.parametrize("name", ["bw_ltr_n16_m64", "bw_ltr_n8_m24"])
+def test_left_to_right_kernels_match_reference_golden(name, monkeypatch):
+    """The two goldens the reference produced for bidiagonal models with 16 / 8 states (oracle/make_golden.py,
+    case_bw_ltr) run on the one-sequence-per-thread left-to-right kernels — asserted, not assumed."""
+    monkeypatch.delenv("HMMB_NO_LTR", raising=False); monkeypatch.delenv("HMMB_FORCE_GENERIC", raising=False)
+    g = load_golden(name)
+    N, M = int(g["N"]), int(g["M"])
+    W = g["A"].shape[0]
+    iters_max = int(g["max_iterations"])
+    with engine.BaumWelch(g["obs"], g["offsets"], g["word_of_seq"], W, N, M) as bw:
+        bw.set_params(g["pi0"], g["A0"], g["B0"])
+        assert bw.kernel_family() == "left_to_right"
+        bw.iterate(iters_max, float(g["epsilon"]), iters_max)
+        pi, A, B = bw.params()
+        hist, iters = bw.history(iters_max)
     _check_bw(name, g, pi, A, B, hist, iters, N, M)
 
 

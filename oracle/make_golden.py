@@ -154,7 +154,23 @@ def case_bw_ltr(ref):
                 if i + 1 < N:
                     A0[w, i, i + 1] = 1.0 - stay
             B0[w] = rng.dirichlet(np.ones(M) * 2.0, size=N)
-        _bw_case(ref, f"bw_ltr_n{N}_m{M}", corpus, N, M, iters, init=(pi0, A0, B0))
+        A, B, pi = _bw_case(ref, f"bw_ltr_n{N}_m{M}", corpus, N, M, iters, init=(pi0, A0, B0))
+        # recognition golden for the same family: held-out utterances (one of a single frame, one the models of word 1
+        # find far less likely than those of word 0) against the trained models and against the initial ones
+        HMM = ref.classes.HMMTrained
+        models = [HMM(N, M, A[w], B[w], pi[w], f"w{w}") for w in range(W)] + \
+                 [HMM(N, M, A0[w], B0[w], pi0[w], f"init{w}") for w in range(W)]
+        test = []
+        for w in range(W):
+            t = S.clustered_sequences(rng, 6, N=N, M=M, tmin=tmin, tmax=3 * tmax, shift=3 * w, spread=max(2, M // (2 * N)))
+            t[0] = t[0][:1]
+            test.append(t)
+        seqs = [s_ for word in test for s_ in word]
+        ll = np.array([[ref.testing.calculate_log_likelihood(s_, m) for m in models] for s_ in seqs])
+        obs, offsets, true_word = S.pack_corpus(test, M)
+        np.savez_compressed(os.path.join(OUT, f"score_ltr_n{N}_m{M}.npz"), obs=obs, offsets=offsets, true_word=true_word,
+                            N=N, M=M, A=np.stack([m.A for m in models]), B=np.stack([m.B for m in models]),
+                            pi=np.stack([m.Pi for m in models]), ll=ll)
 
 
 def case_vq(ref):

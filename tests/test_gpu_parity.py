@@ -303,6 +303,17 @@ def test_scoring_matches_reference_golden(kernel_family):
     assert np.array_equal(arg, O.argmax_first(g["ll"]))
 
 
+@pytest.mark.parametrize("name", ["score_ltr_n16_m64", "score_ltr_n8_m24"])
+def test_scoring_left_to_right_matches_reference_golden(name, kernel_family):
+    """Recognition with bidiagonal 16- / 8-state models against the reference's own numbers (k_scoreL by default, the
+    generic scorer under HMMB_FORCE_GENERIC), -inf pattern included."""
+    g = load_golden(name)
+    ll, arg = engine.score(g["obs"], g["offsets"], int(g["N"]), int(g["M"]), g["pi"], g["A"], g["B"])
+    assert np.array_equal(np.isneginf(ll), np.isneginf(g["ll"]))
+    assert_close(ll, g["ll"], "score ll")
+    assert np.array_equal(arg, O.argmax_first(g["ll"]))
+
+
 @pytest.mark.parametrize("N,M", [(4, 256), (6, 32), (16, 1024), (4, 512), (4, 513), (5, 4096), (32, 64), (1, 7)])
 def test_scoring_matches_oracle_with_structural_zeros(N, M):
     rng = np.random.default_rng(N + M)

@@ -43,6 +43,20 @@ def test_oracle_scoring_matches_reference():
     assert np.array_equal(O.argmax_first(ll), O.argmax_first(g["ll"]))
 
 
+@pytest.mark.parametrize("name", ["score_ltr_n16_m64", "score_ltr_n8_m24"])
+def test_oracle_scoring_matches_reference_left_to_right(name):
+    """Bidiagonal models with 16 / 8 states (trained and initial), utterances up to 3x the training length, one of a
+    single frame; the 16-state initial models enter in state 0 only, so some utterances are impossible (-inf)."""
+    g = load_golden(name)
+    off = g["offsets"]
+    seqs = [g["obs"][off[r]:off[r + 1]].astype(np.int64) for r in range(len(off) - 1)]
+    models = [(g["A"][w], g["B"][w], g["pi"][w]) for w in range(g["A"].shape[0])]
+    ll = O.score_batch(seqs, models)
+    assert np.array_equal(np.isneginf(ll), np.isneginf(g["ll"]))
+    assert_close(ll, g["ll"], "score ll")
+    assert np.array_equal(O.argmax_first(ll), O.argmax_first(g["ll"]))
+
+
 def test_oracle_vq_matches_reference_bit_exact():
     g = load_golden("vq_2000x256")
     idx = vq_oracle.encode(g["X"], g["C"])

@@ -71,3 +71,29 @@ def test_pipeline_matches_transformers_audio_utils():
         want = dct(S[:, 0], type=2, norm="ortho")[:13]
         got = MO.mfcc_frame(y, sr)
         assert np.abs(got - want).max() <= 1e-7 * max(1.0, np.abs(want).max())
+
+
+def test_pipeline_matches_torchaudio():
+    """A second independent implementation of librosa's conventions (still NOT a pin): `torchaudio.transforms.MFCC` with
+    `norm="slaney", mel_scale="slaney"` filters, a periodic Hann window, un-centred frames, power spectrogram, the
+    80 dB `AmplitudeToDB` and the orthonormal DCT-II — torchaudio's own test-suite compares exactly this configuration
+    with librosa.  It builds its filterbank in float32 (5.6e-9 from the oracle's), so the 13 coefficients of the
+    reference's per-frame call (CodeVector/codevector_classes.py:226-250) agree to 4e-7 rather than to rounding."""
+    torch = pytest.importorskip("torch")
+    torchaudio = pytest.importorskip("torchaudio")
+    sr, n = 16000, 320
+    mfcc = torchaudio.transforms.MFCC(sample_rate=sr, n_mfcc=13, dct_type=2, norm="ortho", log_mels=False,
+                                      melkwargs=dict(n_fft=n, win_length=n, hop_length=n, center=False, n_mels=26, f_min=0.0,
+                                                     f_max=sr / 2, power=2.0, norm="slaney", mel_scale="slaney")).double()
+    fb = torchaudio.functional.melscale_fbanks(n // 2 + 1, 0.0, sr / 2, 26, sr, norm="slaney", mel_scale="slaney").double().numpy()
+    assert np.abs(MO.mel_filterbank(sr, n, 26) - fb.T).max() < 2e-8
+    rng = np.random.default_rng(0)
+    for k in range(40):
+        y = rng.normal(size=n) * 10 ** rng.uniform(-3, 0)
+        if k == 0:
+            y[:] = 0.0
+        if k == 1:
+            y = np.sin(2 * np.pi * 440.0 * np.arange(n) / sr)
+        want = mfcc(torch.from_numpy(y)[None])[0, :, 0].numpy()
+        got = MO.mfcc_frame(y, sr)
+        assert np.abs(got - want).max() <= 2e-6 * max(1.0, np.abs(want).max())

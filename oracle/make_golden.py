@@ -96,6 +96,15 @@ def case_bw_small(ref):
     _bw_case(ref, "bw_converge_eps", S.word_corpus(3, 4, 6, M=16, tmin=15, tmax=25), 4, 16, 60, eps=1e-3)
 
 
+def case_bw_empty(ref):
+    """A word without a single sequence next to two ordinary ones: the reference does not refuse it — every log sum is
+    -inf, A and B come back as zeros, pi as NaN (0 / 0 at hmm_training.py:529), the statistic is -inf in every iteration
+    and |(-inf) - (-inf)| = NaN never ends the loop early."""
+    corpus = S.word_corpus(7, 3, 5, M=16, tmin=5, tmax=15)
+    corpus[1] = []
+    _bw_case(ref, "bw_word_without_sequences", corpus, 4, 16, 3)
+
+
 def case_bw_warm(ref):
     """N != 4 through the reference's own warm-start route, and structural zeros."""
     rng = np.random.default_rng(5)
@@ -281,7 +290,7 @@ def case_pipeline(ref):
                         pi=np.stack([m.Pi for m in models]), true=np.array(true), pred=np.array(pred))
 
 
-CASES = {"bw_c1": case_bw_c1, "bw_small": case_bw_small, "bw_warm": case_bw_warm, "bw_ltr": case_bw_ltr,
+CASES = {"bw_c1": case_bw_c1, "bw_small": case_bw_small, "bw_warm": case_bw_warm, "bw_ltr": case_bw_ltr, "bw_empty": case_bw_empty,
          "vq": case_vq, "lbg": case_lbg, "frames": case_frames, "pipeline": case_pipeline}
 
 if __name__ == "__main__":

@@ -1,0 +1,60 @@
+"""Edge shapes through the training / scoring API next to the oracle: a word without sequences, R = 0, one state, one
+codeword, 32 states with a 65536-codeword alphabet, every sequence impossible."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from hmm_training_b200 import engine
+from oracle import hmm_oracle as O
+
+rng = np.random.default_rng(3)
+
+def fit(seqs, wos, W, N, M, init, iters=2):
+    obs = np.concatenate(seqs) if seqs else np.zeros(0, np.int64)
+    off = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.int64)
+    return engine.bw_fit(obs, off, np.asarray(wos, np.int32), W, N, M, *init, max_iterations=iters, epsilon=-1.0)
+
+def rand_init(W, N, M):
+    return (rng.dirichlet(np.ones(N), size=W), rng.dirichlet(np.ones(N), size=(W, N)), rng.dirichlet(np.ones(M), size=(W, N)))
+
+def check(name, seqs, wos, W, N, M, init, iters=2):
+    pi, A, B, hist, it = fit(seqs, wos, W, N, M, init, iters)
+    worst = 0.0
+    for w in range(W):
+        mine = [seqs[r] for r in range(len(seqs)) if wos[r] == w]
+        if not mine:
+            same = np.array_equal(pi[w], init[0][w]) and np.array_equal(A[w], init[1][w]) and np.array_equal(B[w], init[2][w])
+            print(f"  {name}: word {w} has no sequences -> parameters unchanged: {same}, iterations {it[w]}, history {hist[w][:2]}")
+            continue
+        Ao, Bo, pio, ho, _ = O.hmm_training(mine, N=N, M=M, epsilon=-1.0, max_iterations=iters, init=(init[0][w], init[1][w], init[2][w]), return_history=True)
+        for x, y in ((A[w], Ao), (B[w], Bo), (pi[w], pio), (hist[w, :iters], np.array(ho))):
+            with np.errstate(invalid="ignore", divide="ignore"):
+                d = np.abs(x - y) / np.maximum(np.abs(y), 1e-300)
+            d = np.where((x == y) | (np.isnan(x) & np.isnan(y)), 0.0, d)
+            worst = max(worst, float(np.nanmax(d)))
+    print(f"{name}: worst relative difference to the oracle {worst:.2e}")
+
+W, N, M = 3, 4, 16
+seqs = [rng.integers(0, M, size=int(rng.integers(3, 20))) for _ in range(10)]
+wos = [0] * 5 + [2] * 5
+check("word 1 without sequences (N=4)", seqs, wos, W, N, M, rand_init(W, N, M))
+check("word 1 without sequences (N=6)", [s % 12 for s in seqs], wos, W, 6, 12, rand_init(W, 6, 12))
+check("one state, one codeword", [np.zeros(5, np.int64), np.zeros(1, np.int64)], [0, 0], 1, 1, 1, (np.ones((1, 1)), np.ones((1, 1, 1)), np.ones((1, 1, 1))))
+check("two states, two codewords", [rng.integers(0, 2, size=9) for _ in range(4)], [0] * 4, 1, 2, 2, rand_init(1, 2, 2))
+check("32 states, 65536 codewords", [rng.integers(0, 65536, size=12) for _ in range(3)], [0] * 3, 1, 32, 65536, rand_init(1, 32, 65536), iters=1)
+# every sequence impossible: state 0 is the only entry and cannot emit codeword 1
+pi0 = np.array([[1.0, 0, 0, 0]]); A0 = np.array([[[.5, .5, 0, 0], [0, .5, .5, 0], [0, 0, .5, .5], [0, 0, 0, 1.0]]])
+B0 = np.full((1, 4, 3), 1 / 3); B0[0, 0] = [1.0, 0.0, 0.0]
+try:
+    check("every sequence impossible", [np.array([1, 0, 2]), np.array([1, 1])], [0, 0], 1, 4, 3, (pi0, A0, B0))
+except Exception as e:
+    print("every sequence impossible ->", type(e).__name__, e)
+try:
+    out = fit([], [], 2, 4, 16, rand_init(2, 4, 16))
+    print("R = 0: iterations", out[4], "history", out[3][:, :1].ravel())
+except Exception as e:
+    print("R = 0 ->", type(e).__name__, e)
+# what a word without sequences comes back as (the reference: A = 0, B = 0, pi = NaN, -inf statistic every iteration)
+pi, A, B, hist, it = fit(seqs, wos, 3, 4, 16, rand_init(3, 4, 16), iters=3)
+print("word without sequences: A", np.unique(A[1]), "B", np.unique(B[1]), "pi", pi[1], "history", hist[1], "iterations", it[1])
+pi, A, B, hist, it = fit([], [], 1, 4, 16, rand_init(1, 4, 16), iters=3)
+print("R = 0: A", np.unique(A[0]), "B", np.unique(B[0]), "pi", pi[0], "history", hist[0], "iterations", it[0])

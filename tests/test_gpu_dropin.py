@@ -62,6 +62,21 @@ def test_hmm_training_signature_and_prints(tmp_path, monkeypatch):
                                   load_initial_params=False)
 
 
+def test_hmm_training_without_recordings_behaves_like_the_reference():
+    """An empty list of recordings is not an error in the reference: zeros for A and B, NaN for pi, "-inf" statistics, all
+    iterations run (the lines below are its output for this call; tests/golden/bw_word_without_sequences.npz holds the
+    same case as one word of three)."""
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        A, B, pi = hmm_training.hmm_training([], N=4, M=16, epsilon=1e-6, max_iterations=2, show_progress=True,
+                                             load_initial_params=False)
+    assert buf.getvalue().splitlines() == [
+        "Using default initial state probabilities", "Using default transition matrix", "Using default emission matrix",
+        "Iteration 1", "Log-likelihood: -inf, Diff: inf", "Iteration 2", "Log-likelihood: -inf, Diff: inf",
+        "Log-likelihood: -inf, Diff: inf", "Reached maximum iterations (2)"]
+    assert A.shape == (4, 4) and B.shape == (4, 16) and not A.any() and not B.any() and np.isnan(pi).all()
+
+
 def test_warm_start_file_route(tmp_path, monkeypatch):
     """../Data/Eighty-five-percent_20/<word>.json relative to the CWD (hmm_training.py:278)."""
     g = load_golden("bw_warm_n6_m32")

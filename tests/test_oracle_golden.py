@@ -8,7 +8,7 @@ from oracle import hmm_oracle as O
 from oracle import vq_oracle
 
 BW_CASES = ["bw_c1_clustered_s0_it10", "bw_uniform_s1_it3", "bw_clustered_s2_it1", "bw_converge_eps",
-            "bw_warm_n6_m32", "bw_structural_zeros", "bw_ltr_n16_m64", "bw_ltr_n8_m24"]
+            "bw_warm_n6_m32", "bw_structural_zeros", "bw_ltr_n16_m64", "bw_ltr_n8_m24", "bw_word_without_sequences"]
 
 
 @pytest.mark.parametrize("name", BW_CASES)

@@ -156,7 +156,9 @@ def pack_sequences(observations: Sequence[np.ndarray], M: int):
         return np.zeros(0, np.uint8), offsets
     flat = np.concatenate([np.asarray(o).reshape(-1) for o in observations])
     if flat.dtype.kind not in "iu":
-        raise TypeError("observation sequences must be integer codeword indices")
+        # what numpy says when the reference indexes log_b_matrix[state, obs] with a float (hmm_training.py:353)
+        raise IndexError("only integers, slices (`:`), ellipsis (`...`), numpy.newaxis (`None`) and integer or boolean "
+                         "arrays are valid indices")
     if flat.dtype.kind == "i" and flat.size and int(flat.min()) < 0:
         raise IndexError("negative codeword index")
     if flat.size and int(flat.max()) >= M:

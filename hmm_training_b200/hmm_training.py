@@ -139,6 +139,10 @@ def hmm_training(observations: List[np.ndarray], N: int = 4, M: int = 256, epsil
                  load_initial_params: bool = True) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Baum-Welch for one word (HMM/hmm_training.py:265-541); returns (A, B, pi) in that order."""
     pi0, A0, B0 = _initial_params(N, M, word_name, load_initial_params, show_progress)
+    if max_iterations <= 0:
+        # the reference's loop body never runs and its closing print reads a variable the body assigns (:516)
+        raise UnboundLocalError("cannot access local variable 'current_log_likelihood_sum' where it is not associated "
+                                "with a value")
     A, B, pi, hist, iters = hmm_training_batched([observations], N, M, epsilon, max_iterations,
                                                  init=(pi0[None], A0[None], B0[None]))
     it = int(iters[0])

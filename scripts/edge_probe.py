@@ -58,3 +58,38 @@ pi, A, B, hist, it = fit(seqs, wos, 3, 4, 16, rand_init(3, 4, 16), iters=3)
 print("word without sequences: A", np.unique(A[1]), "B", np.unique(B[1]), "pi", pi[1], "history", hist[1], "iterations", it[1])
 pi, A, B, hist, it = fit([], [], 1, 4, 16, rand_init(1, 4, 16), iters=3)
 print("R = 0: A", np.unique(A[0]), "B", np.unique(B[0]), "pi", pi[0], "history", hist[0], "iterations", it[0])
+# recognition against degenerate models (what training returns for a word without sequences, negative / NaN entries):
+# the reference's safe_log maps everything that is not > 0 to -inf, NaN included
+U = [rng.integers(0, 16, size=int(rng.integers(1, 12))) for _ in range(9)]
+obs = np.concatenate(U); off = np.concatenate([[0], np.cumsum([len(u) for u in U])]).astype(np.int64)
+for N in (4, 6, 8, 16):
+    pi_, A_, B_ = rand_init(4, N, 16)
+    if N in (8, 16):  # bidiagonal: the left-to-right scorer
+        A_ = np.zeros((4, N, N))
+        for i in range(N):
+            A_[:, i, i] = 0.6 if i + 1 < N else 1.0
+            if i + 1 < N:
+                A_[:, i, i + 1] = 0.4
+    pi_[1] = np.nan; A_[1] = 0.0; B_[1] = 0.0          # the model of a word without sequences
+    B_[2] = -B_[2]                                       # negative entries
+    pi_[3, 0] = np.nan                                   # one NaN entry
+    ll, arg = engine.score(obs, off, N, 16, pi_, A_, B_)
+    want = O.score_batch(U, [(A_[w], B_[w], pi_[w]) for w in range(4)])
+    with np.errstate(invalid="ignore"):
+        ok = np.array_equal(np.isneginf(ll), np.isneginf(want)) and not np.isnan(ll).any() and \
+            np.allclose(np.where(np.isneginf(want), 0, ll), np.where(np.isneginf(want), 0, want), rtol=1e-9, atol=0)
+    print(f"degenerate models, N = {N}: matches the oracle: {ok}; argmax equal: {np.array_equal(arg, O.argmax_first(want))}")
+    if not ok:
+        print(ll[:3]); print(want[:3])
+# training FROM a degenerate model (warm start from the file of a word that had no sequences; one NaN; negative entries)
+for N in (4, 6, 8):
+    M = 12
+    seqs2 = [rng.integers(0, M, size=int(rng.integers(2, 15))) for _ in range(6)]
+    init = rand_init(3, N, M)
+    init[0][0] = np.nan; init[1][0] = 0.0; init[2][0] = 0.0
+    init[0][1, 0] = np.nan
+    init[2][2, 0] = -init[2][2, 0]
+    try:
+        check(f"degenerate initial models, N = {N}", seqs2 * 3, [0] * 6 + [1] * 6 + [2] * 6, 3, N, M, init, iters=3)
+    except Exception as e:
+        print(f"degenerate initial models, N = {N} ->", type(e).__name__, e)

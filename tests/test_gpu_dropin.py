@@ -60,6 +60,11 @@ def test_hmm_training_signature_and_prints(tmp_path, monkeypatch):
     with pytest.raises(IndexError):  # empty recording: hmm_training.py:376
         hmm_training.hmm_training([np.array([], dtype=np.int64)], N=4, M=16, max_iterations=1, show_progress=False,
                                   load_initial_params=False)
+    with pytest.raises(IndexError, match="only integers"):  # float codewords: numpy's message at :353
+        hmm_training.hmm_training([np.array([1.0, 2.0, 3.0])], N=4, M=16, max_iterations=1, show_progress=False,
+                                  load_initial_params=False)
+    with pytest.raises(UnboundLocalError):  # max_iterations = 0: the closing print at :516 reads an unassigned local
+        hmm_training.hmm_training(corpus[0], N=4, M=16, max_iterations=0, show_progress=False, load_initial_params=False)
 
 
 def test_hmm_training_without_recordings_behaves_like_the_reference():

@@ -275,6 +275,31 @@ def test_left_to_right_kernels_at_config4_shape(monkeypatch):
     assert a[6] == b[6] == (0, 0)  # neither family needed the exact log-space path on this data
 
 
+@pytest.mark.parametrize("N", [4, 6, 8])
+def test_training_from_degenerate_initial_models(N):
+    """Warm start from what the reference saves for a word without sequences (pi = NaN, A = 0, B = 0), from a model with
+    one NaN and from one with negative emission entries: safe_log (hmm_training.py:29-39) turns everything that is not > 0
+    into -inf, so the reference trains on (checked against it on the CPU: the oracle agrees to 1e-14 on exactly these
+    initial models); so must the kernels — no NaN may leak into the other words or the statistics."""
+    rng = np.random.default_rng(70 + N)
+    M, W = 12, 3
+    word = [rng.integers(0, M, size=int(rng.integers(2, 15))) for _ in range(6)]
+    corpus = [word, word, word]
+    obs, offsets, wos = synthetic.pack_corpus(corpus, M)
+    pi0 = rng.dirichlet(np.ones(N), size=W); A0 = rng.dirichlet(np.ones(N), size=(W, N)); B0 = rng.dirichlet(np.ones(M), size=(W, N))
+    pi0[0] = np.nan; A0[0] = 0.0; B0[0] = 0.0
+    pi0[1, 0] = np.nan
+    B0[2, 0] = -B0[2, 0]
+    pi, A, B, hist, iters = engine.bw_fit(obs, offsets, wos, W, N, M, pi0, A0, B0, epsilon=-1.0, max_iterations=3)
+    for w in range(W):
+        Ao, Bo, pio, h, it = O.hmm_training(word, N=N, M=M, epsilon=-1.0, max_iterations=3, init=(pi0[w], A0[w], B0[w]),
+                                            return_history=True)
+        assert it == iters[w]
+        assert_close(hist[w, :it], h, f"N{N} w{w} ll"); assert_close(A[w], Ao, f"N{N} w{w} A")
+        assert_close(B[w], Bo, f"N{N} w{w} B"); assert_close(pi[w], pio, f"N{N} w{w} pi")
+    assert np.isneginf(hist[0, :3]).all() and np.isfinite(hist[1:, :3]).all()
+
+
 def test_baum_welch_is_deterministic():
     g = load_golden("bw_clustered_s2_it1")
     N, M, W = 4, 256, 3
@@ -312,6 +337,35 @@ def test_scoring_left_to_right_matches_reference_golden(name, kernel_family):
     assert np.array_equal(np.isneginf(ll), np.isneginf(g["ll"]))
     assert_close(ll, g["ll"], "score ll")
     assert np.array_equal(arg, O.argmax_first(g["ll"]))
+
+
+@pytest.mark.parametrize("N", [4, 6, 8, 16])
+def test_scoring_against_degenerate_models(N):
+    """What training returns for a word without sequences (pi = NaN, A = 0, B = 0: tests/golden/
+    bw_word_without_sequences.npz), a model with negative emission entries and one with a single NaN: the reference's
+    safe_log (hmm_testing.py:66-68) maps everything that is not > 0 to -inf, NaN included, so such a model scores -inf and
+    is never recognised; every scorer family must say the same and must not let a NaN through."""
+    rng = np.random.default_rng(40 + N)
+    M, W = 16, 4
+    U = [rng.integers(0, M, size=int(rng.integers(1, 12))) for _ in range(9)]
+    obs = np.concatenate(U)
+    off = np.concatenate([[0], np.cumsum([len(u) for u in U])]).astype(np.int64)
+    pi = rng.dirichlet(np.ones(N), size=W); A = rng.dirichlet(np.ones(N), size=(W, N)); B = rng.dirichlet(np.ones(M), size=(W, N))
+    if N in (8, 16):  # bidiagonal: the left-to-right scorer
+        A = np.zeros((W, N, N))
+        for i in range(N):
+            A[:, i, i] = 0.6 if i + 1 < N else 1.0
+            if i + 1 < N:
+                A[:, i, i + 1] = 0.4
+    pi[1] = np.nan; A[1] = 0.0; B[1] = 0.0
+    B[2] = -B[2]
+    pi[3, 0] = np.nan
+    ll, arg = engine.score(obs, off, N, M, pi, A, B)
+    want = O.score_batch(U, [(A[w], B[w], pi[w]) for w in range(W)])
+    assert not np.isnan(ll).any()
+    assert np.array_equal(np.isneginf(ll), np.isneginf(want)) and np.isneginf(ll[:, 1:3]).all()
+    assert_close(ll, want, "score against degenerate models")
+    assert np.array_equal(arg, O.argmax_first(want))
 
 
 @pytest.mark.parametrize("N,M", [(4, 256), (6, 32), (16, 1024), (4, 512), (4, 513), (5, 4096), (32, 64), (1, 7)])

@@ -96,6 +96,8 @@ def createCodeVector(raw_data_vocabulary: List[RawDataMFCC], centroids_quantity:
     print("=" * 50)
 
     X = frames_matrix(raw_data_vocabulary)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        int(np.log2(centroids_quantity))  # (:465) K = 0 -> OverflowError, K < 0 -> ValueError, as in the reference
     C, gens, assign, iters, gdist, hist = engine.lbg_fit(X, centroids_quantity, max_iterations, epsilon, history=True)
     n_gen = len(iters)
     for g in range(1, n_gen + 1):

@@ -93,3 +93,25 @@ for N in (4, 6, 8):
         check(f"degenerate initial models, N = {N}", seqs2 * 3, [0] * 6 + [1] * 6 + [2] * 6, 3, N, M, init, iters=3)
     except Exception as e:
         print(f"degenerate initial models, N = {N} ->", type(e).__name__, e)
+# codebook build on edge inputs next to the C oracle (which matches the reference on every one of them, checked on the CPU)
+from oracle import vq_oracle as V
+from hmm_training_b200 import synthetic as S
+X = S.mfcc_mixture(3, 200, K=8)
+Xn = X.copy(); Xn[3, 4] = np.nan
+for name, Xc, K, mi, eps in (("max_iterations = 0", X, 8, 0, 1e-3), ("max_iterations = 1", X, 8, 1, 1e-3), ("epsilon = 0", X, 8, 20, 0.0),
+                             ("K = 2", X, 2, 20, 1e-3), ("K = 3", X, 3, 20, 1e-3), ("K > frames", X[:5], 16, 20, 1e-3),
+                             ("one frame", X[:1], 4, 20, 1e-3), ("identical frames", np.tile(X[:1], (30, 1)), 8, 20, 1e-3),
+                             ("a NaN coordinate", Xn, 4, 5, 1e-3)):
+    try:
+        got = engine.lbg_fit(Xc, K, mi, eps)
+        want = V.lbg(Xc, K, mi, eps)
+        ok = got[0].shape == want[0].shape and np.allclose(got[0], want[0], rtol=1e-9, atol=0, equal_nan=True) and \
+            np.array_equal(got[2][:len(Xc)], want[2]) and list(got[3]) == list(want[3])
+        print(f"LBG {name}: matches the oracle: {ok}; iterations {list(got[3])} vs {list(want[3])}")
+    except Exception as e:
+        print(f"LBG {name} ->", type(e).__name__, e)
+for K in (0, -1):
+    try:
+        engine.lbg_fit(X, K, 5, 1e-3); print(f"LBG K = {K}: no error")
+    except Exception as e:
+        print(f"LBG K = {K} ->", type(e).__name__, e)

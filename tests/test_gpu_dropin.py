@@ -163,6 +163,13 @@ def test_create_code_vector_side_effects(tmp_path):
     assert all(f.generation == 5 for f in frames)                                # (:479-480)
     summary = json.load(open(tmp_path / "cv" / "training_summary.json"))
     assert summary["total_frames"] == 600 and summary["max_generation"] == 5
+    with contextlib.redirect_stdout(io.StringIO()):
+        with pytest.raises(OverflowError):  # int(np.log2(0)) at :465
+            cvf.createCodeVector(frames[:10], centroids_quantity=0, save_updates=False)
+        with pytest.raises(ValueError):     # int(np.log2(-1))
+            cvf.createCodeVector(frames[:10], centroids_quantity=-1, save_updates=False)
+        with pytest.raises(ValueError, match="No raw data provided"):
+            cvf.createCodeVector([], centroids_quantity=4, save_updates=False)
     reloaded = DataStorage.load_raw_data_mfcc(str(tmp_path / "cv" / "codevector_frames_updated.json"), print_messages=False)
     assert reloaded[7].parent_centroid_id == frames[7].parent_centroid_id and np.array_equal(reloaded[7].mfcc, frames[7].mfcc)
     with pytest.raises(ValueError):

@@ -553,6 +553,35 @@ def test_lbg_no_data():
         engine.lbg_fit(np.zeros((0, 13)), 4)
 
 
+@pytest.mark.parametrize("case", ["max_iterations_0", "max_iterations_1", "epsilon_0", "k2", "k3", "k_above_frames", "one_frame",
+                                  "identical_frames", "nan_coordinate"])
+def test_lbg_edge_inputs_match_oracle(case):
+    """Edge inputs of createCodeVector (CodeVector/codevector_functions.py:442-531).  The C oracle was compared with the
+    reference itself on every one of them (same centroids, assignments and iteration counts: scripts/edge_probe.py has
+    the list); here the device path is held to the oracle — a NaN coordinate included, which the reference carries
+    through its distances and means without complaint."""
+    from oracle import vq_oracle as V
+    X = synthetic.mfcc_mixture(3, 200, K=8)
+    K, mi, eps = 8, 20, 1e-3
+    if case == "max_iterations_0": mi = 0
+    elif case == "max_iterations_1": mi = 1
+    elif case == "epsilon_0": eps = 0.0
+    elif case == "k2": K = 2
+    elif case == "k3": K = 3
+    elif case == "k_above_frames": X, K = X[:5], 16
+    elif case == "one_frame": X, K = X[:1], 4
+    elif case == "identical_frames": X = np.tile(X[:1], (30, 1))
+    elif case == "nan_coordinate":
+        X = X.copy(); X[3, 4] = np.nan; K, mi = 4, 5
+    C, gens, assign, iters, gdist = engine.lbg_fit(X, K, mi, eps)
+    Co, genso, assigno, iterso, gdisto = V.lbg(X, K, mi, eps)
+    assert C.shape == Co.shape and np.array_equal(iters, iterso)
+    assert np.allclose(C, Co, rtol=1e-9, atol=0, equal_nan=True)
+    assert np.array_equal(assign[:len(X)], assigno)
+    for a, b in zip(gens, genso):
+        assert np.allclose(a, b, rtol=1e-9, atol=0, equal_nan=True)
+
+
 def test_large_roundtrip_properties():
     """BASELINE-size properties that need no oracle: rows sum to 1, VQ idempotence
     (a centroid encodes to itself or an identical earlier twin), scoring the training

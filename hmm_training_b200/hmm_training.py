@@ -62,6 +62,9 @@ def get_observations(recordings: List[List[RawDataMFCC]], centroids: List[Centro
         return [np.array([]) for _ in recordings]  # np.array([]) is what the reference builds for an empty recording
     # a recording is a list of RawDataMFCC (the reference's layout) or a packed [T, 13] matrix
     # (codevector_classes.load_mfcc_matrix: the fast loader that skips the per-frame objects)
+    if len(centroids) == 0:
+        # the reference's inner loop does not run and every frame keeps closest_centroid_id = 0 (:103)
+        return [np.zeros(n, dtype=np.int64) if n else np.array([]) for n in lens]
     X = np.concatenate([frames_matrix(r) for r in recordings if len(r)], axis=0)
     C = frames_matrix(centroids)
     idx = engine.vq_encode(X, C).astype(np.int64)

@@ -115,3 +115,19 @@ for K in (0, -1):
         engine.lbg_fit(X, K, 5, 1e-3); print(f"LBG K = {K}: no error")
     except Exception as e:
         print(f"LBG K = {K} ->", type(e).__name__, e)
+# VQ encode on edge inputs next to the C oracle (which matches the reference on all of them but "no centroids")
+X = S.mfcc_mixture(0, 4000, K=8); C = S.random_codebook(1, 256)
+Xn = X.copy(); Xn[2, 5] = np.nan; Xn[3, 0] = np.nan; Xn[4, 1] = np.inf; Xn[5, 2] = -np.inf; Xn[100:200, 7] = np.nan
+Cn = C.copy(); Cn[0, 3] = np.nan; Cn[7] = np.inf; Cn[2, 0] = np.nan
+for name, Xc, Cc in (("NaN / inf in frames", Xn, C), ("NaN / inf in centroids", X, Cn), ("every centroid NaN", X, np.full((4, 13), np.nan)),
+                     ("one centroid", X, C[:1]), ("huge values", X * 1e200, C * 1e200), ("large values (fp32 overflow only)", X * 1e30, C * 1e30),
+                     ("tiny values", X * 1e-200, C * 1e-200), ("small values (fp32 underflow only)", X * 1e-30, C * 1e-30)):
+    try:
+        got = engine.vq_encode(Xc, Cc); want = V.encode(Xc, Cc)
+        print(f"VQ {name}: equal to the oracle: {np.array_equal(got, want)} ({int((got != want).sum())} of {len(want)} differ)")
+    except Exception as e:
+        print(f"VQ {name} ->", type(e).__name__, e)
+try:
+    print("VQ no centroids ->", engine.vq_encode(X[:5], C[:0]))
+except Exception as e:
+    print("VQ no centroids ->", type(e).__name__, e)

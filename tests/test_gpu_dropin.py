@@ -39,6 +39,8 @@ def test_get_observations_matches_reference_golden():
     assert len(obs) == len(recs) and len(obs[1]) == 0
     assert obs[0].dtype == np.int64
     assert np.array_equal(np.concatenate([obs[0], obs[2], obs[3]]), g["idx"])
+    none = hmm_training.get_observations(recs[:2], [])  # no centroids: every frame keeps index 0 (:103)
+    assert len(none) == 2 and len(none[1]) == 0 and none[0].dtype == np.int64 and len(none[0]) == lens[0] and not none[0].any()
 
 
 def test_hmm_training_signature_and_prints(tmp_path, monkeypatch):

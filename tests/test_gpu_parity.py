@@ -514,6 +514,28 @@ def test_vq_encode_matches_oracle(F, K):
     assert np.array_equal(idx, vq_oracle.encode(X, C))
 
 
+@pytest.mark.parametrize("case", ["nan_inf_frames", "nan_inf_centroids", "all_centroids_nan", "one_centroid", "huge", "fp32_overflow",
+                                  "tiny", "fp32_underflow"])
+def test_vq_encode_edge_values_match_oracle(case):
+    """Values the fp32 prefilter cannot represent (overflow, underflow, NaN, inf) must not change a single index: the
+    reference's `distance < min_distance` (hmm_training.py:102-114) never selects a NaN or an infinite distance and keeps
+    index 0 when nothing is selected.  The C oracle was compared with the reference on each of these (scripts/
+    edge_probe.py); the device path is held to the oracle, bit for bit."""
+    from oracle import vq_oracle as V
+    X = synthetic.mfcc_mixture(0, 4000, K=8); C = synthetic.random_codebook(1, 256)
+    if case == "nan_inf_frames":
+        X = X.copy(); X[2, 5] = np.nan; X[3, 0] = np.nan; X[4, 1] = np.inf; X[5, 2] = -np.inf; X[100:200, 7] = np.nan
+    elif case == "nan_inf_centroids":
+        C = C.copy(); C[0, 3] = np.nan; C[7] = np.inf; C[2, 0] = np.nan
+    elif case == "all_centroids_nan": C = np.full((4, 13), np.nan)
+    elif case == "one_centroid": C = C[:1]
+    elif case == "huge": X, C = X * 1e200, C * 1e200
+    elif case == "fp32_overflow": X, C = X * 1e30, C * 1e30
+    elif case == "tiny": X, C = X * 1e-200, C * 1e-200
+    elif case == "fp32_underflow": X, C = X * 1e-30, C * 1e-30
+    assert np.array_equal(engine.vq_encode(X, C), V.encode(X, C))
+
+
 def test_vq_encode_empty():
     assert engine.vq_encode(np.zeros((0, 13)), synthetic.random_codebook(0, 4)).shape == (0,)
 

@@ -83,7 +83,7 @@ k_bw_bwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
           int64_t per_group, int N, int M, const double *__restrict__ A, const double *__restrict__ Bt,
           const double *__restrict__ spill, const double *__restrict__ ll_seq, const int32_t *__restrict__ active,
           double *__restrict__ accum, int64_t astride, uint8_t *__restrict__ flag, int32_t *__restrict__ new_flags) {
-    __shared__ double sStage[BW_WARPS][128];
+    __shared__ __align__(16) double sStage[BW_WARPS][128];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int GPW = 32 / NP;
     const int i = lane % NP, gbase = lane - i;
@@ -151,8 +151,13 @@ k_bw_bwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
                     q = i < N ? 1.0 : 0.0;  // log beta_{T-1} = 0 (:363)
                 } else {
                     const double *sv = stage + par * 32 + gbase;
+                    const double2 *sv2 = reinterpret_cast<const double2 *>(sv);  // (gbase is a multiple of NP >= 4)
 #pragma unroll
-                    for (int jj = 0; jj < NP; ++jj) q = fma(arow[jj], sv[jj], q);
+                    for (int jj = 0; jj < NP; jj += 2) {
+                        const double2 x = sv2[jj / 2];
+                        q = fma(arow[jj], x.x, q);
+                        q = fma(arow[jj + 1], x.y, q);
+                    }
                     if (q == 0.0 && i < N) {
                         bool reach = false;
                         for (int jj = 0; jj < NP; ++jj) reach |= (arow[jj] > 0.0 && sv[jj] > 0.0);
@@ -189,9 +194,16 @@ k_bw_bwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
                 sym = sym_c;
                 if (!last) {
                     u *= r1;
-                    const double *sv = stage + par * 32 + gbase;
+                    // xi_t(i, j) / a_ij = u_i (v_j sc wscale): sc and wscale are powers of two, so scaling u once instead of
+                    // every v_j leaves each product's exact value — and the rounded sum — as it was
+                    const double uf = (u * sc) * wscale;
+                    const double2 *sv2 = reinterpret_cast<const double2 *>(stage + par * 32 + gbase);
 #pragma unroll
-                    for (int jj = 0; jj < NP; ++jj) Xrow[jj] = fma(u, (sv[jj] * sc) * wscale, Xrow[jj]);
+                    for (int jj = 0; jj < NP; jj += 2) {
+                        const double2 x = sv2[jj / 2];
+                        Xrow[jj] = fma(uf, x.x, Xrow[jj]);
+                        Xrow[jj + 1] = fma(uf, x.y, Xrow[jj + 1]);
+                    }
                     if (al > 0.0) seenrow |= vmask;
                 }
                 if (i < N && g > 0.0) {

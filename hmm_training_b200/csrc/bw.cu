@@ -184,7 +184,7 @@ k_scoreG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, c
          const int32_t *__restrict__ order, int64_t U, int64_t per_group, int N, int M, int W,
          const double *__restrict__ pi, const double *__restrict__ A, const double *__restrict__ Bt,
          double *__restrict__ ll_out, int32_t *__restrict__ any_nan) {
-    __shared__ double sStage[BW_WARPS][128];
+    __shared__ __align__(16) double sStage[BW_WARPS][128];
     const int w = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int GPW = 32 / NP;

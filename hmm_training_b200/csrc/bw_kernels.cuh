@@ -39,7 +39,7 @@ k_bw_fwdG(const SymT *__restrict__ obs, const int64_t *__restrict__ off_sorted, 
           int64_t per_group, int N, int M, const double *__restrict__ pi, const double *__restrict__ A,
           const double *__restrict__ Bt, double *__restrict__ spill, double *__restrict__ ll_seq,
           const int32_t *__restrict__ active, uint8_t *__restrict__ flag) {
-    __shared__ double sStage[BW_WARPS][128];
+    __shared__ __align__(16) double sStage[BW_WARPS][128];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int GPW = 32 / NP;
     const int j = lane % NP, gbase = lane - j;

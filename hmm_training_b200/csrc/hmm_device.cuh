@@ -209,13 +209,15 @@ __device__ __forceinline__ double fwdG_run(int T, int Tw, int N, int j, int gbas
                 n = pj;
             } else {
                 const double *prev = stage + par * 32 + gbase;
+                const double2 *prev2 = reinterpret_cast<const double2 *>(prev);  // (gbase is a multiple of NP >= 4; stage is 16-byte aligned)
                 double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;  // four chains: shorter dependency
 #pragma unroll
                 for (int i = 0; i < NP; i += 4) {
-                    n0 = fma(prev[i], acol[i], n0);
-                    n1 = fma(prev[i + 1], acol[i + 1], n1);
-                    n2 = fma(prev[i + 2], acol[i + 2], n2);
-                    n3 = fma(prev[i + 3], acol[i + 3], n3);
+                    const double2 x = prev2[i / 2], y = prev2[i / 2 + 1];
+                    n0 = fma(x.x, acol[i], n0);
+                    n1 = fma(x.y, acol[i + 1], n1);
+                    n2 = fma(y.x, acol[i + 2], n2);
+                    n3 = fma(y.y, acol[i + 3], n3);
                 }
                 n = (n0 + n1) + (n2 + n3);
                 if (n == 0.0) {  // keep "n > 0 <=> structurally reachable"

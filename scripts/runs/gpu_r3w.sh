@@ -1,5 +1,5 @@
 #!/bin/bash
-# fwdG_run: staged alpha read as double2 — A/B on dense models (training) and on the generic scorer, then the generic-heavy tests
+# k_bw_bwdG: the two group reductions of a step in one interleaved shuffle pass — A/B on dense models, then all GPU tests
 mkdir -p gpurun_out
 for v in "" gbase ""; do
   echo "== variant '${v}'"
@@ -7,4 +7,4 @@ for v in "" gbase ""; do
   timeout 300 python scripts/dense_probe.py 2>&1 | tail -2
 done
 unset HMMB_LIB_PATH
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r3v_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r3v_pytest.log
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r3w_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r3w_pytest.log

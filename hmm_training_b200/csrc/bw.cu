@@ -306,13 +306,15 @@ struct PendingPrepare {
     int cta_end[MAX_STAGES] = {};    // CTA work items [.., cta_end) only touch those blocks
 };
 
-// stages of the pipelined first E-step (HMMB_PIPE_STAGES overrides).  Measured on config 3 (8 upload chunks, 1120
-// CTAs): 2 stages 6.8 ms per fit call, 4 stages on two streams 6.1 ms, 8 stages 7.9 ms — a CTA's own duration
-// (~1.6 ms for repack + forward + backward of its 28 blocks) bounds the tail behind the last chunk, and eight
-// stages leave only 280 of the 592 CTA slots busy.
+// stages of the pipelined first E-step (HMMB_PIPE_STAGES overrides).  The tail of a fit call behind the last upload chunk
+// is the last stage's repack + forward + backward, and a stage launches whole work items: with the resident iterations'
+// list (two items per SM, one fat backward CTA each) a stage of config 3 kept a quarter of the SMs busy for the 1.5 ms one
+// item takes, and more stages only made that worse (4 stages 6.1 ms per fit call, 8 stages 8.0).  With the finer list the
+// staged E-step launches from (SeqSet::cta_begin_fine, about eight items per SM) the picture turns: 4 stages 5.75 ms,
+// 8 stages 5.50.
 static int pipeline_stages() {
     const char *e = getenv("HMMB_PIPE_STAGES");
-    return e ? std::max(1, std::min(atoi(e), (int)PendingPrepare::MAX_STAGES)) : 4;
+    return e ? std::max(1, std::min(atoi(e), (int)PendingPrepare::MAX_STAGES)) : 8;
 }
 // left-to-right kernels (config 4, 200 MB of codewords + 131 MB of parameters up): 2 stages 16.1 ms per fit call,
 // 4 stages 14.0 - 14.6, 8 stages 13.85
@@ -338,6 +340,12 @@ struct SeqSet {
     std::vector<int64_t> seq_begin;   // per word [W+1] (sorted order)
     std::vector<int32_t> cta_begin;   // per word [W+1]
     int nblk = 0, ncta = 0;
+    // N = 4, pipelined create only: a finer work list for the staged first E-step.  A stage holds a fraction of the
+    // blocks; cut into the resident iterations' items (about two per SM, sized for the fat backward CTA) it would keep
+    // a quarter of the SMs busy, and the tail behind the last upload chunk would be one such item (~1.5 ms)
+    std::vector<int32_t> cta_begin_fine;
+    int ncta_fine = 0;
+    CtaWork *d_work_fine = nullptr;
     int64_t spill_steps = 0;          // special: sum of tmax over blocks
     int tmax_all = 0;                 // longest sequence
     // device
@@ -353,8 +361,9 @@ struct SeqSet {
         pend.reset();  // waits for the copy stream before the raw buffer goes back to the allocator
         dev_free(d_bad);
         d_bad = nullptr;
-        dev_free(d_obs); dev_free(d_meta); dev_free(d_blks); dev_free(d_work);
+        dev_free(d_obs); dev_free(d_meta); dev_free(d_blks); dev_free(d_work); dev_free(d_work_fine);
         d_obs = d_meta = nullptr; d_off = d_foff = nullptr; d_len = d_word = d_order = nullptr; d_blks = nullptr; d_work = nullptr;
+        d_work_fine = nullptr;
     }
 };
 
@@ -620,7 +629,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     }
 
     std::vector<Blk> blks;
-    std::vector<CtaWork> work;
+    std::vector<CtaWork> work, work_fine;
     blks.reserve((size_t)(R / 32 + nwords + 1));
     int64_t obs_rows = 0;
     if (s.blocked()) {
@@ -665,6 +674,27 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         }
         s.cta_begin[nwords] = (int)work.size();
         s.ncta = (int)work.size();
+        if (s.special4 && defer) {
+            static const int fine_items_per_sm = getenv("HMMB_BW4_STAGE_ITEMS_PER_SM") ? std::max(1, atoi(getenv("HMMB_BW4_STAGE_ITEMS_PER_SM"))) : 8;
+            int bpf = std::max(1, (s.nblk + c.sm_count * fine_items_per_sm - 1) / (c.sm_count * fine_items_per_sm));
+            if (bpf > 1) bpf = (bpf + cta_warps - 1) / cta_warps * cta_warps;
+            if (bpf < bpc) {
+                s.cta_begin_fine.assign(nwords + 1, 0);
+                for (int w = 0; w < nwords; ++w) {
+                    s.cta_begin_fine[w] = (int)work_fine.size();
+                    for (int b = word_blk_begin[w]; b < word_blk_begin[w + 1]; b += bpf) {
+                        CtaWork cw;
+                        cw.word = w;
+                        cw.blk_begin = b;
+                        cw.blk_end = std::min(word_blk_begin[w + 1], b + bpf);
+                        cw.seq_begin = blks[b].first;
+                        work_fine.push_back(cw);
+                    }
+                }
+                s.cta_begin_fine[nwords] = (int)work_fine.size();
+                s.ncta_fine = (int)work_fine.size();
+            }
+        }
     }
 
     const double t1 = now_ms();
@@ -687,6 +717,10 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         if (!blks.empty()) {
             HMMB_TRY(h2d_small(s.d_blks, blks.data(), blks.size() * sizeof(Blk)));
             HMMB_TRY(h2d_small(s.d_work, work.data(), work.size() * sizeof(CtaWork)));
+            if (s.ncta_fine > 0) {
+                HMMB_TRY(dev_alloc_t(&s.d_work_fine, work_fine.size()));
+                HMMB_TRY(h2d_small(s.d_work_fine, work_fine.data(), work_fine.size() * sizeof(CtaWork)));
+            }
         }
         HMMB_TRY(dev_alloc(&s.d_obs, (size_t)std::max<int64_t>(obs_rows, 1) * sizeof(uint4)));
     } else {
@@ -727,13 +761,15 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         p->idx_bytes = idx_bytes;
         p->nstage = std::max(1, std::min<int>(std::min<int>(PendingPrepare::MAX_STAGES, max_stages), up.nchunk));
         int bdone = 0, cdone = 0;
+        const std::vector<CtaWork> &wl = s.ncta_fine > 0 ? work_fine : work;  // the list the staged E-step launches from
+        const int nwl = (int)wl.size();
         for (int j = 0; j < p->nstage; ++j) {
             const int k = (j + 1) * up.nchunk / p->nstage - 1;  // the stage is complete when chunk k has landed
             p->ev_index[j] = k;
             bdone = (j == p->nstage - 1) ? s.nblk : blocks_within(blks, bdone, off_s, len_s, idx_bytes, up.hi[k]);
-            while (cdone < s.ncta && work[cdone].blk_end <= bdone) ++cdone;
+            while (cdone < nwl && wl[cdone].blk_end <= bdone) ++cdone;
             p->blk_end[j] = bdone;
-            p->cta_end[j] = (j == p->nstage - 1) ? s.ncta : cdone;
+            p->cta_end[j] = (j == p->nstage - 1) ? nwl : cdone;
         }
         p->up = std::move(up_owner);
         s.pend = std::move(p);
@@ -811,6 +847,8 @@ struct hmmb_bw {
     double *d_spill = nullptr, *d_llseq = nullptr, *d_accum = nullptr, *d_partials = nullptr;
     double *d_prev = nullptr, *d_hist = nullptr;
     int32_t *d_active = nullptr, *d_iters = nullptr, *d_any = nullptr, *d_cta_begin = nullptr;
+    int32_t *d_cta_begin_fine = nullptr;  // per-word ranges of the staged first E-step's finer work list (SeqSet::cta_begin_fine)
+    bool estep_fine = false;              // the partials of the last E-step are laid out by the finer list
     int32_t *d_bzero = nullptr;   // per word: B has an exact zero (disables the lean backward path)
     bool bidiag = false;          // every word's A is upper-bidiagonal (checked in set_params)
     int64_t *d_seq_begin = nullptr;
@@ -856,7 +894,7 @@ static void bw_release(hmmb_bw *h) {
     dev_free(h->d_raw);
     dev_free(h->d_pi); dev_free(h->d_A); dev_free(h->d_Bt); dev_free(h->d_spill); dev_free(h->d_llseq);
     dev_free(h->d_accum); dev_free(h->d_partials); dev_free(h->d_prev); dev_free(h->d_hist); dev_free(h->d_active);
-    dev_free(h->d_iters); dev_free(h->d_any); dev_free(h->d_cta_begin); dev_free(h->d_seq_begin);
+    dev_free(h->d_iters); dev_free(h->d_any); dev_free(h->d_cta_begin); dev_free(h->d_cta_begin_fine); dev_free(h->d_seq_begin);
     dev_free(h->d_bzero); dev_free(h->d_flag_base); dev_free(h->d_newflags); dev_free(h->d_nexact); dev_free(h->d_exact_scratch);
     dev_free(h->d_thinmask); dev_free(h->d_thin_new); dev_free(h->d_redo); dev_free(h->d_redo_in); dev_free(h->d_slot_of);
 }
@@ -919,8 +957,12 @@ static int bw_finish_create(hmmb_bw *h, int64_t R) {
         // + BWD4_SPILL_PAD rows in front: k_bw_bwd4 loads row t - 2 unconditionally (for t < 2 that is the tail of
         // the previous block, or this padding for the first block; the values are never used)
         spill_bytes = (size_t)(std::max<int64_t>(s.spill_steps, 1) + BWD4_SPILL_PAD) * 64 * sizeof(double2);
-        TRYF(dev_alloc_t(&h->d_partials, (size_t)std::max(s.ncta, 1) * h->pstride));
+        TRYF(dev_alloc_t(&h->d_partials, (size_t)std::max(std::max(s.ncta, s.ncta_fine), 1) * h->pstride));
         TRYF(dev_alloc_t(&h->d_cta_begin, (size_t)W + 1));
+        if (s.ncta_fine > 0) {
+            TRYF(dev_alloc_t(&h->d_cta_begin_fine, (size_t)W + 1));
+            TRYF(h2d_small(h->d_cta_begin_fine, s.cta_begin_fine.data(), (W + 1) * sizeof(int32_t)));
+        }
         TRYF(dev_alloc_t(&h->d_allfull, (size_t)std::max<int64_t>(R, 1)));
         TRYF(h2d_small(h->d_cta_begin, s.cta_begin.data(), (W + 1) * sizeof(int32_t)));
     } else {
@@ -1341,13 +1383,15 @@ static int launch_special_estep(hmmb_bw *h) {
     size_t smem_b = 0;
     const int bwd_threads = 32 * bwd4_warps(h->M, REP, BIDIAG, c.smem_optin, &smem_b);
     HMMB_CUDA(cudaFuncSetAttribute((k_bw_bwd4<BIDIAG, MT, REP>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    // forward + backward of the CTA work items [c0, c1)
+    // forward + backward of the CTA work items [c0, c1) of the staged E-step's list (the finer one where it exists)
+    const CtaWork *stage_work = s.ncta_fine > 0 ? s.d_work_fine : s.d_work;
+    const int stage_ncta = s.ncta_fine > 0 ? s.ncta_fine : s.ncta;
     auto launch_range = [&](int c0, int c1) -> int {
         if (c1 <= c0) return HMMB_OK;
-        HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, (c1 - c0) * FWD4_SPLIT, BW_THREADS, smem_f, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
+        HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, (c1 - c0) * FWD4_SPLIT, BW_THREADS, smem_f, stage_work + c0, s.d_blks, (const uint4 *)s.d_obs,
                     s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->act_cur, h->d_flag,
                     h->d_allfull, FWD4_SPLIT, s.symmask());
-        HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT, REP>), c1 - c0, bwd_threads, smem_b, s.d_work + c0, s.d_blks, (const uint4 *)s.d_obs,
+        HMMB_LAUNCH("bw_backward", (k_bw_bwd4<BIDIAG, MT, REP>), c1 - c0, bwd_threads, smem_b, stage_work + c0, s.d_blks, (const uint4 *)s.d_obs,
                     s.d_len, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->act_cur, h->d_bzero,
                     h->d_allfull, h->d_partials + (size_t)c0 * h->pstride, h->pstride, h->d_flag, h->d_newflags);
         return HMMB_OK;
@@ -1414,10 +1458,12 @@ static int launch_special_estep(hmmb_bw *h) {
         // accumulator contributions are independent of the backward pass); the per-CTA statistic, taken inside
         // k_bw_bwd4 while those sequences still carried their NaN mark, is then retaken
         HMMB_TRY((launch_exact<uint16_t, true>(h)));
-        HMMB_LAUNCH("bw_exact", k_bw_llstat_fix, s.ncta, BW_THREADS, 0, s.d_work, s.d_blks, h->d_llseq, h->act_cur,
+        HMMB_LAUNCH("bw_exact", k_bw_llstat_fix, stage_ncta, BW_THREADS, 0, stage_work, s.d_blks, h->d_llseq, h->act_cur,
                     h->d_flag, h->d_partials, h->pstride, h->M);
+        h->estep_fine = s.ncta_fine > 0;  // k_bw_reduce sums this E-step's partials over the finer list's per-word ranges
         return HMMB_OK;
     }
+    h->estep_fine = false;
     HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta * FWD4_SPLIT, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
                 s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->act_cur, h->d_flag,
                 h->d_allfull, FWD4_SPLIT, s.symmask());
@@ -1647,7 +1693,7 @@ static int bw_one_pass(hmmb_bw *h, int32_t *mask, double eps, int max_iter, int 
     if (!h->estep_reduced) {
         const dim3 rgrid((unsigned)h->W, h->s.special4 ? (unsigned)((h->nacc + RED_EX - 1) / RED_EX) : 1u);
         HMMB_LAUNCH("bw_reduce", k_bw_reduce, rgrid, RED_THREADS, 0, h->s.special4 ? h->d_partials : nullptr, h->pstride,
-                    h->d_cta_begin, h->d_llseq, h->d_seq_begin, h->d_accum, h->astride, h->nacc,
+                    (h->s.special4 && h->estep_fine) ? h->d_cta_begin_fine : h->d_cta_begin, h->d_llseq, h->d_seq_begin, h->d_accum, h->astride, h->nacc,
                     h->d_accum + (size_t)h->W * h->astride, h->rank, h->W, mask);
         if (h->allreduce && h->world > 1) {
             static int pid_ar = -1;

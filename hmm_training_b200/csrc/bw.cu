@@ -322,9 +322,11 @@ static int ltr_pipeline_stages() {
     const char *e = getenv("HMMB_PIPE_STAGES");
     return e ? std::max(1, std::min(atoi(e), (int)PendingPrepare::MAX_STAGES)) : 8;
 }
-static int score_stages() {
+static int score_stages(bool want_ll) {
+    // 1 M utterances x 10 models, pinned buffers (scripts/score_stage_probe.py), 2 / 3 / 4 / 6 / 8 stages: 5.11 / 4.66 / 4.50 /
+    // 4.35 / 4.41 ms with the log-likelihood matrix going back stage by stage, 4.17 / 3.95 / 3.82 / 4.01 / 3.95 ms argmax only
     const char *e = getenv("HMMB_SCORE_STAGES");
-    return e ? std::max(1, std::min(atoi(e), (int)PendingPrepare::MAX_STAGES)) : 3;  // 1M utterances: 6.8 / 6.5 / 6.9 ms at 2 / 3 / 4
+    return e ? std::max(1, std::min(atoi(e), (int)PendingPrepare::MAX_STAGES)) : (want_ll ? 6 : 4);
 }
 
 // ---------------------------------------------------------------- sequence set (shared by BW and scoring)
@@ -1961,7 +1963,7 @@ int hmmb_score(const void *obs, int idx_bytes, int obs_on_device, const int64_t 
     // to the host while the next stage is being scored.
     const bool pipeline = !ltr && nB * sizeof(double) <= (size_t(4) << 20) && !getenv("HMMB_SCORE_NO_PIPELINE");
     HMMB_TRY(seqset_build(s, obs, idx_bytes, obs_on_device, offsets, nullptr, U, 1, N, M, ltr ? LAYOUT_LTR : LAYOUT_AUTO,
-                          pipeline, pipeline ? &upload_models : nullptr, score_stages()));
+                          pipeline, pipeline ? &upload_models : nullptr, score_stages(ll_out != nullptr)));
     if (U == 0) return HMMB_OK;
     if (!models_up) HMMB_TRY(upload_models());
     if (s.pend) {

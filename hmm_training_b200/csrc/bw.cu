@@ -514,10 +514,12 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
                 up.ev[k] = event_get();
                 up.nchunk = k + 1;
             }
-            // as many chunks as the host-side pass below takes (~1 ms per million sequences); the metadata goes
-            // next in the DMA queue, the rest of the codewords behind it
+            // as many chunks as the host-side pass below takes (~0.55 ms per million sequences = one chunk of config 3's
+            // eight); the metadata goes next in the DMA queue, the rest of the codewords behind it.  The first stage of the
+            // pipelined E-step cannot start before the metadata has landed: with two chunks ahead of it (the default
+            // until late in round 2) that was 1.8 ms into the call, with one 1.5 ms — 5.6 -> 5.4 ms per fit call
             const char *fe = getenv("HMMB_UPLOAD_FIRST");
-            HMMB_TRY(up.issue(fe ? std::max(1, atoi(fe)) : std::max(1, nchunk / 4)));
+            HMMB_TRY(up.issue(fe ? std::max(1, atoi(fe)) : std::max(1, nchunk / 8)));
             c.h2d_on_copy = true;
         }
     }

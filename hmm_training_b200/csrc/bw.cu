@@ -348,6 +348,11 @@ struct SeqSet {
     std::vector<int32_t> cta_begin_fine;
     int ncta_fine = 0;
     CtaWork *d_work_fine = nullptr;
+    // N = 4 with the exact item count (seqset_build): the forward kernel keeps a list of its own, items of whole rounds
+    // (it has no per-item state to reduce, cuts every item into FWD4_SPLIT CTAs of 8 warps, and is bound by the HBM
+    // write stream: 296 x 4 CTAs of 26.4 blocks take four block-times each just like 280 x 4 of 28, and 6 % longer in total)
+    int ncta_fwd = 0;
+    CtaWork *d_work_fwd = nullptr;
     int64_t spill_steps = 0;          // special: sum of tmax over blocks
     int tmax_all = 0;                 // longest sequence
     // device
@@ -363,7 +368,8 @@ struct SeqSet {
         pend.reset();  // waits for the copy stream before the raw buffer goes back to the allocator
         dev_free(d_bad);
         d_bad = nullptr;
-        dev_free(d_obs); dev_free(d_meta); dev_free(d_blks); dev_free(d_work); dev_free(d_work_fine);
+        dev_free(d_obs); dev_free(d_meta); dev_free(d_blks); dev_free(d_work); dev_free(d_work_fine); dev_free(d_work_fwd);
+        d_work_fwd = nullptr;
         d_obs = d_meta = nullptr; d_off = d_foff = nullptr; d_len = d_word = d_order = nullptr; d_blks = nullptr; d_work = nullptr;
         d_work_fine = nullptr;
     }
@@ -633,7 +639,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
     }
 
     std::vector<Blk> blks;
-    std::vector<CtaWork> work, work_fine;
+    std::vector<CtaWork> work, work_fine, work_fwd;
     blks.reserve((size_t)(R / 32 + nwords + 1));
     int64_t obs_rows = 0;
     if (s.blocked()) {
@@ -665,8 +671,53 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         int bpc = std::max(1, (s.nblk + target - 1) / target);
         if (bpc > 1 || !s.special4) bpc = (bpc + cta_warps - 1) / cta_warps * cta_warps;
         s.cta_begin.assign(nwords + 1, 0);
+        // N = 4, large inputs: EXACTLY `target` items of (almost) equal size, apportioned to the words by their block counts
+        // (largest remainder).  The fat backward CTA works in rounds of 16 blocks and one CTA occupies an SM, so the kernel
+        // takes waves x rounds-per-item: items rounded up to whole rounds left config 3 with 280 items of 7 rounds on 2 x 148
+        // CTA slots — 14 rounds per SM for 13.2 rounds of work, 16 SMs idle in the second wave.  296 items of 105.6 blocks
+        // are 6 full rounds and one with 10 of the 16 warps busy, which is shorter than a full one.
+        static const bool exact_items = !(getenv("HMMB_BW4_EXACT_ITEMS") && atoi(getenv("HMMB_BW4_EXACT_ITEMS")) == 0);
+        std::vector<int> items_of_word;
+        if (s.special4 && exact_items && (int64_t)s.nblk >= (int64_t)target * cta_warps * 2) {
+            items_of_word.assign(nwords, 0);
+            std::vector<std::pair<double, int>> rem;
+            int64_t assigned = 0;
+            for (int w = 0; w < nwords; ++w) {
+                const int nb = word_blk_begin[w + 1] - word_blk_begin[w];
+                if (nb == 0) continue;
+                const double q = (double)nb * target / s.nblk;
+                items_of_word[w] = std::max(1, (int)q);
+                assigned += items_of_word[w];
+                rem.emplace_back(q - (int)q, w);
+            }
+            std::sort(rem.begin(), rem.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) {
+                return a.first != b.first ? a.first > b.first : a.second < b.second;
+            });
+            for (size_t k = 0; k < rem.size() && assigned < target; ++k, ++assigned) ++items_of_word[rem[k].second];
+        }
         for (int w = 0; w < nwords; ++w) {
             s.cta_begin[w] = (int)work.size();
+            if (!items_of_word.empty()) {
+                for (int b = word_blk_begin[w]; b < word_blk_begin[w + 1]; b += bpc) {  // the forward kernel's list
+                    CtaWork cw;
+                    cw.word = w;
+                    cw.blk_begin = b;
+                    cw.blk_end = std::min(word_blk_begin[w + 1], b + bpc);
+                    cw.seq_begin = blks[b].first;
+                    work_fwd.push_back(cw);
+                }
+                const int b0 = word_blk_begin[w], nb = word_blk_begin[w + 1] - b0, ni = items_of_word[w];
+                for (int i = 0; i < ni; ++i) {
+                    CtaWork cw;
+                    cw.word = w;
+                    cw.blk_begin = b0 + (int)((int64_t)nb * i / ni);
+                    cw.blk_end = b0 + (int)((int64_t)nb * (i + 1) / ni);
+                    if (cw.blk_end == cw.blk_begin) continue;
+                    cw.seq_begin = blks[cw.blk_begin].first;
+                    work.push_back(cw);
+                }
+                continue;
+            }
             for (int b = word_blk_begin[w]; b < word_blk_begin[w + 1]; b += bpc) {
                 CtaWork cw;
                 cw.word = w;
@@ -678,6 +729,7 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
         }
         s.cta_begin[nwords] = (int)work.size();
         s.ncta = (int)work.size();
+        s.ncta_fwd = (int)work_fwd.size();
         if (s.special4 && defer) {
             static const int fine_items_per_sm = getenv("HMMB_BW4_STAGE_ITEMS_PER_SM") ? std::max(1, atoi(getenv("HMMB_BW4_STAGE_ITEMS_PER_SM"))) : 8;
             int bpf = std::max(1, (s.nblk + c.sm_count * fine_items_per_sm - 1) / (c.sm_count * fine_items_per_sm));
@@ -724,6 +776,10 @@ static int seqset_build(SeqSet &s, const void *obs, int idx_bytes, int obs_on_de
             if (s.ncta_fine > 0) {
                 HMMB_TRY(dev_alloc_t(&s.d_work_fine, work_fine.size()));
                 HMMB_TRY(h2d_small(s.d_work_fine, work_fine.data(), work_fine.size() * sizeof(CtaWork)));
+            }
+            if (s.ncta_fwd > 0) {
+                HMMB_TRY(dev_alloc_t(&s.d_work_fwd, work_fwd.size()));
+                HMMB_TRY(h2d_small(s.d_work_fwd, work_fwd.data(), work_fwd.size() * sizeof(CtaWork)));
             }
         }
         HMMB_TRY(dev_alloc(&s.d_obs, (size_t)std::max<int64_t>(obs_rows, 1) * sizeof(uint4)));
@@ -1468,7 +1524,8 @@ static int launch_special_estep(hmmb_bw *h) {
         return HMMB_OK;
     }
     h->estep_fine = false;
-    HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, s.ncta * FWD4_SPLIT, BW_THREADS, smem_f, s.d_work, s.d_blks, (const uint4 *)s.d_obs,
+    HMMB_LAUNCH("bw_forward", k_bw_fwd4<BIDIAG>, (s.ncta_fwd ? s.ncta_fwd : s.ncta) * FWD4_SPLIT, BW_THREADS, smem_f,
+                s.ncta_fwd ? s.d_work_fwd : s.d_work, s.d_blks, (const uint4 *)s.d_obs,
                 s.d_len, h->d_pi, h->d_A, h->d_Bt, h->M, spill4(h), h->d_llseq, h->act_cur, h->d_flag,
                 h->d_allfull, FWD4_SPLIT, s.symmask());
     HMMB_TRY((launch_exact<uint16_t, true>(h)));
